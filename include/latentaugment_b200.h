@@ -1,0 +1,159 @@
+/* latentaugment_b200 -- C ABI of the B200-native LatentAugment hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every pointer
+ * named `d_*` is a DEVICE pointer to fp32 data owned by the caller (the Python host keeps
+ * them in torch tensors); the library allocates nothing on the device except what it carves
+ * out of the caller-provided workspace (and one transient scratch in la_set_latent_bank).
+ * All calls are asynchronous on the given stream unless stated; return value 0 = success,
+ * otherwise an error code whose text is la_last_error().
+ *
+ * Reference interfaces replaced (paths relative to the reference repository root):
+ *   la_engine_create      <- LatentAug.__init__/load_stylegan   augments/utils/util_latent_aug.py:70-121,466-484
+ *                            (+ the parameter contract models/stylegan3/legacy.py:122-203)
+ *   la_set_latent_bank    <- register_buffer('W') from compute_stats('latent')   util_latent_aug.py:140-148,503-563
+ *   la_set_image_bank     <- register_buffer('X') from compute_stats('img')      util_latent_aug.py:150-158
+ *   la_mapping            <- G.mapping(z, None, truncation_psi) in z_to_w / forward_ganrand   util_latent_aug.py:202-205,459-464
+ *   la_synthesis          <- G.synthesis(ws, noise_mode=...) / synthetize         util_latent_aug.py:227,486-489
+ *                            (ops: torch_utils/ops/{conv2d_resample,upfirdn2d,bias_act,fma}.py)
+ *   la_augment            <- LatentAug.forward: the N-step Adam loop, criteria, gate, final synthesis
+ *                                                                                util_latent_aug.py:207-310
+ *   la_pairwise_sqdist    <- l2_loss_vectorized(X, Y, compute_mean=False)         util_latent_aug.py:315-361
+ *   la_nearest_codes      <- (north_star extension) argmin / top-k of that matrix
+ */
+#ifndef LATENTAUGMENT_B200_H
+#define LATENTAUGMENT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LA_MAX_BLOCKS 12          /* resolutions 4 .. 8192 */
+#define LA_MAX_CONV (2 * LA_MAX_BLOCKS)
+#define LA_MAX_MAPPING 8
+#define LA_MAX_STEPS 64
+
+typedef struct la_engine la_engine;
+typedef void* la_stream;          /* cudaStream_t */
+
+enum la_precision {
+    LA_PRECISION_BF16 = 0,        /* one bf16 tensor-core pass, fp32 accumulate (tolerance: rel-L2 1e-2) */
+    LA_PRECISION_FP32_PARITY = 1  /* split-bf16 (hi/lo) operands, 3 passes, fp32 accumulate (rel-L2 1e-3) */
+};
+
+enum la_noise_mode { LA_NOISE_NONE = 0, LA_NOISE_CONST = 1, LA_NOISE_RANDOM = 2 };
+
+/* One 3x3 modulated-conv layer: names per legacy.py:178-195. */
+typedef struct la_conv_params {
+    const float* d_weight;         /* [cout, cin, 3, 3] */
+    const float* d_bias;           /* [cout] */
+    const float* d_noise_const;    /* [res, res] */
+    float noise_strength;
+    const float* d_affine_weight;  /* [cin, w_dim] */
+    const float* d_affine_bias;    /* [cin] */
+} la_conv_params;
+
+/* One toRGB layer: legacy.py:196-199. */
+typedef struct la_torgb_params {
+    const float* d_weight;         /* [img_channels, cin, 1, 1] */
+    const float* d_bias;           /* [img_channels] */
+    const float* d_affine_weight;  /* [cin, w_dim] */
+    const float* d_affine_bias;    /* [cin] */
+} la_torgb_params;
+
+/* StyleGAN2 generator (skip architecture) description; constructor kwargs per legacy.py:122-144. */
+typedef struct la_generator_desc {
+    int img_resolution;            /* power of two >= 8 */
+    int img_channels;              /* 1..3 */
+    int w_dim, z_dim;
+    int num_blocks;                /* log2(res) - 1 */
+    int channels[LA_MAX_BLOCKS];   /* feature maps of block 4, 8, ... (multiples of 64) */
+    float conv_clamp;              /* < 0: no clamp */
+    const float* d_const;          /* synthesis.b4.const [channels[0], 4, 4] */
+    const float* d_resample_filter;/* [4, 4] (setup_filter([1,3,3,1])) */
+    la_conv_params conv[LA_MAX_CONV];     /* b4.conv1, b8.conv0, b8.conv1, b16.conv0, ... (2*num_blocks - 1) */
+    la_torgb_params torgb[LA_MAX_BLOCKS]; /* b4.torgb, b8.torgb, ... */
+    int mapping_layers;            /* 0: no mapping network given */
+    float mapping_lr_multiplier;
+    const float* d_mapping_weight[LA_MAX_MAPPING];   /* fc{i}.weight [out, in] */
+    const float* d_mapping_bias[LA_MAX_MAPPING];
+    const float* d_w_avg;          /* [w_dim] */
+} la_generator_desc;
+
+/* Options of one augmentation call: the opt.* fields LatentAug.forward reads
+ * (augments/latent_aug.py:45-98, util_latent_aug.py:84-112). */
+typedef struct la_augment_options {
+    int num_steps;                 /* opt_num_epochs */
+    float lr;                      /* opt_lr */
+    float w_latent, w_pix;         /* criteria weights; perceptual / discriminator terms must be 0 here */
+    int soft_aug;                  /* 0: hard_aug, 1: smooth_aug */
+    float alpha;
+    int final_noise_mode;          /* la_noise_mode of the last synthesis (reference default: random) */
+    int n_modalities;              /* number of leading image channels the pixel criterion covers */
+} la_augment_options;
+
+const char* la_last_error(void);
+int la_version(void);
+
+/* Bytes of device workspace an engine of this shape needs. */
+int la_engine_workspace_bytes(const la_generator_desc* g, int batch, int precision, size_t* bytes);
+
+/* Builds an engine over caller-owned workspace.  Weight preparation kernels are enqueued on
+ * `stream`; the generator parameter tensors must stay alive for the engine's lifetime (biases,
+ * noise constants are read in place). */
+int la_engine_create(const la_generator_desc* g, int batch, int precision, void* d_workspace, size_t workspace_bytes,
+                     la_stream stream, la_engine** out);
+void la_engine_destroy(la_engine* e);
+
+/* Real-code bank W [M, num_ws, w_dim] and real-image bank X [M, C, res, res] in [-1, 1].
+ * Only their moments are kept; the tensors are not referenced afterwards. */
+int la_set_latent_bank(la_engine* e, const float* d_W, int M, la_stream stream);
+int la_set_image_bank(la_engine* e, const float* d_X, int M, la_stream stream);
+
+/* w[n, :] = mapping(z[n, :]) with truncation; n <= engine batch.  One row per sample (the
+ * reference broadcasts it to num_ws rows). */
+int la_mapping(la_engine* e, const float* d_z, int n, float truncation_psi, float* d_w, la_stream stream);
+
+/* img [batch, C, res, res] (NCHW fp32) = G.synthesis(ws).  ws element (n, i, k) is read at
+ * d_ws[n*stride_n + i*stride_i + k] (stride_i = 0 broadcasts one row per sample).
+ * noise: LA_NOISE_CONST uses the layers' noise_const; LA_NOISE_RANDOM reads unit normal noise
+ * from d_noise, laid out layer after layer as [batch, res_l, res_l] (conv order of la_generator_desc). */
+int la_synthesis(la_engine* e, const float* d_ws, long long stride_n, long long stride_i, int noise_mode,
+                 const float* d_noise, float* d_img, la_stream stream);
+size_t la_noise_floats(const la_engine* e);
+
+/* The hot path.  d_w0 [batch, w_dim] initial codes; outputs: d_img [batch, C, res, res],
+ * d_w_aug [batch, w_dim] (one row per sample), d_loss_log [num_steps, 4] = (latent, pixel, total, 0)
+ * or NULL.  d_final_noise as in la_synthesis (may be NULL unless final_noise_mode == RANDOM). */
+int la_augment(la_engine* e, const float* d_w0, const la_augment_options* opt, const float* d_final_noise, float* d_img,
+               float* d_w_aug, float* d_loss_log, la_stream stream);
+
+/* D[j, i] = |Y_j|^2 + |X_i|^2 - 2 <Y_j, X_i>  ([bank, batch] orientation, fp32, the reference's
+ * association order).  X [n, K], Y [m, K]. */
+int la_pairwise_sqdist(const float* d_X, int n, const float* d_Y, int m, int K, float* d_D, la_stream stream);
+
+/* k nearest bank rows per query under that distance, ties to the lowest index.  Candidates are
+ * selected by a bf16 tensor-core GEMM with a fused per-tile top-k and re-ranked in exact fp32.
+ * d_bank_bf16 / d_bank_sqnorm come from la_bank_prepare.  index_offset is added to the returned
+ * indices (bank shards).  Outputs: d_dist [n, k] fp32, d_idx [n, k] int64. */
+int la_bank_prepare(const float* d_Y, int m, int K, void* d_bank_bf16, float* d_bank_sqnorm, la_stream stream);
+int la_nearest_codes(const float* d_X, int n, const float* d_Y, const void* d_bank_bf16, const float* d_bank_sqnorm, int m, int K,
+                     int k, long long index_offset, void* d_workspace, size_t workspace_bytes, float* d_dist, long long* d_idx,
+                     la_stream stream);
+int la_nearest_codes_workspace_bytes(int n, int m, int K, int k, size_t* bytes);
+/* Merges per-shard (dist, idx) lists [shards, n, k] into the global k best. */
+int la_merge_topk(const float* d_dist, const long long* d_idx, int shards, int n, int k, float* d_out_dist, long long* d_out_idx,
+                  la_stream stream);
+
+/* Test hooks: run every tap-GEMM of the engine once through the SIMT twin as well and report
+ * the largest deviation (debug cross-check of the tensor-core path; not a product path). */
+int la_debug_set_simt(la_engine* e, int use_simt);
+int la_debug_check(la_engine* e, la_stream stream);   /* synchronises; non-zero if a pipeline wait timed out */
+long long la_debug_launch_count(const la_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,259 @@
+// Distance-to-bank: exact pairwise squared L2 (reference l2_loss_vectorized, compute_mean=False,
+// augments/utils/util_latent_aug.py:315-361) and the nearest-code / top-k extension
+// (SURVEY.md F3): tensor-core candidate selection (tap-GEMM with the fused top-k epilogue,
+// split-bf16 operands) followed by an exact fp32 re-rank in the reference's association order.
+#include <cuda_bf16.h>
+#include <math.h>
+#include <string.h>
+
+#include <string>
+
+#include "../../include/latentaugment_b200.h"
+#include "tapgemm.cuh"
+
+using namespace la;
+
+int la_fail_msg(int code, const char* msg);   // engine.cu
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+constexpr int kCand = 8;          // candidates kept per (query, 256-code tile)
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// rows -> bf16 hi / lo planes + |row|^2 (fp64 accumulate, rounded once to fp32).  Warp per row.
+__global__ void split_rows_kernel(const float* __restrict__ src, int rows, int rows_padded, int K, bf16* hi, bf16* lo, float* sqnorm) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= rows_padded) return;
+    double acc = 0.0;
+    for (int k = lane; k < K; k += 32) {
+        const float v = r < rows ? src[static_cast<long long>(r) * K + k] : 0.f;
+        const bf16 h = __float2bfloat16_rn(v);
+        hi[static_cast<long long>(r) * K + k] = h;
+        lo[static_cast<long long>(r) * K + k] = __float2bfloat16_rn(v - __bfloat162float(h));
+        acc += static_cast<double>(v) * v;
+    }
+    acc = warp_sum_d(acc);
+    if (lane == 0 && r < rows && sqnorm) sqnorm[r] = static_cast<float>(acc);
+}
+
+// D[j, i] = (|Y_j|^2 + |X_i|^2) - 2 <Y_j, X_i>; warp per (j, i); dot in fp64, one rounding.
+__global__ void pairwise_kernel(const float* __restrict__ X, int n, const float* __restrict__ Y, int m, int K, float* D) {
+    const long long pair = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (pair >= static_cast<long long>(m) * n) return;
+    const int j = static_cast<int>(pair / n), i = static_cast<int>(pair % n);
+    const float* x = X + static_cast<long long>(i) * K;
+    const float* y = Y + static_cast<long long>(j) * K;
+    double xx = 0.0, yy = 0.0, yx = 0.0;
+    for (int k = lane; k < K; k += 32) {
+        const double a = x[k], b = y[k];
+        xx += a * a; yy += b * b; yx += a * b;
+    }
+    xx = warp_sum_d(xx); yy = warp_sum_d(yy); yx = warp_sum_d(yx);
+    if (lane == 0) D[pair] = (static_cast<float>(yy) + static_cast<float>(xx)) - 2.f * static_cast<float>(yx);
+}
+
+// Exact re-rank: warp per query over its n_blocks*kCand candidates; keeps the k smallest
+// (distance, index) pairs, ties to the lowest index.
+__global__ void rerank_kernel(const float* __restrict__ X, const float* __restrict__ xx, const float* __restrict__ Y,
+                              const float* __restrict__ yy, int n, int K, const int* __restrict__ cand_idx, int ncand, int k,
+                              long long index_offset, float* out_dist, long long* out_idx) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= n) return;
+    float bd[8];
+    int bi[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) { bd[t] = __int_as_float(0x7f800000); bi[t] = 0x7fffffff; }
+    const float* x = X + static_cast<long long>(i) * K;
+    const float xi = xx[i];
+    for (int c = 0; c < ncand; ++c) {
+        const int j = cand_idx[static_cast<long long>(i) * ncand + c];
+        if (j < 0) continue;
+        const float* y = Y + static_cast<long long>(j) * K;
+        double dot = 0.0;
+        for (int kk = lane; kk < K; kk += 32) dot += static_cast<double>(x[kk]) * y[kk];
+        dot = warp_sum_d(dot);
+        float d = (yy[j] + xi) - 2.f * static_cast<float>(dot);
+        int id = j;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            if (d < bd[t] || (d == bd[t] && id < bi[t])) {
+                const float td = bd[t]; const int ti = bi[t];
+                bd[t] = d; bi[t] = id; d = td; id = ti;
+            }
+        }
+    }
+    if (lane == 0)
+        for (int t = 0; t < k; ++t) {
+            out_dist[static_cast<long long>(i) * k + t] = bd[t];
+            out_idx[static_cast<long long>(i) * k + t] = bi[t] == 0x7fffffff ? -1 : bi[t] + index_offset;
+        }
+}
+
+// merge [shards, n, k] sorted lists -> k best per query (thread per query)
+__global__ void merge_topk_kernel(const float* __restrict__ dist, const long long* __restrict__ idx, int shards, int n, int k,
+                                  float* out_dist, long long* out_idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float bd[8];
+    long long bi[8];
+    for (int t = 0; t < 8; ++t) { bd[t] = __int_as_float(0x7f800000); bi[t] = 0x7fffffffffffffffLL; }
+    for (int s = 0; s < shards; ++s)
+        for (int t = 0; t < k; ++t) {
+            float d = dist[(static_cast<long long>(s) * n + i) * k + t];
+            long long id = idx[(static_cast<long long>(s) * n + i) * k + t];
+            if (id < 0) continue;
+            for (int u = 0; u < 8; ++u)
+                if (d < bd[u] || (d == bd[u] && id < bi[u])) {
+                    const float td = bd[u]; const long long ti = bi[u];
+                    bd[u] = d; bi[u] = id; d = td; id = ti;
+                }
+        }
+    for (int t = 0; t < k; ++t) {
+        out_dist[static_cast<long long>(i) * k + t] = bd[t];
+        out_idx[static_cast<long long>(i) * k + t] = bi[t] == 0x7fffffffffffffffLL ? -1 : bi[t];
+    }
+}
+
+struct NearestLayout {
+    int Hq, rows_padded, n_blocks, ncand;
+    size_t off_xhi, off_xlo, off_xx, off_cs, off_ci, total;
+};
+NearestLayout nearest_layout(int n, int m, int K) {
+    NearestLayout L;
+    L.Hq = (n + 15) / 16;
+    L.Hq = (L.Hq + 7) / 8 * 8;                 // whole 8x16 query tiles
+    L.rows_padded = L.Hq * 16;
+    L.n_blocks = (m + 255) / 256;
+    L.ncand = L.n_blocks * kCand;
+    size_t off = 0;
+    auto take = [&](size_t b) { off = (off + 1023) & ~size_t(1023); size_t o = off; off += b; return o; };
+    L.off_xhi = take(static_cast<size_t>(L.rows_padded) * K * 2);
+    L.off_xlo = take(static_cast<size_t>(L.rows_padded) * K * 2);
+    L.off_xx = take(static_cast<size_t>(L.rows_padded) * 4);
+    L.off_cs = take(static_cast<size_t>(n) * L.ncand * 4);
+    L.off_ci = take(static_cast<size_t>(n) * L.ncand * 4);
+    L.total = off + 1024;
+    return L;
+}
+
+}  // namespace
+
+#define DCU(x)                                                                           \
+    do {                                                                                 \
+        cudaError_t e_ = (x);                                                            \
+        if (e_ != cudaSuccess) return la_fail_msg(static_cast<int>(e_), cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" {
+
+__attribute__((visibility("default")))
+int la_pairwise_sqdist(const float* d_X, int n, const float* d_Y, int m, int K, float* d_D, la_stream stream) {
+    if (!d_X || !d_Y || !d_D || n < 1 || m < 1 || K < 1) return la_fail_msg(-2, "bad arguments");
+    const long long pairs = static_cast<long long>(m) * n;
+    pairwise_kernel<<<static_cast<unsigned>((pairs + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_X, n, d_Y, m, K, d_D);
+    DCU(cudaGetLastError());
+    return 0;
+}
+
+__attribute__((visibility("default")))
+int la_bank_prepare(const float* d_Y, int m, int K, void* d_bank_bf16, float* d_bank_sqnorm, la_stream stream) {
+    if (!d_Y || !d_bank_bf16 || !d_bank_sqnorm || m < 1 || K < 64 || K % 64) return la_fail_msg(-2, "bad arguments (K must be a multiple of 64)");
+    bf16* hi = static_cast<bf16*>(d_bank_bf16);
+    bf16* lo = hi + static_cast<size_t>(m) * K;
+    split_rows_kernel<<<(m + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_Y, m, m, K, hi, lo, d_bank_sqnorm);
+    DCU(cudaGetLastError());
+    return 0;
+}
+
+__attribute__((visibility("default")))
+int la_nearest_codes_workspace_bytes(int n, int m, int K, int k, size_t* bytes) {
+    if (!bytes || n < 1 || m < 1 || K % 64 || k < 1 || k > 8) return la_fail_msg(-2, "bad arguments (k <= 8, K % 64 == 0)");
+    *bytes = nearest_layout(n, m, K).total;
+    return 0;
+}
+
+__attribute__((visibility("default")))
+int la_nearest_codes(const float* d_X, int n, const float* d_Y, const void* d_bank_bf16, const float* d_bank_sqnorm, int m, int K, int k,
+                     long long index_offset, void* d_workspace, size_t workspace_bytes, float* d_dist, long long* d_idx,
+                     la_stream stream) {
+    if (!d_X || !d_Y || !d_bank_bf16 || !d_bank_sqnorm || !d_workspace || !d_dist || !d_idx) return la_fail_msg(-2, "bad arguments");
+    if (k < 1 || k > 8 || K % 64 || K < 64) return la_fail_msg(-2, "k must be 1..8 and K a multiple of 64");
+    const NearestLayout L = nearest_layout(n, m, K);
+    if (workspace_bytes < L.total) return la_fail_msg(-2, "nearest-codes workspace too small");
+    if (reinterpret_cast<uintptr_t>(d_workspace) & 1023) return la_fail_msg(-2, "workspace must be 1024-byte aligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    char* ws = static_cast<char*>(d_workspace);
+    bf16* xhi = reinterpret_cast<bf16*>(ws + L.off_xhi);
+    bf16* xlo = reinterpret_cast<bf16*>(ws + L.off_xlo);
+    float* xx = reinterpret_cast<float*>(ws + L.off_xx);
+    float* cs = reinterpret_cast<float*>(ws + L.off_cs);
+    int* ci = reinterpret_cast<int*>(ws + L.off_ci);
+    split_rows_kernel<<<(L.rows_padded + 7) / 8, 256, 0, s>>>(d_X, n, L.rows_padded, K, xhi, xlo, xx);
+    DCU(cudaGetLastError());
+
+    int dev = 0, sms = 0;
+    DCU(cudaGetDevice(&dev));
+    DCU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    TapGemmParams P;
+    memset(&P, 0, sizeof P);
+    P.th = 8; P.tw = 16; P.nb = 1;
+    P.tiles_h = L.Hq / 8; P.tiles_w = 1; P.tiles_n = 1;
+    P.vh = L.Hq; P.vw = 16; P.batch = 1; P.nprob = 1;
+    P.m_tiles = P.tiles_h;
+    P.kchunks = K / 64;
+    P.n_blocks = L.n_blocks; P.n_total = L.n_blocks * 256;
+    P.epilogue = kEpiTopK;
+    P.OH = L.Hq; P.OW = 16; P.osy = P.osx = 1;
+    P.code_sqnorm = d_bank_sqnorm; P.n_codes = m; P.n_queries = n; P.topk = kCand;
+    P.cand_score = cs; P.cand_idx = ci;
+    P.taps[0] = Tap{0, 0, 0, 0};      // x_hi . y_hi
+    P.taps[1] = Tap{0, 0, 0, 1};      // x_lo . y_hi
+    P.taps[2] = Tap{0, 0, 1, 0};      // x_hi . y_lo
+    P.prob[0].tap_begin = 0; P.prob[0].ntaps = 3;
+    uint64_t adims[4] = {static_cast<uint64_t>(K), 16, static_cast<uint64_t>(L.Hq), 1};
+    uint64_t astr[3] = {static_cast<uint64_t>(K) * 2, static_cast<uint64_t>(K) * 32, static_cast<uint64_t>(K) * 32 * L.Hq};
+    uint32_t abox[4] = {64, 16, 8, 1};
+    if (encode_tmap_bf16(&P.a_map[0], xhi, 4, adims, astr, abox) || encode_tmap_bf16(&P.a_map[1], xlo, 4, adims, astr, abox))
+        return la_fail_msg(-5, "tensor map encoding failed (queries)");
+    uint64_t bdims[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(m), 2};
+    uint64_t bstr[2] = {static_cast<uint64_t>(K) * 2, static_cast<uint64_t>(K) * 2 * m};
+    uint32_t bbox[3] = {64, 256, 1};
+    if (encode_tmap_bf16(&P.b_map, d_bank_bf16, 3, bdims, bstr, bbox)) return la_fail_msg(-5, "tensor map encoding failed (bank)");
+    static int* err_flag = nullptr;
+    if (!err_flag) { DCU(cudaMalloc(&err_flag, sizeof(int))); DCU(cudaMemset(err_flag, 0, sizeof(int))); }
+    P.err_flag = err_flag;
+    if (getenv("LA_DEBUG_SIMT_DIST")) {
+        TapSimtOperands ops{};
+        ops.a_ptrs[0] = xhi; ops.a_ptrs[1] = xlo;
+        ops.a_sw = K; ops.a_sh = 16LL * K; ops.a_sn = 16LL * K * L.Hq; ops.a_w = 16; ops.a_h = L.Hq;
+        ops.w = d_bank_bf16;
+        int r = launch_tapgemm_simt(P, ops, s);
+        if (r) return la_fail_msg(r, "launch_tapgemm_simt failed");
+    } else {
+        int r = launch_tapgemm(P, sms, s);
+        if (r) return la_fail_msg(r, "launch_tapgemm failed");
+    }
+    rerank_kernel<<<(n + 7) / 8, 256, 0, s>>>(d_X, xx, d_Y, d_bank_sqnorm, n, K, ci, L.ncand, k, index_offset, d_dist, d_idx);
+    DCU(cudaGetLastError());
+    return 0;
+}
+
+__attribute__((visibility("default")))
+int la_merge_topk(const float* d_dist, const long long* d_idx, int shards, int n, int k, float* d_out_dist, long long* d_out_idx,
+                  la_stream stream) {
+    if (!d_dist || !d_idx || !d_out_dist || !d_out_idx || shards < 1 || n < 1 || k < 1 || k > 8) return la_fail_msg(-2, "bad arguments");
+    merge_topk_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(d_dist, d_idx, shards, n, k, d_out_dist, d_out_idx);
+    DCU(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+// Tap-GEMM: the one tensor-core kernel of the synthesis path (forward and backward-to-w).
+//
+//   acc[pixel, col] = sum_{t in taps} sum_{k < K}  A_{src_t}[pixel + (dy_t, dx_t), k] * Wstack[widx_t][col][k]
+//
+// A_* are NHWC bf16 activation tensors (each described by one 4-D TMA tensor map), Wstack a
+// stack of K-major [N x K] bf16 matrices.  Every 3x3 modulated convolution of the generator,
+// its data gradient, the four sub-pixel phases of the x2 up-sampling convolution (transposed
+// conv + 4x4 FIR folded into per-phase 3x3 weights) and the gradient of that layer are
+// instances of this contraction; split-bf16 ("fp32-parity") precision is three taps per
+// geometric tap: (A_hi,W_hi) + (A_lo,W_hi) + (A_hi,W_lo).   See DESIGN.md §3.
+//
+// M tile = nb images x th rows x tw cols (<= 128 pixels) fetched by one TMA box load per
+// (tap, 64-channel chunk); zero padding is TMA out-of-bounds fill.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace la {
+
+constexpr int kMaxTaps = 108;     // 36 geometric taps x 3 split-precision passes
+constexpr int kMaxProblems = 4;   // 4 sub-pixel phases
+constexpr int kMaxAMaps = 8;      // 4 phase planes x {hi, lo}
+
+struct Tap {
+    int8_t dy, dx;       // spatial offset added to the tile origin
+    uint8_t widx;        // which [N x K] matrix of the weight stack
+    uint8_t src;         // which A tensor map
+};
+
+struct TapProblem {
+    int tap_begin, ntaps;
+    int oy0, ox0;                  // output pixel = (h*osy + oy0, w*osx + ox0)
+    int tile_begin;                // first M-tile index of this problem
+};
+
+enum TapEpilogue : int {
+    kEpiRawF32 = 0,    // store accumulators as fp32 [pixel][n_total]                  (tests)
+    kEpiFwd = 1,       // demod + noise + bias + lrelu*gain + clamp -> x, x*s_next, toRGB partials
+    kEpiBwd = 2,       // style-gradient reductions + activation backward of the producer layer -> g_y
+    kEpiTopK = 3,      // rows = queries, columns = bank codes: per-tile k smallest |y|^2 - 2<x,y> per row
+};
+
+struct TapGemmParams {
+    alignas(64) CUtensorMap a_map[kMaxAMaps];
+    alignas(64) CUtensorMap b_map;
+    Tap taps[kMaxTaps];
+    TapProblem prob[kMaxProblems];
+    int nprob;
+    int th, tw, nb;        // M-tile box: nb images x th rows x tw cols (nb*th*tw <= 128)
+    int tiles_h, tiles_w, tiles_n;   // tile grid of ONE problem (all problems share the geometry)
+    int vh, vw;            // valid extent of the tile grid (rows, cols); overhang is masked
+    int batch;             // images
+    int kchunks;           // K / 64 per tap
+    int n_total;           // N (columns = output channels of this GEMM)
+    int n_blocks;          // N / BN
+    int m_tiles;           // sum of M tiles over problems
+    int epilogue;          // TapEpilogue
+    int OH, OW, osy, osx;  // output tensor spatial dims and the pixel stride of the tile grid in it
+    int split;             // 1: *_lo planes are written / read (split-bf16 precision)
+    float act_gain, act_clamp, act_slope;
+
+    float* raw_out;                    // kEpiRawF32: [batch, OH, OW, n_total]
+
+    // ---- kEpiFwd: this GEMM is layer l, columns = its output channels
+    const float* demod;                // [batch, N]
+    const float* bias;                 // [N]
+    const float* noise;                // [*, OH, OW] unit noise, or null
+    long long noise_stride_n;          // 0 = shared across the batch, OH*OW = per sample
+    float noise_scale;                 // noise_strength
+    const float* s_next;               // [batch, N] style of the consumer conv, or null
+    void* x_hi; void* x_lo;            // bf16 [batch, OH, OW, N]  activation (saved for backward)
+    void* xs_hi; void* xs_lo;          // bf16 [batch, OH, OW, N]  x * s_next (A operand of the consumer)
+    const float4* rgbw;                // [batch, N] (W_rgb[c][col] * s_rgb[n][col], c = x,y,z) or null
+    float4* rgb_part;                  // [n_blocks][batch, OH, OW] per-column-block toRGB partial sums
+
+    // ---- kEpiBwd: this GEMM is the data gradient of layer l; columns = channels of x_{l-1}
+    const float* s_cur;                // [batch, N] style of layer l
+    const void* xp_hi; const void* xp_lo;   // bf16 x_{l-1} [batch(or 1), OH, OW, N]
+    long long xp_stride_n;             // OH*OW*N, or 0 when x_{l-1} is the learned constant
+    const float4* g_rgb;               // [batch, OH, OW] gradient wrt the toRGB output fed by x_{l-1}, or null
+    const float4* rgbw_prev;           // [batch, N]
+    const float* demod_prev;           // [batch, N]   (layer l-1)
+    const float* bias_prev;            // [N]
+    const float* noise_prev;           // [*, OH, OW] or null
+    long long noise_prev_stride_n;
+    float noise_prev_scale;
+    void* gy_hi; void* gy_lo;          // bf16 [batch, OH, OW, N]  g_y of layer l-1 (A operand of its dgrad)
+    float* red_s;                      // [batch, N]      += sum_px acc * x_{l-1}
+    float* red_d;                      // [batch, N]      += sum_px g_z * (z - noise - bias)
+    float* red_rgb;                    // [3][batch, N]   += sum_px x_{l-1} * g_rgb[c]
+    int bwd_last;                      // 1: x_{l-1} is the constant input: only red_s is produced
+
+    // ---- kEpiTopK: acc[query, code] = <x, y>
+    const float* code_sqnorm;          // [n_codes] |y_j|^2
+    int n_codes, n_queries, topk;      // topk <= 8
+    float* cand_score;                 // [n_queries][n_blocks][topk]
+    int* cand_idx;                     // [n_queries][n_blocks][topk]
+
+    int* err_flag;
+};
+
+// tcgen05 path.  Returns cudaError_t as int.
+int launch_tapgemm(const TapGemmParams& p, int num_sms, cudaStream_t stream);
+
+// SIMT evaluation of the same contraction with the SAME epilogue code.  Used (a) with
+// ntaps == 0 as the "seed" of the backward chain (acc == 0), (b) as the debug cross-check
+// of the tensor-core path in tests.  `a_ptrs[i]` / `a_dims` describe what a_map[i] maps
+// (dims = {C, W, H, N}, strides in elements {sW, sH, sN}); `w` is the weight stack.
+struct TapSimtOperands {
+    const void* a_ptrs[kMaxAMaps];
+    long long a_sw, a_sh, a_sn;
+    int a_w, a_h;
+    const void* w;
+};
+int launch_tapgemm_simt(const TapGemmParams& p, const TapSimtOperands& ops, cudaStream_t stream);
+
+// Host helper: encode a bf16 tiled tensor map with 128B swizzle.  dims/box are innermost
+// first; strides (bytes) has rank-1 entries.  Returns 0 on success.
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                     const uint32_t* box);
+
+}  // namespace la

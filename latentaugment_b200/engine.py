@@ -1,0 +1,258 @@
+"""Python host over the C ABI: owns device memory (torch tensors) and streams, nothing else.
+
+``SynthesisEngine`` wraps one ``la_engine`` (one generator at one batch size).
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+
+_PARAM_ORDER_DOC = 'parameter names follow the reference contract models/stylegan3/legacy.py:171-203'
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def generator_state(G):
+    """state_dict-like mapping name -> tensor from an nn.Module or a plain dict."""
+    sd = G if isinstance(G, dict) else dict(G.state_dict())
+    return {k: v for k, v in sd.items()}
+
+
+class SynthesisEngine:
+    """One generator + batch size on one GPU.
+
+    ``state``: mapping with the reference parameter names (``synthesis.b{res}.conv0.weight``,
+    ``...affine.weight``, ``...noise_const``, ``...noise_strength``, ``synthesis.b4.const``,
+    ``synthesis.b{res}.torgb.*``, ``synthesis.b{res}.resample_filter`` or
+    ``synthesis.b{res}.conv0.resample_filter``, ``mapping.fc{i}.*``, ``mapping.w_avg``).
+    """
+
+    def __init__(self, state, *, img_resolution, img_channels, w_dim=512, z_dim=512, conv_clamp=256.0,
+                 batch, precision='fp32_parity', device=None, mapping_lr_multiplier=0.01):
+        if not torch.cuda.is_available():
+            raise _lib.LatentAugmentError('latentaugment_b200 needs a CUDA device (sm_100a); there is no CPU path')
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else f'cuda:{torch.cuda.current_device()}')
+        self.batch, self.precision = int(batch), precision
+        self.img_resolution, self.img_channels, self.w_dim, self.z_dim = img_resolution, img_channels, w_dim, z_dim
+        log2 = int(math.log2(img_resolution))
+        self.num_blocks = log2 - 1
+        self.num_ws = 2 * self.num_blocks
+        self._keep = []          # tensors whose storage the engine reads in place
+
+        def dev(name, default=None):
+            t = state.get(name, default)
+            if t is None:
+                raise KeyError(f'generator parameter {name!r} missing')
+            t = torch.as_tensor(t).detach().to(self.device, torch.float32).contiguous()
+            self._keep.append(t)
+            return t
+
+        d = _lib.GeneratorDesc()
+        d.img_resolution, d.img_channels, d.w_dim, d.z_dim = img_resolution, img_channels, w_dim, z_dim
+        d.num_blocks = self.num_blocks
+        d.conv_clamp = float(conv_clamp) if conv_clamp is not None else -1.0
+        d.d_const = _ptr(dev('synthesis.b4.const'))
+        f = state.get('synthesis.b4.resample_filter', state.get('synthesis.b8.conv0.resample_filter'))
+        if f is None:
+            f1 = torch.tensor([1., 3., 3., 1.])
+            f = torch.outer(f1, f1) / 64.0
+        d.d_resample_filter = _ptr(dev('__filter__', f))
+        li = 0
+        self.conv_res = []
+        for b in range(self.num_blocks):
+            res = 4 << b
+            names = (['conv0'] if b > 0 else []) + ['conv1']
+            for nm in names:
+                p = f'synthesis.b{res}.{nm}.'
+                w = dev(p + 'weight')
+                if nm == 'conv1':
+                    d.channels[b] = w.shape[0]
+                cp = d.conv[li]
+                cp.d_weight, cp.d_bias = _ptr(w), _ptr(dev(p + 'bias'))
+                cp.d_noise_const = _ptr(dev(p + 'noise_const'))
+                cp.noise_strength = float(torch.as_tensor(state[p + 'noise_strength']).item())
+                cp.d_affine_weight, cp.d_affine_bias = _ptr(dev(p + 'affine.weight')), _ptr(dev(p + 'affine.bias'))
+                self.conv_res.append(res)
+                li += 1
+            p = f'synthesis.b{res}.torgb.'
+            tp = d.torgb[b]
+            tp.d_weight, tp.d_bias = _ptr(dev(p + 'weight')), _ptr(dev(p + 'bias'))
+            tp.d_affine_weight, tp.d_affine_bias = _ptr(dev(p + 'affine.weight')), _ptr(dev(p + 'affine.bias'))
+        nmap = 0
+        while f'mapping.fc{nmap}.weight' in state and nmap < _lib.LA_MAX_MAPPING:
+            d.d_mapping_weight[nmap] = _ptr(dev(f'mapping.fc{nmap}.weight'))
+            d.d_mapping_bias[nmap] = _ptr(dev(f'mapping.fc{nmap}.bias'))
+            nmap += 1
+        d.mapping_layers = nmap
+        d.mapping_lr_multiplier = mapping_lr_multiplier
+        d.d_w_avg = _ptr(dev('mapping.w_avg', torch.zeros(w_dim)))
+        self.desc = d
+
+        nbytes = C.c_size_t(0)
+        prec = _lib.PRECISION[precision]
+        _lib.check(self.lib.la_engine_workspace_bytes(C.byref(d), self.batch, prec, C.byref(nbytes)))
+        self.workspace_bytes = nbytes.value
+        self.workspace = torch.empty(nbytes.value + 1024, dtype=torch.uint8, device=self.device)
+        base = (self.workspace.data_ptr() + 1023) // 1024 * 1024
+        handle = C.c_void_p(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.la_engine_create(C.byref(d), self.batch, prec, C.c_void_p(base), nbytes.value,
+                                                 _stream_ptr(self.device), C.byref(handle)))
+        self.handle = handle
+        self.noise_floats = self.lib.la_noise_floats(self.handle)
+
+    def __del__(self):
+        h = getattr(self, 'handle', None)
+        if h:
+            self.lib.la_engine_destroy(h)
+            self.handle = None
+
+    # ---- banks
+    def set_latent_bank(self, W):
+        W = W.detach().to(self.device, torch.float32).contiguous()
+        if W.ndim == 2:
+            W = W.unsqueeze(1).repeat(1, self.num_ws, 1).contiguous()
+        assert W.shape[1:] == (self.num_ws, self.w_dim), W.shape
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.la_set_latent_bank(self.handle, _ptr(W), W.shape[0], _stream_ptr(self.device)))
+        torch.cuda.current_stream(self.device).synchronize()      # W may be freed by the caller afterwards
+
+    def set_image_bank(self, X):
+        X = X.detach().to(self.device, torch.float32).contiguous()
+        assert X.shape[1:] == (self.img_channels, self.img_resolution, self.img_resolution), X.shape
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.la_set_image_bank(self.handle, _ptr(X), X.shape[0], _stream_ptr(self.device)))
+        torch.cuda.current_stream(self.device).synchronize()
+
+    # ---- network
+    def mapping(self, z, truncation_psi=1.0):
+        """[n, z_dim] -> [n, num_ws, w_dim] (broadcast rows), reference G.mapping(z, None, truncation_psi)."""
+        z = z.detach().to(self.device, torch.float32).contiguous()
+        n = z.shape[0]
+        out = torch.empty([n, self.w_dim], device=self.device)
+        with torch.cuda.device(self.device):
+            for i in range(0, n, self.batch):
+                j = min(n, i + self.batch)
+                _lib.check(self.lib.la_mapping(self.handle, _ptr(z[i:j]), j - i, float(truncation_psi), _ptr(out[i:j]),
+                                               _stream_ptr(self.device)))
+        return out.unsqueeze(1).repeat(1, self.num_ws, 1)
+
+    def _noise(self, noise_mode, noise):
+        if noise_mode != 'random':
+            return None
+        if noise is None:
+            noise = torch.randn([self.noise_floats], device=self.device)
+        elif isinstance(noise, (list, tuple)):
+            noise = torch.cat([n.reshape(-1) for n in noise])
+        noise = noise.detach().to(self.device, torch.float32).contiguous()
+        assert noise.numel() == self.noise_floats, (noise.numel(), self.noise_floats)
+        return noise
+
+    def synthesis(self, ws, noise_mode='random', noise=None):
+        """reference G.synthesis(ws, noise_mode=...): ws [batch, num_ws, w_dim] -> [batch, C, res, res]."""
+        ws = ws.detach().to(self.device, torch.float32).contiguous()
+        assert ws.shape == (self.batch, self.num_ws, self.w_dim), ws.shape
+        nz = self._noise(noise_mode, noise)
+        img = torch.empty([self.batch, self.img_channels, self.img_resolution, self.img_resolution], device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.la_synthesis(self.handle, _ptr(ws), self.num_ws * self.w_dim, self.w_dim,
+                                             _lib.NOISE[noise_mode], _ptr(nz), _ptr(img), _stream_ptr(self.device)))
+        return img
+
+    def augment(self, w0, *, num_steps=10, lr=0.01, w_latent=1.0, w_pix=1.0, soft_aug=False, alpha=1.0,
+                final_noise_mode='random', final_noise=None, return_losses=False):
+        """The hot path (reference LatentAug.forward).  w0 [batch, w_dim] or [batch, 1, w_dim]."""
+        w0 = w0.detach().to(self.device, torch.float32).reshape(self.batch, self.w_dim).contiguous()
+        nz = self._noise(final_noise_mode, final_noise)
+        img = torch.empty([self.batch, self.img_channels, self.img_resolution, self.img_resolution], device=self.device)
+        w_aug = torch.empty([self.batch, self.w_dim], device=self.device)
+        losses = torch.zeros([max(num_steps, 1), 4], device=self.device) if return_losses else None
+        opt = _lib.AugmentOptions(num_steps, lr, w_latent, w_pix, int(bool(soft_aug)), alpha, _lib.NOISE[final_noise_mode],
+                                  self.img_channels)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.la_augment(self.handle, _ptr(w0), C.byref(opt), _ptr(nz), _ptr(img), _ptr(w_aug), _ptr(losses),
+                                           _stream_ptr(self.device)))
+        if return_losses:
+            return img, w_aug, losses[:num_steps]
+        return img, w_aug
+
+    # ---- debug hooks (tests)
+    def debug_set_simt(self, flag):
+        _lib.check(self.lib.la_debug_set_simt(self.handle, int(flag)))
+
+    def debug_check(self):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.la_debug_check(self.handle, _stream_ptr(self.device)))
+
+    @property
+    def launch_count(self):
+        return self.lib.la_debug_launch_count(self.handle)
+
+
+def pairwise_sqdist(X, Y):
+    """D [m, n] = l2_loss_vectorized(X, Y, compute_mean=False) (reference util_latent_aug.py:315-361)."""
+    lib = _lib.load()
+    n, m = X.shape[0], Y.shape[0]
+    X = X.detach().reshape(n, -1).float().contiguous()
+    Y = Y.detach().reshape(m, -1).float().contiguous()
+    D = torch.empty([m, n], device=X.device)
+    with torch.cuda.device(X.device):
+        _lib.check(lib.la_pairwise_sqdist(_ptr(X), n, _ptr(Y), m, X.shape[1], _ptr(D), _stream_ptr(X.device)))
+    return D
+
+
+class LatentBank:
+    """Device-resident real-code bank (or one shard of it) prepared for nearest-code queries."""
+
+    def __init__(self, Y, index_offset=0):
+        self.lib = _lib.load()
+        m = Y.shape[0]
+        self.Y = Y.detach().reshape(m, -1).float().contiguous()
+        self.m, self.K = m, self.Y.shape[1]
+        self.index_offset = int(index_offset)
+        self.bf16 = torch.empty([2, m, self.K], dtype=torch.bfloat16, device=self.Y.device)
+        self.sqnorm = torch.empty([m], device=self.Y.device)
+        with torch.cuda.device(self.Y.device):
+            _lib.check(self.lib.la_bank_prepare(_ptr(self.Y), m, self.K, _ptr(self.bf16), _ptr(self.sqnorm),
+                                                _stream_ptr(self.Y.device)))
+        self._ws = None
+
+    def nearest(self, X, k=1):
+        """(dist [n, k], idx [n, k] int64) of the k nearest bank rows per query, ties to the lowest index."""
+        n = X.shape[0]
+        X = X.detach().reshape(n, -1).float().contiguous()
+        assert X.shape[1] == self.K
+        nbytes = C.c_size_t(0)
+        _lib.check(self.lib.la_nearest_codes_workspace_bytes(n, self.m, self.K, k, C.byref(nbytes)))
+        if self._ws is None or self._ws.numel() < nbytes.value + 1024:
+            self._ws = torch.empty(nbytes.value + 1024, dtype=torch.uint8, device=X.device)
+        base = (self._ws.data_ptr() + 1023) // 1024 * 1024
+        dist = torch.empty([n, k], device=X.device)
+        idx = torch.empty([n, k], dtype=torch.int64, device=X.device)
+        with torch.cuda.device(X.device):
+            _lib.check(self.lib.la_nearest_codes(_ptr(X), n, _ptr(self.Y), _ptr(self.bf16), _ptr(self.sqnorm), self.m, self.K,
+                                                 k, self.index_offset, C.c_void_p(base), nbytes.value, _ptr(dist), _ptr(idx),
+                                                 _stream_ptr(X.device)))
+        return dist, idx
+
+
+def merge_topk(dist, idx):
+    """[shards, n, k] -> [n, k] global k best (ties to the lowest index)."""
+    lib = _lib.load()
+    s, n, k = dist.shape
+    dist = dist.float().contiguous()
+    idx = idx.to(torch.int64).contiguous()
+    od = torch.empty([n, k], device=dist.device)
+    oi = torch.empty([n, k], dtype=torch.int64, device=dist.device)
+    with torch.cuda.device(dist.device):
+        _lib.check(lib.la_merge_topk(_ptr(dist), _ptr(idx), s, n, k, _ptr(od), _ptr(oi), _stream_ptr(dist.device)))
+    return od, oi

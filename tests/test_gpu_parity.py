@@ -1,0 +1,197 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs, and against the reference-generated golden fixtures.
+
+Tolerances (relative L2, written here as the north_star states them):
+  * fp32_parity mode (split-bf16 operands, fp32 accumulate): 1e-3 on images and final w
+  * bf16 mode: widened to 1e-2 (measured ~2-3e-3, tools/precision_study.py)
+  * nearest-code indices: bit-exact
+"""
+import random
+
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = {'fp32_parity': 1e-3, 'bf16': 1e-2}
+
+
+def _engine(wl, precision, batch=None):
+    from latentaugment_b200.engine import SynthesisEngine
+    G = wl['G']
+    return SynthesisEngine(dict(G.state_dict()), img_resolution=G.img_resolution, img_channels=G.img_channels,
+                           w_dim=G.w_dim, z_dim=G.z_dim, batch=batch or wl['w0'].shape[0], precision=precision)
+
+
+def _workload(cfg, noise_strength=0.1):
+    from oracle import synthetic
+    return synthetic.make_workload(cfg, noise_strength=noise_strength)
+
+
+@pytest.mark.parametrize('cfg', ['tiny', 'tiny128', 'small'])
+@pytest.mark.parametrize('precision', ['fp32_parity', 'bf16'])
+def test_synthesis_matches_oracle(cfg, precision):
+    wl = _workload(cfg)
+    G = wl['G']
+    eng = _engine(wl, precision)
+    ws = wl['w0'].repeat(1, G.num_ws, 1)
+    with torch.no_grad():
+        ref_const = G.synthesis(ws, noise_mode='const')
+        ref_none = G.synthesis(ws, noise_mode='none')
+    out_const = eng.synthesis(ws, noise_mode='const').cpu()
+    out_none = eng.synthesis(ws, noise_mode='none').cpu()
+    eng.debug_check()
+    e1, e2 = rel_l2(out_const, ref_const), rel_l2(out_none, ref_none)
+    print(f'\n[synthesis {cfg} {precision}] rel_l2 const={e1:.3e} none={e2:.3e}')
+    tol = 1e-4 if precision == 'fp32_parity' else 1e-2
+    assert e1 < tol and e2 < tol
+    # distinct ws rows per layer (general G.synthesis(ws) call)
+    ws2 = ws + 0.05 * torch.randn(ws.shape, generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        ref2 = G.synthesis(ws2, noise_mode='const')
+    e3 = rel_l2(eng.synthesis(ws2, noise_mode='const').cpu(), ref2)
+    print(f'[synthesis {cfg} {precision}] per-layer ws rel_l2={e3:.3e}')
+    assert e3 < tol
+
+
+@pytest.mark.parametrize('cfg', ['tiny', 'tiny128'])
+def test_tensor_core_path_matches_simt_twin(cfg):
+    """tcgen05 tap-GEMM vs its SIMT twin (same epilogue code, brute-force accumulation)."""
+    wl = _workload(cfg)
+    G = wl['G']
+    eng = _engine(wl, 'fp32_parity')
+    ws = wl['w0'].repeat(1, G.num_ws, 1)
+    a = eng.synthesis(ws, noise_mode='const').cpu()
+    eng.debug_set_simt(1)
+    b = eng.synthesis(ws, noise_mode='const').cpu()
+    eng.debug_set_simt(0)
+    e = rel_l2(a, b)
+    print(f'\n[tc vs simt {cfg}] rel_l2={e:.3e}')
+    assert e < 2e-5
+
+
+def test_random_noise_synthesis_matches_oracle():
+    wl = _workload('tiny')
+    G = wl['G']
+    eng = _engine(wl, 'fp32_parity')
+    ws = wl['w0'].repeat(1, G.num_ws, 1)
+    torch.manual_seed(77)
+    with torch.no_grad():
+        ref = G.synthesis(ws, noise_mode='random')
+    torch.manual_seed(77)       # same draws, same layer order (conv0, conv1 per block)
+    noise = [torch.randn([ws.shape[0], 1, r, r]) for r in eng.conv_res]
+    out = eng.synthesis(ws, noise_mode='random', noise=noise).cpu()
+    e = rel_l2(out, ref)
+    print(f'\n[random noise] rel_l2={e:.3e}')
+    assert e < 1e-4
+
+
+@pytest.mark.parametrize('cfg,steps', [('tiny', 3), ('tiny128', 2), ('small', 2), ('tiny', 10)])
+@pytest.mark.parametrize('precision', ['fp32_parity', 'bf16'])
+def test_augment_loop_matches_oracle(cfg, steps, precision):
+    from oracle import latent_aug as ola
+    wl = _workload(cfg)
+    G = wl['G']
+    eng = _engine(wl, precision)
+    eng.set_latent_bank(wl['W'])
+    eng.set_image_bank(wl['X'])
+    orc = ola.LatentAugOracle(G, wl['W'], wl['X'], num_epochs=steps, fused=True)
+    random.seed(0)
+    torch.manual_seed(1234)
+    img_ref, w_ref = orc.forward(wl['w0'].clone())
+    torch.manual_seed(1234)
+    noise = [torch.randn([wl['w0'].shape[0], 1, r, r]) for r in eng.conv_res]
+    img, w_aug, losses = eng.augment(wl['w0'], num_steps=steps, lr=0.01, w_latent=1.0, w_pix=1.0,
+                                     final_noise_mode='random', final_noise=noise, return_losses=True)
+    eng.debug_check()
+    ew, ei = rel_l2(w_aug.cpu(), w_ref[:, 0]), rel_l2(img.cpu(), img_ref)
+    l0 = losses[0].cpu()
+    print(f'\n[augment {cfg} steps={steps} {precision}] rel_w={ew:.3e} rel_img={ei:.3e} '
+          f'loss0 ours=({l0[0]:.6f},{l0[1]:.6f}) oracle=({orc.loss_log[0][0]:.6f},{orc.loss_log[0][1]:.6f})')
+    assert abs(float(l0[0]) - orc.loss_log[0][0]) <= 1e-4 * abs(orc.loss_log[0][0])
+    assert abs(float(l0[1]) - orc.loss_log[0][1]) <= (1e-3 if precision == 'fp32_parity' else 2e-2) * abs(orc.loss_log[0][1])
+    assert ew < TOL[precision] and ei < TOL[precision]
+
+
+@pytest.mark.parametrize('name', ['loop_tiny.pt', 'loop_tiny_soft.pt', 'loop_tiny128.pt', 'loop_small.pt'])
+def test_augment_loop_matches_reference_golden(golden, name):
+    """Against outputs of the REFERENCE's own LatentAug.forward (tests/golden, oracle/make_golden.py)."""
+    g = golden(name)
+    wl = _workload(g['config'], noise_strength=g['noise_strength'])
+    eng = _engine(wl, 'fp32_parity')
+    eng.set_latent_bank(wl['W'])
+    eng.set_image_bank(wl['X'])
+    G = wl['G']
+    ws0 = wl['w0'].repeat(1, G.num_ws, 1)
+    e0 = rel_l2(eng.synthesis(ws0, noise_mode='const').cpu(), g['img0_const'])
+    torch.manual_seed(1234)
+    noise = [torch.randn([wl['w0'].shape[0], 1, r, r]) for r in eng.conv_res]
+    img, w_aug, losses = eng.augment(wl['w0'], num_steps=g['steps'], lr=0.01, w_latent=g['w_latent'], w_pix=g['w_pix'],
+                                     soft_aug=g['soft_aug'], alpha=g['alpha'], final_noise_mode='random', final_noise=noise,
+                                     return_losses=True)
+    ew, ei = rel_l2(w_aug.cpu(), g['w_aug']), rel_l2(img.cpu(), g['img'])
+    print(f'\n[golden {name}] img0={e0:.3e} rel_w={ew:.3e} rel_img={ei:.3e}')
+    assert e0 < 1e-4
+    assert abs(float(losses[0, 0]) - g['loss_latent0']) <= 1e-4 * abs(g['loss_latent0'])
+    assert abs(float(losses[0, 1]) - g['loss_pix0']) <= 1e-3 * abs(g['loss_pix0'])
+    assert ew < 1e-3 and ei < 1e-3
+
+
+def test_latent_only_and_zero_steps():
+    """w_pix = 0 skips synthesis in the loop; num_steps = 0 is the rand_aug configuration."""
+    from oracle import latent_aug as ola
+    wl = _workload('tiny', noise_strength=0.0)
+    G = wl['G']
+    eng = _engine(wl, 'fp32_parity')
+    eng.set_latent_bank(wl['W'])
+    orc = ola.LatentAugOracle(G, wl['W'], None, num_epochs=4, w_pix=0.0)
+    img_ref, w_ref = orc.forward(wl['w0'].clone())
+    img, w_aug = eng.augment(wl['w0'], num_steps=4, w_pix=0.0, final_noise_mode='const')
+    assert rel_l2(w_aug.cpu(), w_ref[:, 0]) < 1e-5
+    assert rel_l2(img.cpu(), img_ref) < 1e-4
+    img0, w0 = eng.augment(wl['w0'], num_steps=0, final_noise_mode='const')
+    assert torch.equal(w0.cpu(), wl['w0'][:, 0])
+
+
+def test_mapping_matches_oracle():
+    wl = _workload('tiny')
+    G = wl['G']
+    eng = _engine(wl, 'fp32_parity')
+    z = torch.randn([3, G.z_dim], generator=torch.Generator().manual_seed(4))
+    G.mapping.w_avg.copy_(torch.randn([G.w_dim], generator=torch.Generator().manual_seed(5)) * 0.1)
+    eng2 = _engine(wl, 'fp32_parity')
+    for psi in (1.0, 0.7):
+        with torch.no_grad():
+            ref = G.mapping(z, None, truncation_psi=psi)
+        out = eng2.mapping(z, truncation_psi=psi).cpu()
+        assert out.shape == ref.shape
+        e = rel_l2(out, ref)
+        print(f'\n[mapping psi={psi}] rel_l2={e:.3e}')
+        assert e < 1e-5
+    del eng
+
+
+@pytest.mark.parametrize('shape', [(32, 4096, 7168), (5, 300, 512), (130, 1000, 512)])
+def test_nearest_codes_bit_exact(shape):
+    from latentaugment_b200.engine import LatentBank, merge_topk, pairwise_sqdist
+    from oracle import latent_aug as ola
+    n, m, K = shape
+    gen = torch.Generator().manual_seed(11)
+    Y = torch.randn([m, K], generator=gen)
+    X = Y[torch.randint(0, m, [n], generator=gen)] + 0.3 * torch.randn([n, K], generator=gen)
+    d_ref, i_ref = ola.nearest_codes(X, Y, k=4)
+    D = pairwise_sqdist(X.cuda(), Y.cuda()).cpu()
+    D_ref = ola.l2_loss_vectorized(X, Y, compute_mean=False)
+    assert D.shape == D_ref.shape == (m, n)
+    torch.testing.assert_close(D, D_ref, rtol=1e-5, atol=1e-3)
+    bank = LatentBank(Y.cuda())
+    dist, idx = bank.nearest(X.cuda(), k=4)
+    assert torch.equal(idx.cpu(), i_ref), (idx.cpu()[:4], i_ref[:4])
+    torch.testing.assert_close(dist.cpu(), d_ref, rtol=1e-5, atol=1e-3)
+    # sharded bank + merge == whole bank
+    half = m // 2
+    parts = [LatentBank(Y[:half].cuda(), 0).nearest(X.cuda(), k=4), LatentBank(Y[half:].cuda(), half).nearest(X.cuda(), k=4)]
+    md, mi = merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+    assert torch.equal(mi.cpu(), i_ref)
