@@ -150,7 +150,10 @@ int la_merge_topk(const float* d_dist, const long long* d_idx, int shards, int n
 /* Test hooks: run every tap-GEMM of the engine once through the SIMT twin as well and report
  * the largest deviation (debug cross-check of the tensor-core path; not a product path). */
 int la_debug_set_simt(la_engine* e, int use_simt);
-int la_debug_check(la_engine* e, la_stream stream);   /* synchronises; non-zero if a pipeline wait timed out */
+int la_debug_check(la_engine* e, la_stream stream);
+/* Times each tap-GEMM launch of one optimisation step alone (CUDA events, `reps` launches each).
+ * h_ms: HOST array [2*L + 1] = forward[0..L), data gradient[0..L), backward seed.  Synchronous. */
+int la_debug_time_gemms(la_engine* e, int reps, float* h_ms, int* n_layers);   /* synchronises; non-zero if a pipeline wait timed out */
 long long la_debug_launch_count(const la_engine* e);
 
 #ifdef __cplusplus

@@ -1,0 +1,221 @@
+"""Optimisation core: B200-native counterpart of the reference
+``augments/utils/util_latent_aug.py`` (``LatentAug``, ``define_latentaugment``).
+
+The reference wraps one ``LatentAug`` nn.Module in ``nn.DataParallel`` (:20-33): every call
+replicates G and the banks to each GPU, scatters ``w`` on dim 0 and runs an independent Adam
+loop per replica with per-replica loss normalisers.  Here each GPU id owns one resident
+``SynthesisEngine`` (weights and bank moments uploaded once); a call slices the batch the same
+way and enqueues the replicas' loops asynchronously on their own devices -- same semantics,
+no per-call replication.  For multi-process runs (one process per GPU, ``torchrun``) each
+rank simply builds its own ``LatentAug`` over its batch shard (bench.py).
+"""
+import random
+
+import torch
+
+from ... import engine as _engine
+from ...utils import synthetic
+from ..criteria import create_criteria
+from ..criteria.pix import center_crop_bounds
+
+
+def l2_loss_vectorized(X, Y, compute_mean=True):
+    """Pairwise squared L2, [bank, batch] orientation (reference :315-361) on the CUDA kernel."""
+    if X.ndim not in (2, 3, 4) or Y.ndim != X.ndim:
+        raise NotImplementedError
+    D = _engine.pairwise_sqdist(X, Y)
+    if compute_mean:
+        D = D.sum() / (D.shape[0] * D.shape[1])
+        n = 1
+        for s in Y.shape[1:]:
+            n *= s
+        D = D / n
+    return D
+
+
+def get_crop_params(load_size, crop_size, preprocess='center_random_crop'):
+    """Same two python ``random`` draws per call as the reference (util_dataset.py:284-296)."""
+    new = load_size
+    if preprocess == 'center_random_crop':
+        new = center_crop_bounds(load_size)[1]
+    x = random.randint(0, max(0, new - crop_size))
+    y = random.randint(0, max(0, new - crop_size))
+    return {'crop_pos': (x, y)}
+
+
+class InvertedCodeTable:
+    """Preloaded table of inverted codes keyed by sample file name: replaces the reference's
+    per-sample zip read + unpickle in ``sample_from_inversion`` (latent_aug.py:310-324;
+    SURVEY.md §8f rank 3) with one pinned ``[N, w_dim]`` tensor and an index lookup."""
+
+    def __init__(self, names, codes):
+        assert len(names) == codes.shape[0]
+        self.index = {n: i for i, n in enumerate(names)}
+        codes = codes.detach().float().reshape(len(names), -1).contiguous()
+        self.codes = codes.pin_memory() if torch.cuda.is_available() else codes
+
+    def __len__(self):
+        return self.codes.shape[0]
+
+    def lookup(self, fnames):
+        idx = torch.tensor([self.index[f] for f in fnames], dtype=torch.long)
+        return self.codes.index_select(0, idx)
+
+
+class LatentAug:
+    """Attributes mirror the reference class (:70-200): ``num_ws, w_dim, z_dim, batch_size,
+    world_size, res, modalities, num_epochs, opt_lr, w_pix, w_lpips, w_latent, w_disc,
+    soft_aug, alpha, truncation_psi, stats_dataset_w``; ``.module`` is the object itself (the
+    reference reaches through ``DataParallel.module``, latent_aug.py:146-149,249)."""
+
+    def __init__(self, phase, opt, save_dir, gpu_ids, generator_state=None, latent_bank=None, image_bank=None,
+                 inverted_codes=None):
+        if not gpu_ids:
+            raise _engine._lib.LatentAugmentError('latentaugment_b200 has no CPU path: pass at least one GPU id')
+        self.phase, self.opt, self.save_dir = phase, opt, save_dir
+        self.gpu_ids = list(gpu_ids)
+        self.world_size = len(self.gpu_ids)
+        self.batch_size = opt.batch_size
+        assert self.batch_size % self.world_size == 0, 'batch_size must divide over gpu_ids_aug'
+        self.num_epochs, self.opt_lr = opt.opt_num_epochs, opt.opt_lr
+        self.w_pix, self.w_lpips, self.w_latent, self.w_disc = opt.w_pix, opt.w_lpips, opt.w_latent, opt.w_disc
+        self.soft_aug, self.alpha = bool(opt.soft_aug), opt.alpha
+        self.truncation_psi = opt.truncation_psi
+        self.crop_size, self.preprocess = opt.crop_size_aug, opt.preprocess_aug
+        self.verbose_flag = bool(getattr(opt, 'verbose_log', False))
+        self.precision = getattr(opt, 'precision', 'fp32_parity')
+        self.criteria = create_criteria(opt)           # raises NotImplementedError for lpips / disc weights > 0
+        self.stats_loss, self.stats_time = {}, {}
+        self.module = self
+
+        # ---- generator (reference: load_stylegan, :466-484)
+        if generator_state is None:
+            if getattr(opt, 'generator_state', ''):
+                generator_state = torch.load(opt.generator_state, map_location='cpu', weights_only=True)
+            elif getattr(opt, 'synthetic', False):
+                generator_state = synthetic.random_generator_state(
+                    img_resolution=opt.img_resolution, img_channels=opt.synthetic_channels,
+                    channel_base=opt.synthetic_channel_base, channel_max=opt.synthetic_channel_max, seed=0)
+            else:
+                raise FileNotFoundError(
+                    'no generator given: pass --generator_state <state_dict.pt> (reference names, legacy.py:171-203) '
+                    'or --synthetic; the reference\'s source-embedding pickles need its persistence module')
+        kw = synthetic.infer_generator_kwargs(generator_state)
+        self.res, self.img_channels = kw['img_resolution'], kw['img_channels']
+        self.w_dim, self.z_dim = kw['w_dim'], kw['z_dim']
+        self.modalities = list(range(self.img_channels))
+        conv_clamp = getattr(opt, 'conv_clamp', 256.0)
+        self.engines = []
+        for gid in self.gpu_ids:
+            self.engines.append(_engine.SynthesisEngine(
+                generator_state, batch=self.batch_size // self.world_size, precision=self.precision,
+                device=f'cuda:{gid}', conv_clamp=conv_clamp, **kw))
+        self.num_ws = self.engines[0].num_ws
+        self.device = self.engines[0].device
+
+        # ---- banks (reference: compute_stats -> register_buffer('W' / 'X'), :140-158)
+        gen = torch.Generator().manual_seed(1)
+        if latent_bank is None and getattr(opt, 'latent_bank', ''):
+            latent_bank = torch.load(opt.latent_bank, map_location='cpu', weights_only=True)
+        if latent_bank is None and getattr(opt, 'synthetic', False):
+            z = torch.randn([opt.synthetic_bank, self.z_dim], generator=gen)
+            latent_bank = self.engines[0].mapping(z)[:, :1].cpu()
+        if image_bank is None and getattr(opt, 'image_bank', ''):
+            image_bank = torch.load(opt.image_bank, map_location='cpu', weights_only=True)
+        if image_bank is None and getattr(opt, 'synthetic', False) and self.w_pix > 0:
+            image_bank = torch.rand([opt.synthetic_img_bank, self.img_channels, self.res, self.res],
+                                    generator=torch.Generator().manual_seed(3)) * 2 - 1
+        self.W = self.X = None
+        if self.w_latent > 0:
+            if latent_bank is None:
+                raise FileNotFoundError('w_latent > 0 needs a latent bank (--latent_bank or --synthetic)')
+            W = latent_bank.float()
+            if W.ndim == 2:
+                W = W.unsqueeze(1)
+            if W.shape[1] == 1:
+                W = W.repeat(1, self.num_ws, 1)
+            self.W = W.to(self.device)
+            for e in self.engines:
+                self.criteria['latent'].attach(e, W)
+        if self.w_pix > 0:
+            if image_bank is None:
+                raise FileNotFoundError('w_pix > 0 needs an image bank (--image_bank or --synthetic)')
+            self.X = image_bank.float()
+            for e in self.engines:
+                self.criteria['pix'].attach(e, self.X)
+        # ---- inverted codes (reference: LatentCodeDataset zip, :140-143; latent_aug.py:310-324)
+        if inverted_codes is None and getattr(opt, 'inverted_codes', ''):
+            blob = torch.load(opt.inverted_codes, map_location='cpu', weights_only=False)
+            inverted_codes = InvertedCodeTable(blob['names'], blob['codes'])
+        if inverted_codes is None and getattr(opt, 'synthetic', False):
+            n = opt.synthetic_codes
+            z = torch.randn([n, self.z_dim], generator=torch.Generator().manual_seed(2))
+            codes = torch.cat([self.engines[0].mapping(z[i:i + 256])[:, 0].cpu() for i in range(0, n, 256)])
+            inverted_codes = InvertedCodeTable([f'synthetic_{i:05d}' for i in range(n)], codes)
+        self.stats_dataset_w = inverted_codes
+
+    # ---- reference helpers
+    def broadcasting(self, latent):
+        return latent.repeat([1, self.num_ws, 1])            # :493-494
+
+    @staticmethod
+    def reverse_broadcasting(latent):
+        return latent[:, :1, :]                               # :496-498
+
+    l2_loss_vectorized = staticmethod(l2_loss_vectorized)
+
+    def calc_loss_latent(self, ws, W):
+        return self.criteria['latent'](ws, W)
+
+    def calc_loss_pix(self, x, x_bank):
+        return self.criteria['pix'](x, x_bank)
+
+    def _shards(self, t):
+        n = self.batch_size // self.world_size
+        return [t[i * n:(i + 1) * n] for i in range(self.world_size)]
+
+    def z_to_w(self, z):
+        """:459-464"""
+        outs = [e.mapping(zs, truncation_psi=self.truncation_psi)[:, :1, :] for e, zs in zip(self.engines, self._shards(z))]
+        return torch.cat([o.to(self.device) for o in outs])
+
+    def forward_ganrand(self, z):
+        """:202-205 -- G.mapping(z, None, truncation_psi) -> G.synthesis(w) (default noise mode)."""
+        imgs, wss = [], []
+        for e, zs in zip(self.engines, self._shards(z)):
+            ws = e.mapping(zs, truncation_psi=self.truncation_psi)
+            imgs.append(e.synthesis(ws, noise_mode='random'))
+            wss.append(ws)
+        return (torch.cat([i.to(self.device) for i in imgs]), torch.cat([w.to(self.device) for w in wss]))
+
+    def forward(self, w, fname=None):
+        """:207-310.  w [B, 1, w_dim] (or z [B, z_dim]) -> (img [B, C, res, res], w_aug [B, num_ws, w_dim])."""
+        if w.ndim == 2:
+            w = self.z_to_w(w)
+        assert w.shape[0] == self.batch_size
+        get_crop_params(self.res, self.crop_size, self.preprocess)      # :216 (RNG draws; the crop feeds lpips only)
+        imgs, ws_out, self.last_losses = [], [], []
+        for e, wsh in zip(self.engines, self._shards(w)):
+            out = e.augment(wsh, num_steps=self.num_epochs, lr=self.opt_lr, w_latent=self.w_latent, w_pix=self.w_pix,
+                            soft_aug=self.soft_aug, alpha=self.alpha, final_noise_mode='random',
+                            return_losses=self.verbose_flag)
+            imgs.append(out[0])
+            ws_out.append(out[1])
+            if self.verbose_flag:
+                self.last_losses.append(out[2])
+        img = torch.cat([i.to(self.device, non_blocking=True) for i in imgs]) if self.world_size > 1 else imgs[0]
+        w_aug = torch.cat([x.to(self.device, non_blocking=True) for x in ws_out]) if self.world_size > 1 else ws_out[0]
+        if self.verbose_flag:
+            for rank, ll in enumerate(self.last_losses):
+                for t, row in enumerate(ll.cpu().tolist()):
+                    print(f'[rank {rank}] epoch {t}: loss_latent {row[0]:.6f} loss_pix {row[1]:.6f} loss {row[2]:.6f}')
+        return img, self.broadcasting(w_aug.unsqueeze(1))
+
+    __call__ = forward
+
+
+def define_latentaugment(module_name, phase, opt, save_dir, gpu_ids, **kw):
+    """:47-66"""
+    if module_name == 'latent_aug':
+        return LatentAug(phase, opt, save_dir, gpu_ids, **kw)
+    raise NotImplementedError('LatentAugmentation module name [%s] is not recognized' % module_name)

@@ -99,7 +99,7 @@ struct la_engine {
     cudaStream_t work = nullptr; cudaEvent_t ev_in = nullptr, ev_out = nullptr;
     cudaGraphExec_t step_graph = nullptr; bool warmed = false; bool graph_disabled = false;
     int use_simt = 0;
-    long long launches = 0;
+    long long launches = 0, launches_captured = 0, graph_kernels = 0;   // kernel launches (graph replays count their kernels)
     float cur_w_pix = -1.f;
 };
 
@@ -450,7 +450,7 @@ int run_forward(la_engine* e, const float* ws, long long sn, long long si, int n
     LA(demod_rgbw_forward(e->table, B, e->s_cat, e->d_cat, e->rgbw, s));
     LA(const_modulate(e->c_f32, e->s_cat + static_cast<size_t>(B) * e->conv[0].soff, B, 16, g.channels[0], e->split, e->xs_hi[0],
                       e->xs_lo[0], s));
-    e->launches += 5;
+    e->launches += 4;
     const int L = static_cast<int>(e->conv.size());
     for (int l = 0; l < L; ++l) {
         Conv& c = e->conv[l];
@@ -681,15 +681,17 @@ LA_API int la_augment(la_engine* e, const float* d_w0, const la_augment_options*
             CU(cudaStreamBeginCapture(w, cudaStreamCaptureModeThreadLocal));
             int r = run_step(e, *opt, w);
             cudaError_t ce = cudaStreamEndCapture(w, &graph);
+            e->launches_captured = e->launches - before;
             e->launches = before;
             if (r) { if (graph) cudaGraphDestroy(graph); return r; }
             CU(ce);
+            e->graph_kernels = e->launches_captured;
             ce = cudaGraphInstantiate(&e->step_graph, graph, 0);
             cudaGraphDestroy(graph);
             CU(ce);
         }
         CU(cudaGraphLaunch(e->step_graph, w));
-        e->launches += 1;
+        e->launches += e->graph_kernels;
     }
     LA(finalize_w(e->w_opt, e->w0, opt->alpha, opt->soft_aug, B, g.w_dim, e->w_aug, w));
     LA(run_forward(e, e->w_aug, g.w_dim, 0, opt->final_noise_mode, d_final_noise, d_img, w));
@@ -707,6 +709,39 @@ LA_API int la_debug_set_simt(la_engine* e, int use_simt) {
     return 0;
 }
 LA_API long long la_debug_launch_count(const la_engine* e) { return e ? e->launches : 0; }
+
+// Times every tap-GEMM launch of one optimisation step in isolation (CUDA events on the launch
+// stream, `reps` back-to-back launches each; buffers hold whatever the last call left).
+// h_ms: host array [2*L + 1] = forward[0..L), data-gradient[0..L), seed.  Synchronous.
+LA_API int la_debug_time_gemms(la_engine* e, int reps, float* h_ms, int* n_layers) {
+    if (!e || !h_ms || reps < 1) return fail(-2, "bad arguments");
+    const int L = static_cast<int>(e->conv.size());
+    if (n_layers) *n_layers = L;
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    cudaStream_t w = e->work;
+    auto timed = [&](int idx, const TapGemmParams& P, const TapSimtOperands& ops, bool simt) -> int {
+        for (int warm = 0; warm < 2; ++warm) { int r = simt ? launch_tapgemm_simt(P, ops, w) : launch_tapgemm(P, e->num_sms, w); if (r) return r; }
+        cudaEventRecord(a, w);
+        for (int i = 0; i < reps; ++i) { int r = simt ? launch_tapgemm_simt(P, ops, w) : launch_tapgemm(P, e->num_sms, w); if (r) return r; }
+        cudaEventRecord(b, w);
+        cudaError_t ce = cudaEventSynchronize(b);
+        if (ce != cudaSuccess) return static_cast<int>(ce);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        h_ms[idx] = ms / reps;
+        return 0;
+    };
+    for (int l = 0; l < L; ++l) {
+        LA(timed(l, e->conv[l].fwd, e->conv[l].fwd_ops, false));
+        LA(timed(L + l, e->conv[l].bwd, e->conv[l].bwd_ops, false));
+    }
+    LA(timed(2 * L, e->seed, e->seed_ops, true));
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    return 0;
+}
 
 LA_API int la_debug_check(la_engine* e, la_stream stream) { return e ? check_err_flag(e, static_cast<cudaStream_t>(stream)) : -2; }
 

@@ -193,6 +193,17 @@ class SynthesisEngine:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.la_debug_check(self.handle, _stream_ptr(self.device)))
 
+    def debug_time_gemms(self, reps=5):
+        """Per-launch device time (ms) of every tap-GEMM of one optimisation step, timed alone."""
+        n = len(self.conv_res)
+        buf = (C.c_float * (2 * n + 1))()
+        nl = C.c_int(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.la_debug_time_gemms(self.handle, reps, buf, C.byref(nl)))
+        assert nl.value == n
+        v = list(buf)
+        return {'forward': v[:n], 'dgrad': v[n:2 * n], 'seed': v[2 * n]}
+
     @property
     def launch_count(self):
         return self.lib.la_debug_launch_count(self.handle)

@@ -1,0 +1,67 @@
+"""Random-init StyleGAN2 generator parameters and synthetic banks for the
+throughput runs and for users without a trained pickle.  Product-side: does NOT use oracle/.
+
+Parameter names and layouts follow the reference contract ``models/stylegan3/legacy.py:171-203``:
+``mapping.fc{i}.{weight,bias}``, ``mapping.w_avg``, ``synthesis.b{res}.{const,resample_filter}``,
+``synthesis.b{res}.{conv0,conv1}.{weight,bias,noise_const,noise_strength,affine.weight,affine.bias}``,
+``synthesis.b{res}.torgb.{weight,bias,affine.weight,affine.bias}``.
+"""
+import math
+
+import torch
+
+
+def channels_for(img_resolution, channel_base=32768, channel_max=512):
+    log2 = int(math.log2(img_resolution))
+    assert 2 ** log2 == img_resolution and img_resolution >= 8
+    return {4 << b: min(channel_base // (4 << b), channel_max) for b in range(log2 - 1)}
+
+
+def random_generator_state(img_resolution=256, img_channels=3, w_dim=512, z_dim=512, channel_base=32768, channel_max=512,
+                           mapping_layers=8, lr_multiplier=0.01, noise_strength=0.0, seed=0, device='cpu'):
+    g = torch.Generator(device='cpu').manual_seed(seed)
+
+    def randn(*shape):
+        return torch.randn(shape, generator=g).to(device)
+    ch = channels_for(img_resolution, channel_base, channel_max)
+    sd = {}
+    dims = [z_dim] + [w_dim] * mapping_layers
+    for i in range(mapping_layers):
+        sd[f'mapping.fc{i}.weight'] = randn(dims[i + 1], dims[i]) / lr_multiplier
+        sd[f'mapping.fc{i}.bias'] = torch.zeros(dims[i + 1], device=device)
+    sd['mapping.w_avg'] = torch.zeros(w_dim, device=device)
+    f1 = torch.tensor([1., 3., 3., 1.])
+    fir = (torch.outer(f1, f1) / 64.0).to(device)
+    for res, c in ch.items():
+        p = f'synthesis.b{res}.'
+        sd[p + 'resample_filter'] = fir
+        layers = []
+        if res == 4:
+            sd[p + 'const'] = randn(c, 4, 4)
+        else:
+            layers.append(('conv0', ch[res // 2]))
+        layers.append(('conv1', c))
+        for name, cin in layers:
+            q = p + name + '.'
+            sd[q + 'weight'] = randn(c, cin, 3, 3)
+            sd[q + 'bias'] = torch.zeros(c, device=device)
+            sd[q + 'noise_const'] = randn(res, res)
+            sd[q + 'noise_strength'] = torch.tensor(float(noise_strength), device=device)
+            sd[q + 'affine.weight'] = randn(cin, w_dim)
+            sd[q + 'affine.bias'] = torch.ones(cin, device=device)
+            sd[q + 'resample_filter'] = fir
+        q = p + 'torgb.'
+        sd[q + 'weight'] = randn(img_channels, c, 1, 1)
+        sd[q + 'bias'] = torch.zeros(img_channels, device=device)
+        sd[q + 'affine.weight'] = randn(c, w_dim)
+        sd[q + 'affine.bias'] = torch.ones(c, device=device)
+    return sd
+
+
+def infer_generator_kwargs(state):
+    """(img_resolution, img_channels, w_dim, z_dim) from a reference-named state dict."""
+    res = max(int(k.split('.')[1][1:]) for k in state if k.startswith('synthesis.b') and k.endswith('torgb.weight'))
+    tw = state[f'synthesis.b{res}.torgb.weight']
+    aw = state['synthesis.b4.conv1.affine.weight']
+    z_dim = state['mapping.fc0.weight'].shape[1] if 'mapping.fc0.weight' in state else aw.shape[1]
+    return dict(img_resolution=res, img_channels=tw.shape[0], w_dim=aw.shape[1], z_dim=z_dim)

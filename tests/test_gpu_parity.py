@@ -151,7 +151,7 @@ def test_latent_only_and_zero_steps():
     img, w_aug = eng.augment(wl['w0'], num_steps=4, w_pix=0.0, final_noise_mode='const')
     assert rel_l2(w_aug.cpu(), w_ref[:, 0]) < 1e-5
     assert rel_l2(img.cpu(), img_ref) < 1e-4
-    img0, w0 = eng.augment(wl['w0'], num_steps=0, final_noise_mode='const')
+    img0, w0 = eng.augment(wl['w0'], num_steps=0, w_pix=0.0, final_noise_mode='const')
     assert torch.equal(w0.cpu(), wl['w0'][:, 0])
 
 
@@ -195,3 +195,46 @@ def test_nearest_codes_bit_exact(shape):
     parts = [LatentBank(Y[:half].cuda(), 0).nearest(X.cuda(), k=4), LatentBank(Y[half:].cuda(), half).nearest(X.cuda(), k=4)]
     md, mi = merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
     assert torch.equal(mi.cpu(), i_ref)
+
+
+def test_plugin_api_end_to_end():
+    """create_augment(opt) -> set_input / forward / get_output / get_latent_* (reference README.md:66-86 usage),
+    synthetic mode; the result must equal the oracle loop started from the same inverted codes."""
+    import random as pyrandom
+
+    from latentaugment_b200.augments import create_augment
+    from latentaugment_b200.options.aug_options import AugOptions
+    from oracle import latent_aug as ola
+    from oracle import sg2
+    argv = ['--aug', 'latent', '--synthetic', '--batch_size', '4', '--img_resolution', '32', '--synthetic_channels', '2',
+            '--synthetic_channel_base', '2048', '--synthetic_channel_max', '64', '--synthetic_bank', '64', '--synthetic_img_bank', '8',
+            '--synthetic_codes', '16', '--opt_num_epochs', '3', '--no_log']
+    opt = AugOptions().parse(args={'p_thres': 0.0, 'w_lpips': 0.0, 'w_disc': 0.0, 'init_w': 'inv'}, argv=argv)
+    aug = create_augment(opt)
+    names = list(aug.stats_dataset_w.index)[:4]
+    data = {'A': torch.zeros(4, 1, 32, 32), 'B': torch.zeros(4, 1, 32, 32), 'A_paths': names, 'B_paths': names}
+    aug.set_input(data)
+    pyrandom.seed(3)
+    aug.forward()
+    out = aug.get_output()
+    assert out['A'].shape == (4, 1, 32, 32) and out['B'].shape == (4, 1, 32, 32) and out['A_paths'] == names
+    assert not out['A'].is_cuda and len(aug.stats_time) == 1 and aug.num_ws == 8
+    w_in, w_out = aug.get_latent_input()['w'], aug.get_latent_output()['w']
+    assert w_in.shape == (4, 512) and w_out.shape == (4, 512)
+    # oracle over the same generator parameters / banks / init codes
+    core = aug.latent_aug.module
+    G = sg2.Generator(img_resolution=32, img_channels=2, channel_base=2048, channel_max=64).eval().requires_grad_(False)
+    from latentaugment_b200.utils import synthetic
+    G.load_state_dict(synthetic.random_generator_state(img_resolution=32, img_channels=2, channel_base=2048, channel_max=64))
+    orc = ola.LatentAugOracle(G, core.W.cpu(), core.X.cpu(), num_epochs=3)
+    img_ref, w_ref = orc.forward(torch.from_numpy(w_in).reshape(4, 1, 512))
+    assert rel_l2(torch.from_numpy(w_out), w_ref[:, 0]) < 1e-3
+    ref = torch.cat([img_ref[:, 0:1], img_ref[:, 1:2]], 1)
+    got = torch.cat([out['A'], out['B']], 1)
+    e = rel_l2(got, ref)
+    print(f'\n[plugin api] rel_img={e:.3e}')
+    assert e < 1e-3          # noise_strength = 0 in synthetic mode, so the random final noise is immaterial
+    # p_thres = 1 (CLI default): never augments, passes the real pair through (reference latent_aug.py:241,268)
+    aug.p_thres = 1.0
+    aug.forward()
+    assert torch.equal(aug.get_output()['A'], data['A'])

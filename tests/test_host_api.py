@@ -1,0 +1,162 @@
+"""CPU tests of the host side: option parsing, plugin registry, criteria registry, the C-ABI
+library (loads; exports every symbol include/*.h declares -- no compute without a GPU), and the
+multi-process plumbing under gloo with world_size 2."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _opts(extra=(), args=None):
+    from latentaugment_b200.options.aug_options import AugOptions
+    argv = ['--aug', 'latent', '--synthetic', '--batch_size', '4', '--no_log'] + list(extra)
+    return AugOptions().parse(args=args, argv=argv)
+
+
+def test_options_defaults_match_reference():
+    """Flag names / defaults of reference augments/latent_aug.py:58-96 and options/base_options.py:28-39."""
+    opt = _opts()
+    ref = dict(gpu_ids_aug='0', img_resolution=256, truncation_psi=1.0, rand_aug=False, lower_bound_clip=False, step_img=20,
+               step_w=5, lpips_script='lpips_script', opt_num_epochs=10, opt_lr=0.01, init_w='random', crop_size_aug=64,
+               preprocess_aug='center_random_crop', w_pix=1.0, w_lpips=1.0, w_latent=1.0, w_disc=1.0, p_thres=1.0,
+               soft_aug=False, alpha=1.0, verbose_log=False, phase='train', load_size=256, dataset_mode='pelvis2.1')
+    for k, v in ref.items():
+        assert getattr(opt, k) == v, k
+    assert opt.gpu_ids == [0] and opt.isTrain is True
+    assert opt.name.startswith('experiment_name-n_imgs_0-opt_lr_0.01-opt_num_epochs_10-w_latent_1.0')
+
+
+def test_options_dict_overrides_like_reference():
+    opt = _opts(args={'p_thres': 0.0, 'opt_num_epochs': 6, 'opt_lr': 0.1, 'w_lpips': 0.0, 'w_disc': 0.0, 'init_w': 'inv', 'n_imgs': 7})
+    assert (opt.p_thres, opt.opt_num_epochs, opt.opt_lr, opt.w_lpips, opt.w_disc, opt.init_w, opt.n_imgs) == (0.0, 6, 0.1, 0.0, 0.0, 'inv', 7)
+    opt = _opts(['--rand_aug'], args={'truncation_psi': 0.5, 'opt_num_epochs': 3})
+    assert opt.truncation_psi == 0.5 and opt.opt_num_epochs == 10      # rand_aug ignores the loop overrides (base_options.py:118-122)
+    assert 'truncation_psi_0.5' in opt.name
+
+
+def test_plugin_registry():
+    from latentaugment_b200 import augments
+    from latentaugment_b200.augments.base_aug import BaseAugment
+    cls = augments.find_augment_using_name('latent')
+    assert cls.__name__ == 'LatentAugment' and issubclass(cls, BaseAugment)
+    assert augments.get_option_setter('latent') is cls.modify_commandline_options
+    with pytest.raises(ImportError):
+        augments.find_augment_using_name('geometric')          # out of scope
+
+
+def test_criteria_registry():
+    from latentaugment_b200.augments import criteria
+    opt = _opts(args={'w_lpips': 0.0, 'w_disc': 0.0})
+    c = criteria.create_criteria(opt)
+    assert sorted(c) == ['latent', 'pix'] and c['latent'].sign == -1.0 and c['pix'].weight == 1.0
+    with pytest.raises(NotImplementedError):
+        criteria.create_criteria(_opts())                      # default w_lpips = w_disc = 1 need unavailable networks
+
+
+def test_no_cpu_fallback():
+    from latentaugment_b200 import LatentAugmentError
+    from latentaugment_b200.augments import create_augment
+    if torch.cuda.is_available():
+        pytest.skip('needs a machine without a GPU')
+    opt = _opts(args={'w_lpips': 0.0, 'w_disc': 0.0})
+    with pytest.raises(LatentAugmentError):
+        create_augment(opt)
+
+
+def test_val_phase_passthrough():
+    from latentaugment_b200.augments import create_augment
+    opt = _opts(['--phase', 'val'])
+    aug = create_augment(opt)
+    a, b = torch.rand(4, 1, 8, 8), torch.rand(4, 1, 8, 8)
+    aug.set_input({'A': a, 'B': b, 'A_paths': ['x'] * 4, 'B_paths': ['x'] * 4})
+    aug.forward()
+    out = aug.get_output()
+    assert torch.equal(out['A'], a) and torch.equal(out['B'], b) and len(aug.stats_time) == 1
+
+
+def test_cabi_exports_every_declared_symbol():
+    from latentaugment_b200 import _build, _lib
+    lib_path = _build.build()
+    header = open(os.path.join(ROOT, 'include', 'latentaugment_b200.h')).read()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    declared = set(re.findall(r'\b(la_[a-z0-9_]+)\s*\(', header))
+    assert {'la_engine_create', 'la_augment', 'la_synthesis', 'la_mapping', 'la_nearest_codes', 'la_pairwise_sqdist'} <= declared
+    lib = ctypes.CDLL(lib_path)
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in the header but not exported'
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert _lib.load().la_version() == 100
+
+
+def test_synthetic_state_follows_reference_naming():
+    from latentaugment_b200.utils import synthetic
+    sd = synthetic.random_generator_state(img_resolution=32, img_channels=2, channel_base=2048, channel_max=64)
+    assert sd['synthesis.b4.const'].shape == (64, 4, 4)
+    assert sd['synthesis.b8.conv0.weight'].shape == (64, 64, 3, 3) and sd['synthesis.b8.conv0.affine.weight'].shape == (64, 512)
+    assert bool((sd['synthesis.b16.conv1.affine.bias'] == 1).all())            # legacy.py:183,189,195,199
+    assert sd['synthesis.b32.torgb.weight'].shape == (2, 64, 1, 1) and 'synthesis.b4.conv0.weight' not in sd
+    assert synthetic.infer_generator_kwargs(sd) == dict(img_resolution=32, img_channels=2, w_dim=512, z_dim=512)
+    from oracle import sg2                                                     # same module tree as the oracle generator
+    G = sg2.Generator(img_resolution=32, img_channels=2, channel_base=2048, channel_max=64)
+    assert set(G.state_dict()) == set(sd)
+
+
+def _merge_cpu(dist_, idx):
+    s, n, k = dist_.shape
+    d = dist_.permute(1, 0, 2).reshape(n, s * k)
+    i = idx.permute(1, 0, 2).reshape(n, s * k)
+    key = torch.argsort(i, dim=1, stable=True)
+    d, i = d.gather(1, key), i.gather(1, key)
+    order = torch.argsort(d, dim=1, stable=True)[:, :k]
+    return d.gather(1, order), i.gather(1, order)
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    from latentaugment_b200 import parallel
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    gen = torch.Generator().manual_seed(0)
+    Y = torch.randn([101, 16], generator=gen)
+    X = torch.randn([6, 16], generator=gen)
+    b, e = parallel.shard_range(101, rank, world)
+
+    def nearest(Xq, k):          # exact search on this rank's rows, global indices
+        D = torch.cdist(Xq, Y[b:e]).square()
+        d, i = torch.sort(D, dim=1, stable=True)
+        return d[:, :k].contiguous(), (i[:, :k] + b).contiguous()
+    xb, xe = parallel.shard_range(6, rank, world)
+    Xall = parallel.all_gather_queries(X[xb:xe].contiguous())
+    d, i = parallel.sharded_nearest_codes(nearest, Xall, 3, merge_fn=_merge_cpu)
+    D = torch.cdist(X, Y).square()
+    dr, ir = torch.sort(D, dim=1, stable=True)
+    ok = torch.equal(Xall, X) and torch.equal(i, ir[:, :3]) and torch.allclose(d, dr[:, :3])
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_sharded_nearest_codes_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
+
+
+def test_shard_range_covers_everything():
+    from latentaugment_b200.parallel import shard_range
+    for n in (1, 7, 128, 1000003):
+        for world in (1, 2, 3, 8):
+            r = [shard_range(n, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n and all(r[k][1] == r[k + 1][0] for k in range(world - 1))
