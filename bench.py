@@ -168,6 +168,7 @@ def main():
     ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32_parity'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile', action='store_true', help='short run for ncu: skips the e2e leg, the CPU baseline and the per-GEMM timing')
     ap.add_argument('--layers-out', default='', help='write the per-layer tap-GEMM timing table (JSON) here')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -241,6 +242,13 @@ def main():
     value = world * B / (ms * 1e-3)
 
     # ---- end to end through the plugin API: host dict in, host dict out
+    if args.profile:
+        clocks.stop(mark)
+        sys.stdout = real_stdout
+        if rank == 0:
+            print(json.dumps({'metric': 'augmented images/sec', 'value': value, 'unit': 'img/s', 'ms_per_step': ms,
+                              'gpu_launches': int(launches), 'note': 'profile mode (no e2e / roofline / cpu_baseline legs)'}))
+        return
     for i in range(2):
         aug.set_input(batch_data(i)); aug.forward(); aug.get_output()
     barrier()
