@@ -133,7 +133,7 @@ NearestLayout nearest_layout(int n, int m, int K) {
     L.Hq = (L.Hq + 7) / 8 * 8;                 // whole 8x16 query tiles
     L.rows_padded = L.Hq * 16;
     L.n_blocks = (m + 255) / 256;
-    L.ncand = L.n_blocks * kCand;
+    L.ncand = L.n_blocks * 2 * kCand;        // two epilogue groups per tile
     size_t off = 0;
     auto take = [&](size_t b) { off = (off + 1023) & ~size_t(1023); size_t o = off; off += b; return o; };
     L.off_xhi = take(static_cast<size_t>(L.rows_padded) * K * 2);

@@ -173,7 +173,7 @@ int plan(la_engine* e, char* ws, size_t* bytes_out) {
         e->conv.push_back(c);
         Rgb r{};
         r.res = res; r.cin = C; r.ws_idx = widx; r.p = g.torgb[b];
-        r.nparts = C / pick_bn(C);
+        r.nparts = 2 * (C / pick_bn(C));      // one toRGB partial per (column block, epilogue group)
         e->rgb.push_back(r);
     }
     for (size_t l = 0; l < e->conv.size(); ++l) {
@@ -487,7 +487,7 @@ int run_backward(la_engine* e, const la_augment_options& /*opt*/, cudaStream_t s
         LA(rgb_backward(r.g_img, r.parts, r.nparts, r.p.d_bias, g.img_channels, g.conv_clamp, B, r.res, r.g_rgb,
                         b > 0 ? e->rgb[b - 1].g_img : nullptr, s));
     }
-    LA(launch_tapgemm_simt(e->seed, e->seed_ops, s));
+    LA(launch_tapgemm_seed(e->seed, e->num_sms, s));
     e->launches += 2 + g.num_blocks;
     for (int l = L - 1; l >= 0; --l) LA(gemm(e, e->conv[l].bwd, e->conv[l].bwd_ops, s));
     LA(style_grad(e->table, B, e->s_cat, e->d_cat, e->red_s, e->red_d, e->red_rgb, e->g_s, s));
@@ -722,9 +722,9 @@ LA_API int la_debug_time_gemms(la_engine* e, int reps, float* h_ms, int* n_layer
     CU(cudaEventCreate(&b));
     cudaStream_t w = e->work;
     auto timed = [&](int idx, const TapGemmParams& P, const TapSimtOperands& ops, bool simt) -> int {
-        for (int warm = 0; warm < 2; ++warm) { int r = simt ? launch_tapgemm_simt(P, ops, w) : launch_tapgemm(P, e->num_sms, w); if (r) return r; }
+        for (int warm = 0; warm < 2; ++warm) { int r = simt ? launch_tapgemm_seed(P, e->num_sms, w) : launch_tapgemm(P, e->num_sms, w); if (r) return r; }
         cudaEventRecord(a, w);
-        for (int i = 0; i < reps; ++i) { int r = simt ? launch_tapgemm_simt(P, ops, w) : launch_tapgemm(P, e->num_sms, w); if (r) return r; }
+        for (int i = 0; i < reps; ++i) { int r = simt ? launch_tapgemm_seed(P, e->num_sms, w) : launch_tapgemm(P, e->num_sms, w); if (r) return r; }
         cudaEventRecord(b, w);
         cudaError_t ce = cudaEventSynchronize(b);
         if (ce != cudaSuccess) return static_cast<int>(ce);
@@ -737,7 +737,7 @@ LA_API int la_debug_time_gemms(la_engine* e, int reps, float* h_ms, int* n_layer
         LA(timed(l, e->conv[l].fwd, e->conv[l].fwd_ops, false));
         LA(timed(L + l, e->conv[l].bwd, e->conv[l].bwd_ops, false));
     }
-    LA(timed(2 * L, e->seed, e->seed_ops, true));
+    LA(timed(2 * L, e->seed, e->seed_ops, true));   // 'simt' flag selects the seed launcher here
     cudaEventDestroy(a);
     cudaEventDestroy(b);
     return 0;

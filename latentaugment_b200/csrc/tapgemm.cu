@@ -14,19 +14,22 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                       // 64 bf16 = one 128-byte swizzle row
 constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
-constexpr int kThreads = 256;                     // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps4-7 epilogue
-constexpr int kEpiThreads = 128;
-constexpr int kRedKinds = 5;                      // red_s, red_d, red_rgb[3]
+constexpr int kThreads = 384;                     // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-11 epilogue
+constexpr int kEpiThreads = 256;                  // two epilogue warpgroups; warp w owns TMEM lanes 32*(w%4)..+31
+constexpr int kStileStride = 68;                  // floats per row of the 128x64 transpose tile (272 B: conflict-free both ways)
+constexpr int kRegsProducer = 56, kRegsEpilogue = 224;   // setmaxnreg: 128*56 + 256*224 = 64512 <= 65536
 
-template <int BN>
+template <int BN, int EPI>
 struct Cfg {
     static constexpr int kBBytes = BN * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-    static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator stages
-    static constexpr int kNCh = BN / 32;
-    static constexpr int kRaccBytes = kRedKinds * kNCh * kEpiThreads * 4;   // per-thread reduction accumulators
-    static constexpr int kSmemBytes = kStages * kStageBytes + kRaccBytes + 256 /*barriers*/ + 1024 /*align slack*/;
+    static constexpr int kStages = EPI == kEpiBwd ? (BN == 256 ? 3 : (BN == 128 ? 5 : 7)) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
+    static constexpr int kTmemCols = 2 * BN;      // two accumulator stages
+    static constexpr int kStileBytes = EPI == kEpiBwd ? kBlockM * kStileStride * 4 : 0;
+    static constexpr int kFlushBytes = EPI == kEpiBwd ? 5 * BN * 4 : 0;
+    static constexpr int kRowInfoBytes = EPI == kEpiBwd ? kBlockM * 4 : 0;
+    static constexpr int kEpiSmemBytes = kStileBytes + kFlushBytes + kRowInfoBytes;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiSmemBytes + 256 /*barriers*/ + 1024 /*align slack*/;
 };
 
 struct TileCoord {
@@ -54,7 +57,7 @@ __device__ __forceinline__ void tile_range(int total, int& begin, int& end) {
     end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * total / gridDim.x);
 }
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -125,24 +128,10 @@ __device__ __forceinline__ void load_f32x32(const float* p, float (&v)[32]) {
     }
 }
 
-// Transposing warp reduction: on return lane L holds sum over lanes of v[L].  31 shuffles.
-__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        const bool up = (lane & off) != 0;
-#pragma unroll
-        for (int i = 0; i < off; ++i) {
-            const float send = up ? v[i] : v[i + off];
-            const float keep = up ? v[i + off] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
-    }
-    return v[0];
-}
 
 // ------------------------------------------------------------------------------------
-// Epilogue shared by the tensor-core kernel and its SIMT twin.  128 threads, thread = one
-// accumulator row (pixel), 32 columns per chunk.
+// Epilogues shared by the tensor-core kernel and its SIMT twin.  256 threads: thread t owns
+// accumulator row (t & 127) of the 32-column chunks with (chunk & 1) == (t >> 7).
 
 struct RowCtx {
     bool valid;
@@ -168,89 +157,28 @@ __device__ __forceinline__ RowCtx make_row(const TapGemmParams& P, const TileCoo
     return r;
 }
 
-// Reduction bookkeeping: per-thread accumulators in shared memory, keyed on (sample, column
-// block); flushed to global memory with one atomicAdd per (kind, column) when the key changes.
-template <int BN>
-__device__ __forceinline__ void racc_flush(const TapGemmParams& P, float* sracc, int key, int tid) {
-    constexpr int NCH = BN / 32;
-    epi_bar();
-    if (key >= 0) {
-        const int n = key / P.n_blocks, nblk = key - n * P.n_blocks;
-        const int kinds = P.bwd_last ? 1 : (P.g_rgb ? kRedKinds : 2);
-        for (int e = tid; e < kinds * NCH * 32; e += kEpiThreads) {
-            const int L = e & 31, ch = (e >> 5) % NCH, kind = e / (32 * NCH);
-            float* base = sracc + (kind * NCH + ch) * kEpiThreads + L;
-            const float s = (base[0] + base[32]) + (base[64] + base[96]);
-            base[0] = base[32] = base[64] = base[96] = 0.f;
-            const long long col = static_cast<long long>(n) * P.n_total + nblk * BN + ch * 32 + L;
-            if (kind == 0) atomicAdd(P.red_s + col, s);
-            else if (kind == 1) atomicAdd(P.red_d + col, s);
-            else atomicAdd(P.red_rgb + static_cast<long long>(kind - 2) * P.batch * P.n_total + col, s);
-        }
-    }
-    epi_bar();
-}
-
-template <int BN>
-__device__ __forceinline__ void racc_add(const TapGemmParams& P, float* sracc, int kind, int ch, int tid, int lane,
-                                         float (&prod)[32], bool smem_mode, bool warp_uniform, const RowCtx& rc,
-                                         int col0) {
-    constexpr int NCH = BN / 32;
-    float* gbase = kind == 0 ? P.red_s : (kind == 1 ? P.red_d : P.red_rgb + static_cast<long long>(kind - 2) * P.batch * P.n_total);
-    if (warp_uniform) {
-        const float s = warp_transpose_sum(prod, lane);
-        if (smem_mode) {
-            sracc[(kind * NCH + ch) * kEpiThreads + tid] += s;
-        } else {
-            const int n = __shfl_sync(0xffffffffu, rc.n, 0);
-            const bool any = __any_sync(0xffffffffu, rc.valid);
-            if (any && n < P.batch) atomicAdd(gbase + static_cast<long long>(n) * P.n_total + col0 + lane, s);
-        }
-    } else if (rc.valid) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(gbase + static_cast<long long>(rc.n) * P.n_total + col0 + j, prod[j]);
-    }
-}
-
+// ---- row-owner epilogues: raw store, forward activation, top-k
 template <int BN, int EPI, class LoadChunk>
-__device__ __forceinline__ void epilogue_tile(const TapGemmParams& P, const TileCoord& tc, int tid, float* sracc,
-                                              int& cur_key, LoadChunk&& load_chunk) {
+__device__ __forceinline__ void rowowner_tile(const TapGemmParams& P, const TileCoord& tc, int t, LoadChunk&& load_chunk) {
     constexpr int NCH = BN / 32;
-    const int lane = tid & 31;
-    const RowCtx rc = make_row(P, tc, tid);
-    const int box_px = P.th * P.tw;
-    const bool warp_uniform = box_px >= 32;          // the 32 rows of a warp belong to one sample
-    const bool smem_mode = P.nb == 1;                // the whole tile belongs to one sample
-
-    if (EPI == kEpiBwd && smem_mode) {
-        const int key = tc.n0 * P.n_blocks + tc.nblk;
-        if (key != cur_key) {
-            if (cur_key >= 0) racc_flush<BN>(P, sracc, cur_key, tid);
-            cur_key = key;
-        }
-    }
-
+    const int eg = t >> 7;
+    const RowCtx rc = make_row(P, tc, t & 127);
     float nz = 0.f;
-    float4 grgb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (rc.valid) {
-        if (EPI == kEpiFwd && P.noise) nz = __ldg(P.noise + rc.n * P.noise_stride_n + rc.px_in_img) * P.noise_scale;
-        if (EPI == kEpiBwd && P.noise_prev) nz = __ldg(P.noise_prev + rc.n * P.noise_prev_stride_n + rc.px_in_img) * P.noise_prev_scale;
-        if (EPI == kEpiBwd && P.g_rgb) grgb = __ldg(P.g_rgb + rc.pix);
-    }
+    if (EPI == kEpiFwd && rc.valid && P.noise) nz = __ldg(P.noise + rc.n * P.noise_stride_n + rc.px_in_img) * P.noise_scale;
     float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
     float best_s[8];
     int best_i[8];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) { best_s[t] = __int_as_float(0x7f800000); best_i[t] = -1; }
+    for (int k = 0; k < 8; ++k) { best_s[k] = __int_as_float(0x7f800000); best_i[k] = -1; }
+    const bool tk_valid = rc.valid && rc.pix < P.n_queries;
 
 #pragma unroll 1
-    for (int ch = 0; ch < NCH; ++ch) {
+    for (int ch = eg; ch < NCH; ch += 2) {
         float acc[32];
         load_chunk(ch, acc);
         const int col0 = tc.nblk * BN + ch * 32;
         const long long eoff = rc.pix * P.n_total + col0;             // element offset in [pixel][N] tensors
         const long long coff = static_cast<long long>(rc.n) * P.n_total + col0;   // offset in [batch][N] tensors
-
         if constexpr (EPI == kEpiRawF32) {
             if (rc.valid) {
                 float4* dst = reinterpret_cast<float4*>(P.raw_out + eoff);
@@ -258,7 +186,7 @@ __device__ __forceinline__ void epilogue_tile(const TapGemmParams& P, const Tile
                 for (int j = 0; j < 8; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
             }
         } else if constexpr (EPI == kEpiTopK) {
-            if (rc.valid && rc.pix < P.n_queries) {
+            if (tk_valid) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int code = col0 + j;
@@ -267,10 +195,10 @@ __device__ __forceinline__ void epilogue_tile(const TapGemmParams& P, const Tile
                         int id = code;
                         if (sc < best_s[7]) {
 #pragma unroll
-                            for (int t = 0; t < 8; ++t) {       // sorted insertion, ascending
-                                if (sc < best_s[t]) {
-                                    const float ts = best_s[t]; const int ti = best_i[t];
-                                    best_s[t] = sc; best_i[t] = id;
+                            for (int k = 0; k < 8; ++k) {       // sorted insertion, ascending
+                                if (sc < best_s[k]) {
+                                    const float ts = best_s[k]; const int ti = best_i[k];
+                                    best_s[k] = sc; best_i[k] = id;
                                     sc = ts; id = ti;
                                 }
                             }
@@ -308,91 +236,195 @@ __device__ __forceinline__ void epilogue_tile(const TapGemmParams& P, const Tile
                     store_bf16x32(P.xs_hi, P.split ? P.xs_lo : nullptr, eoff, acc);
                 }
             }
-        } else {   // kEpiBwd
-            float xp[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) xp[j] = 0.f;
-            if (rc.valid)
-                load_bf16x32(P.xp_hi, P.split ? P.xp_lo : nullptr,
-                             static_cast<long long>(rc.n) * P.xp_stride_n + rc.px_in_img * P.n_total + col0, xp);
-            float prod[32];
-            // (1) style-gradient reduction: sum_px g_xs * x_{l-1}
-#pragma unroll
-            for (int j = 0; j < 32; ++j) prod[j] = rc.valid ? acc[j] * xp[j] : 0.f;
-            racc_add<BN>(P, sracc, 0, ch, tid, lane, prod, smem_mode, warp_uniform, rc, col0);
-            if (!P.bwd_last) {
-                float sc[32];
-                if (rc.valid) {
-                    load_f32x32(P.s_cur + coff, sc);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[j] *= sc[j];      // g_x (conv part)
-                    if (P.g_rgb) {
-                        const float4* rw = P.rgbw_prev + coff;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float4 w4 = __ldg(rw + j);
-                            acc[j] += grgb.x * w4.x + grgb.y * w4.y + grgb.z * w4.z;
-                        }
-                    }
-                    // activation backward of layer l-1 (decided by its saved output) and y recovery
-                    load_f32x32(P.bias_prev + col0, sc);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float out = xp[j];
-                        const bool pos = out > 0.f;
-                        float gz = acc[j] * P.act_gain * (pos ? 1.f : P.act_slope);
-                        if (P.act_clamp >= 0.f && !(fabsf(out) < P.act_clamp)) gz = 0.f;
-                        const float z = pos ? out / P.act_gain : out / (P.act_gain * P.act_slope);
-                        prod[j] = gz * (z - nz - sc[j]);
-                        acc[j] = gz;
-                    }
-                    load_f32x32(P.demod_prev + coff, sc);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[j] *= sc[j];      // g_y of layer l-1
-                    store_bf16x32(P.gy_hi, P.split ? P.gy_lo : nullptr, eoff, acc);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) prod[j] = 0.f;
-                }
-                racc_add<BN>(P, sracc, 1, ch, tid, lane, prod, smem_mode, warp_uniform, rc, col0);
-                if (P.g_rgb) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) prod[j] = xp[j] * grgb.x;
-                    racc_add<BN>(P, sracc, 2, ch, tid, lane, prod, smem_mode, warp_uniform, rc, col0);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) prod[j] = xp[j] * grgb.y;
-                    racc_add<BN>(P, sracc, 3, ch, tid, lane, prod, smem_mode, warp_uniform, rc, col0);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) prod[j] = xp[j] * grgb.z;
-                    racc_add<BN>(P, sracc, 4, ch, tid, lane, prod, smem_mode, warp_uniform, rc, col0);
-                }
-            }
         }
     }
-    if (EPI == kEpiTopK && rc.valid && rc.pix < P.n_queries) {
-        const long long base = (rc.pix * P.n_blocks + tc.nblk) * P.topk;
+    if (EPI == kEpiTopK && tk_valid) {
+        const long long base = ((rc.pix * P.n_blocks + tc.nblk) * 2 + eg) * P.topk;
 #pragma unroll
-        for (int t = 0; t < 8; ++t)
-            if (t < P.topk) { P.cand_score[base + t] = best_s[t]; P.cand_idx[base + t] = best_i[t]; }
+        for (int k = 0; k < 8; ++k)
+            if (k < P.topk) { P.cand_score[base + k] = best_s[k]; P.cand_idx[base + k] = best_i[k]; }
     }
-    if (EPI == kEpiFwd && P.rgbw && rc.valid)
-        P.rgb_part[static_cast<long long>(tc.nblk) * P.batch * P.OH * P.OW + rc.pix] = make_float4(rgb0, rgb1, rgb2, 0.f);
+    if (EPI == kEpiFwd && P.rgbw && rc.valid)     // one partial per (column block, epilogue group): summed in fixed order later
+        P.rgb_part[static_cast<long long>(tc.nblk * 2 + eg) * P.batch * P.OH * P.OW + rc.pix] = make_float4(rgb0, rgb1, rgb2, 0.f);
+}
+
+// ---- column-owner backward epilogue.
+// Phase A (row owners): TMEM -> registers -> 128x64 fp32 tile in shared memory.  Phase B: thread
+// (cp = t & 31, rg = t >> 5) owns columns 2cp, 2cp+1 of the chunk and rows rg*16..+15, so the
+// per-column coefficients sit in registers, global accesses are 128-byte coalesced rows and the
+// style-gradient column sums are plain per-thread accumulations (10 registers per 64-column chunk).
+template <int BN>
+struct BwdState {
+    float racc[BN / 64][10];     // (red_s, red_d, red_rgb0..2) x 2 columns, per 64-column chunk
+    int key;                      // (sample, column block) the accumulators belong to, -1 = empty
+};
+
+template <int BN>
+__device__ __forceinline__ void bwd_state_init(BwdState<BN>& st) {
+#pragma unroll
+    for (int c = 0; c < BN / 64; ++c)
+#pragma unroll
+        for (int k = 0; k < 10; ++k) st.racc[c][k] = 0.f;
+    st.key = -1;
+}
+
+__device__ __forceinline__ float* red_base(const TapGemmParams& P, int kind) {
+    return kind == 0 ? P.red_s : (kind == 1 ? P.red_d : P.red_rgb + static_cast<long long>(kind - 2) * P.batch * P.n_total);
 }
 
 template <int BN>
-__device__ __forceinline__ void racc_init(float* sracc, int tid) {
-    for (int e = tid; e < kRedKinds * (BN / 32) * kEpiThreads; e += kEpiThreads) sracc[e] = 0.f;
-    epi_bar();
+__device__ __forceinline__ void bwd_flush(const TapGemmParams& P, BwdState<BN>& st, int t, float* sflush) {
+    constexpr int NCH = BN / 64;
+    const int cp = t & 31, rg = t >> 5;
+    const int kinds = P.bwd_last ? 1 : (P.g_rgb ? 5 : 2);
+    const int n = st.key / P.n_blocks, nblk = st.key - n * P.n_blocks;
+    if (P.nb == 1) {
+        // every thread of the CTA holds the same key: reduce the 8 row groups through shared memory
+#pragma unroll 1
+        for (int round = 0; round < 8; ++round) {
+            if (rg == round) {
+#pragma unroll
+                for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                    for (int k = 0; k < 10; ++k) {
+                        if ((k >> 1) < kinds) {
+                            float* p = sflush + (k >> 1) * BN + c * 64 + 2 * cp + (k & 1);
+                            *p = (round == 0 ? 0.f : *p) + st.racc[c][k];
+                        }
+                    }
+            }
+            epi_bar();
+        }
+        for (int e = t; e < kinds * BN; e += kEpiThreads) {
+            const int kind = e / BN, col = e - kind * BN;
+            atomicAdd(red_base(P, kind) + static_cast<long long>(n) * P.n_total + nblk * BN + col, sflush[e]);
+        }
+        epi_bar();
+    } else if (n < P.batch) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int k = 0; k < 10; ++k)
+                if ((k >> 1) < kinds)
+                    atomicAdd(red_base(P, k >> 1) + static_cast<long long>(n) * P.n_total + nblk * BN + c * 64 + 2 * cp + (k & 1), st.racc[c][k]);
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int k = 0; k < 10; ++k) st.racc[c][k] = 0.f;
+}
+
+template <int BN, bool kHaveAcc, class LoadChunk, class Release>
+__device__ __forceinline__ void bwd_tile(const TapGemmParams& P, const TileCoord& tc, int t, float* stile, float* sflush, int* rowinfo,
+                                         BwdState<BN>& st, LoadChunk&& load_chunk, Release&& release_acc) {
+    constexpr int NCH = BN / 64;
+    const int row = t & 127, eg = t >> 7;        // phase A
+    const int cp = t & 31, rg = t >> 5;          // phase B
+    const int box_px = P.th * P.tw;
+    const int ni_rg = (rg * 16) / box_px;
+    const int n_rg = tc.n0 + ni_rg;
+    const bool n_ok = ni_rg < P.nb && n_rg < P.batch;
+    const int new_key = (P.nb == 1 ? tc.n0 : n_rg) * P.n_blocks + tc.nblk;
+    if (new_key != st.key) {
+        if (st.key >= 0) bwd_flush<BN>(P, st, t, sflush);
+        st.key = new_key;
+    }
+    if (eg == 0) {
+        const RowCtx rc = make_row(P, tc, row);
+        rowinfo[row] = rc.valid ? static_cast<int>(rc.px_in_img) : -1;
+    }
+    const float inv_gain = 1.f / P.act_gain, inv_gain_slope = 1.f / (P.act_gain * P.act_slope);
+    const long long img_px = static_cast<long long>(P.OH) * P.OW;
+    const unsigned* xph = reinterpret_cast<const unsigned*>(P.xp_hi);
+    const unsigned* xpl = P.split ? reinterpret_cast<const unsigned*>(P.xp_lo) : nullptr;
+    unsigned* gyh = reinterpret_cast<unsigned*>(P.gy_hi);
+    unsigned* gyl = P.split ? reinterpret_cast<unsigned*>(P.gy_lo) : nullptr;
+
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        if (kHaveAcc) {
+            float acc[32];
+            load_chunk(c * 2 + eg, acc);
+            float4* dst = reinterpret_cast<float4*>(stile + row * kStileStride + eg * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+            if (c == NCH - 1) release_acc();
+        }
+        epi_bar();
+        const int col = tc.nblk * BN + c * 64 + 2 * cp;
+        const long long coff = static_cast<long long>(n_rg) * P.n_total + col;
+        float2 sc = make_float2(0.f, 0.f), dm = sc, bs = sc;
+        float4 rw0 = make_float4(0.f, 0.f, 0.f, 0.f), rw1 = rw0;
+        if (n_ok && !P.bwd_last) {
+            sc = __ldg(reinterpret_cast<const float2*>(P.s_cur + coff));
+            dm = __ldg(reinterpret_cast<const float2*>(P.demod_prev + coff));
+            bs = __ldg(reinterpret_cast<const float2*>(P.bias_prev + col));
+            if (P.g_rgb) { rw0 = __ldg(P.rgbw_prev + coff); rw1 = __ldg(P.rgbw_prev + coff + 1); }
+        }
+        float r[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) r[k] = 0.f;
+        if (n_ok) {
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+                const int rr = rg * 16 + i;
+                const int pxi = rowinfo[rr];
+                if (pxi < 0) continue;
+                float2 a = make_float2(0.f, 0.f);
+                if (kHaveAcc) a = *reinterpret_cast<const float2*>(stile + rr * kStileStride + 2 * cp);
+                const long long xoff = (static_cast<long long>(n_rg) * P.xp_stride_n + static_cast<long long>(pxi) * P.n_total + col) >> 1;
+                const unsigned xu = __ldg(xph + xoff);
+                float x0 = bf16lo_f(xu), x1 = bf16hi_f(xu);
+                if (xpl) { const unsigned xl = __ldg(xpl + xoff); x0 += bf16lo_f(xl); x1 += bf16hi_f(xl); }
+                r[0] = fmaf(a.x, x0, r[0]);
+                r[1] = fmaf(a.y, x1, r[1]);
+                if (!P.bwd_last) {
+                    const long long pix = static_cast<long long>(n_rg) * img_px + pxi;
+                    float g0 = a.x * sc.x, g1 = a.y * sc.y;
+                    if (P.g_rgb) {
+                        const float4 g = __ldg(P.g_rgb + pix);
+                        g0 += g.x * rw0.x + g.y * rw0.y + g.z * rw0.z;
+                        g1 += g.x * rw1.x + g.y * rw1.y + g.z * rw1.z;
+                        r[4] = fmaf(x0, g.x, r[4]); r[5] = fmaf(x1, g.x, r[5]);
+                        r[6] = fmaf(x0, g.y, r[6]); r[7] = fmaf(x1, g.y, r[7]);
+                        r[8] = fmaf(x0, g.z, r[8]); r[9] = fmaf(x1, g.z, r[9]);
+                    }
+                    const float nz = P.noise_prev ? __ldg(P.noise_prev + n_rg * P.noise_prev_stride_n + pxi) * P.noise_prev_scale : 0.f;
+                    // activation backward of layer l-1 decided by its saved output; y recovered from it
+                    const bool p0 = x0 > 0.f, p1 = x1 > 0.f;
+                    float gz0 = g0 * P.act_gain * (p0 ? 1.f : P.act_slope);
+                    float gz1 = g1 * P.act_gain * (p1 ? 1.f : P.act_slope);
+                    if (P.act_clamp >= 0.f) {
+                        if (!(fabsf(x0) < P.act_clamp)) gz0 = 0.f;
+                        if (!(fabsf(x1) < P.act_clamp)) gz1 = 0.f;
+                    }
+                    const float z0 = x0 * (p0 ? inv_gain : inv_gain_slope), z1 = x1 * (p1 ? inv_gain : inv_gain_slope);
+                    r[2] = fmaf(gz0, z0 - nz - bs.x, r[2]);
+                    r[3] = fmaf(gz1, z1 - nz - bs.y, r[3]);
+                    const float y0 = gz0 * dm.x, y1 = gz1 * dm.y;
+                    const long long goff = (pix * P.n_total + col) >> 1;
+                    gyh[goff] = pack_bf16(y0, y1);
+                    if (gyl) gyl[goff] = pack_bf16(y0 - bf16_round(y0), y1 - bf16_round(y1));
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 10; ++k) st.racc[c][k] += r[k];
+        epi_bar();           // the tile / rowinfo may be overwritten from here on
+    }
 }
 
 // ------------------------------------------------------------------------------------
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams P) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, EPI>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float* sracc = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes + C::kRaccBytes);
+    uint8_t* epi_smem = smem + C::kStages * C::kStageBytes;
+    float* stile = reinterpret_cast<float*>(epi_smem);
+    float* sflush = reinterpret_cast<float*>(epi_smem + C::kStileBytes);
+    int* rowinfo = reinterpret_cast<int*>(epi_smem + C::kStileBytes + C::kFlushBytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + C::kEpiSmemBytes);
     uint64_t* empty_bar = full_bar + C::kStages;
     uint64_t* tfull_bar = empty_bar + C::kStages;
     uint64_t* tempty_bar = tfull_bar + 2;
@@ -415,7 +447,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], 4);
+            mbar_init(&tempty_bar[a], kEpiThreads / 32);
         }
         fence_barrier_init();
     }
@@ -427,81 +459,93 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
 
     const uint32_t a_tx_bytes = static_cast<uint32_t>(P.nb * P.th * P.tw) * 128u;
 
-    if (warp == 0 && lane == 0) {
-        // ------------------------------------------------------------------ TMA producer
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int t = t_begin; t < t_end; ++t) {
-            const TileCoord tc = decode_tile(P, t);
-            const TapProblem& pr = P.prob[tc.prob];
-            for (int ti = 0; ti < pr.ntaps; ++ti) {
-                const Tap tap = P.taps[pr.tap_begin + ti];
-                const CUtensorMap* amap = &P.a_map[tap.src];
-                for (int kc = 0; kc < P.kchunks; ++kc) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1, P.err_flag, 1);
-                    uint8_t* sa = smem + stage * C::kStageBytes;
-                    mbar_expect_tx(&full_bar[stage], a_tx_bytes + C::kBBytes);
-                    tma_load_4d(sa, amap, &full_bar[stage], kc * kBlockK, tc.w0 + tap.dx, tc.h0 + tap.dy, tc.n0);
-                    tma_load_3d(sa + kABytes, &P.b_map, &full_bar[stage], kc * kBlockK, tc.nblk * BN, tap.widx);
-                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+    if (warp < 4) {
+        setmaxnreg_dec<kRegsProducer>();
+        if (warp == 0 && lane == 0) {
+            // ---------------------------------------------------------------- TMA producer
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = t_begin; t < t_end; ++t) {
+                const TileCoord tc = decode_tile(P, t);
+                const TapProblem& pr = P.prob[tc.prob];
+                for (int ti = 0; ti < pr.ntaps; ++ti) {
+                    const Tap tap = P.taps[pr.tap_begin + ti];
+                    const CUtensorMap* amap = &P.a_map[tap.src];
+                    for (int kc = 0; kc < P.kchunks; ++kc) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1, P.err_flag, 1);
+                        uint8_t* sa = smem + stage * C::kStageBytes;
+                        mbar_expect_tx(&full_bar[stage], a_tx_bytes + C::kBBytes);
+                        tma_load_4d(sa, amap, &full_bar[stage], kc * kBlockK, tc.w0 + tap.dx, tc.h0 + tap.dy, tc.n0);
+                        tma_load_3d(sa + kABytes, &P.b_map, &full_bar[stage], kc * kBlockK, tc.nblk * BN, tap.widx);
+                        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                    }
                 }
             }
-        }
-    } else if (warp == 1 && lane == 0) {
-        // ------------------------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN);
-        int stage = 0;
-        uint32_t phase = 0;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int t = t_begin; t < t_end; ++t) {
-            const TileCoord tc = decode_tile(P, t);
-            const int ksteps = P.prob[tc.prob].ntaps * P.kchunks;
-            mbar_wait(&tempty_bar[acc], acc_phase ^ 1, P.err_flag, 2);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-            for (int ks = 0; ks < ksteps; ++ks) {
-                mbar_wait(&full_bar[stage], phase, P.err_flag, 3);
+        } else if (warp == 1 && lane == 0) {
+            // ---------------------------------------------------------------- MMA issuer
+            constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int t = t_begin; t < t_end; ++t) {
+                const TileCoord tc = decode_tile(P, t);
+                const int ksteps = P.prob[tc.prob].ntaps * P.kchunks;
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1, P.err_flag, 2);
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
-                const uint64_t adesc = make_sw128_kmajor_desc(sa);
-                const uint64_t bdesc = make_sw128_kmajor_desc(sa + kABytes);
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    mbar_wait(&full_bar[stage], phase, P.err_flag, 3);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+                    const uint64_t adesc = make_sw128_kmajor_desc(sa);
+                    const uint64_t bdesc = make_sw128_kmajor_desc(sa + kABytes);
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k)
-                    umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
-                              (ks | k) != 0 ? 1u : 0u);
-                umma_commit(&empty_bar[stage]);
-                if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                    for (int k = 0; k < kBlockK / 16; ++k)
+                        umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                                  (ks | k) != 0 ? 1u : 0u);
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            umma_commit(&tfull_bar[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-    } else if (warp >= 4) {
-        // ------------------------------------------------------------------ epilogue (128 threads)
-        const int q = warp - 4;               // TMEM lane quarter == warp % 4
-        const int tid = q * 32 + lane;
+    } else {
+        // -------------------------------------------------------------------- epilogue (256 threads)
+        setmaxnreg_inc<kRegsEpilogue>();
+        const int t = threadIdx.x - 128;
+        const int q = warp & 3;               // TMEM lane quarter
         int acc = 0;
         uint32_t acc_phase = 0;
-        int cur_key = -1;
-        if (EPI == kEpiBwd) racc_init<BN>(sracc, tid);
-        for (int t = t_begin; t < t_end; ++t) {
-            const TileCoord tc = decode_tile(P, t);
+        BwdState<BN> st;
+        if (EPI == kEpiBwd) bwd_state_init<BN>(st);
+        for (int tile = t_begin; tile < t_end; ++tile) {
+            const TileCoord tc = decode_tile(P, tile);
             mbar_wait(&tfull_bar[acc], acc_phase, P.err_flag, 4);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
-            epilogue_tile<BN, EPI>(P, tc, tid, sracc, cur_key, [&](int ch, float (&v)[32]) {
+            auto load_chunk = [&](int ch, float (&v)[32]) {
                 uint32_t u[32];
                 tmem_ld32(t_addr + ch * 32, u);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]);
-            });
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            };
+            auto release = [&]() {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            };
+            if constexpr (EPI == kEpiBwd) {
+                bwd_tile<BN, true>(P, tc, t, stile, sflush, rowinfo, st, load_chunk, release);
+            } else {
+                rowowner_tile<BN, EPI>(P, tc, t, load_chunk);
+                release();
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (EPI == kEpiBwd && cur_key >= 0) racc_flush<BN>(P, sracc, cur_key, tid);
+        if (EPI == kEpiBwd && st.key >= 0) bwd_flush<BN>(P, st, t, sflush);
     }
 
     tc_fence_before();
@@ -510,30 +554,35 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
 }
 
 // ------------------------------------------------------------------------------------
-// SIMT twin: 128 threads, same tile walk and the same epilogue; the accumulator row is
-// computed by brute force (zero when the problem has no taps: the backward-chain seed).
+// SIMT twin: 256 threads, same tile walk and the same epilogue code; the accumulator chunk is
+// computed by brute force.  Debug cross-check of the tensor-core path (tests), never a fallback.
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kEpiThreads) tapgemm_simt_kernel(const __grid_constant__ TapGemmParams P,
                                                                    const TapSimtOperands ops) {
-    __shared__ float sracc[kRedKinds * (BN / 32) * kEpiThreads];
-    const int tid = threadIdx.x;
+    __shared__ __align__(16) float stile[EPI == kEpiBwd ? kBlockM * kStileStride : 4];
+    __shared__ float sflush[EPI == kEpiBwd ? 5 * BN : 1];
+    __shared__ int rowinfo[kBlockM];
+    const int t = threadIdx.x;
     const int total_tiles = P.m_tiles * P.n_blocks;
     int t_begin, t_end;
     tile_range(total_tiles, t_begin, t_end);
-    int cur_key = -1;
-    if (EPI == kEpiBwd) racc_init<BN>(sracc, tid);
+    BwdState<BN> st;
+    if (EPI == kEpiBwd) bwd_state_init<BN>(st);
     const int K = P.kchunks * kBlockK;
     const int box_px = P.th * P.tw;
-    for (int t = t_begin; t < t_end; ++t) {
-        const TileCoord tc = decode_tile(P, t);
+    for (int tile = t_begin; tile < t_end; ++tile) {
+        const TileCoord tc = decode_tile(P, tile);
         const TapProblem& pr = P.prob[tc.prob];
-        const int ni = tid / box_px, rem = tid - ni * box_px;
+        const int row = t & 127;
+        const int ni = row / box_px, rem = row - ni * box_px;
         const int n = tc.n0 + ni, h = tc.h0 + rem / P.tw, w = tc.w0 + rem % P.tw;
         const bool in_box = ni < P.nb && n < P.batch;
-        epilogue_tile<BN, EPI>(P, tc, tid, sracc, cur_key, [&](int ch, float (&v)[32]) {
+        auto load_chunk = [&](int ch, float (&v)[32]) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
             if (!in_box) return;
+            const int rows_total = EPI == kEpiTopK ? P.n_codes : P.n_total;
+            const int jmax = rows_total - (tc.nblk * BN + ch * 32);
             for (int ti = 0; ti < pr.ntaps; ++ti) {
                 const Tap tap = P.taps[pr.tap_begin + ti];
                 const int hh = h + tap.dy, ww = w + tap.dx;
@@ -541,9 +590,7 @@ __global__ void __launch_bounds__(kEpiThreads) tapgemm_simt_kernel(const __grid_
                 const __nv_bfloat16* arow = reinterpret_cast<const __nv_bfloat16*>(ops.a_ptrs[tap.src]) +
                                             n * ops.a_sn + hh * ops.a_sh + ww * ops.a_sw;
                 const __nv_bfloat16* wmat = reinterpret_cast<const __nv_bfloat16*>(ops.w) +
-                                            (static_cast<long long>(tap.widx) * (EPI == kEpiTopK ? P.n_codes : P.n_total) + tc.nblk * BN + ch * 32) * K;
-                const int rows_total = EPI == kEpiTopK ? P.n_codes : P.n_total;
-                const int jmax = rows_total - (tc.nblk * BN + ch * 32);
+                                            (static_cast<long long>(tap.widx) * rows_total + tc.nblk * BN + ch * 32) * K;
                 for (int k = 0; k < K; ++k) {
                     const float a = __bfloat162float(arow[k]);
 #pragma unroll
@@ -551,9 +598,29 @@ __global__ void __launch_bounds__(kEpiThreads) tapgemm_simt_kernel(const __grid_
                         if (j < jmax) v[j] = fmaf(a, __bfloat162float(wmat[static_cast<long long>(j) * K + k]), v[j]);
                 }
             }
-        });
+        };
+        if constexpr (EPI == kEpiBwd) bwd_tile<BN, true>(P, tc, t, stile, sflush, rowinfo, st, load_chunk, [] {});
+        else rowowner_tile<BN, EPI>(P, tc, t, load_chunk);
     }
-    if (EPI == kEpiBwd && cur_key >= 0) racc_flush<BN>(P, sracc, cur_key, tid);
+    if (EPI == kEpiBwd && st.key >= 0) bwd_flush<BN>(P, st, t, sflush);
+}
+
+// Seed of the backward chain: the backward epilogue with a zero accumulator (activation backward
+// of the top layer from the toRGB gradient alone).  Memory-bound elementwise pass.
+template <int BN>
+__global__ void __launch_bounds__(kEpiThreads) tapgemm_seed_kernel(const __grid_constant__ TapGemmParams P) {
+    __shared__ float sflush[5 * BN];
+    __shared__ int rowinfo[kBlockM];
+    const int t = threadIdx.x;
+    int t_begin, t_end;
+    tile_range(P.m_tiles * P.n_blocks, t_begin, t_end);
+    BwdState<BN> st;
+    bwd_state_init<BN>(st);
+    for (int tile = t_begin; tile < t_end; ++tile) {
+        const TileCoord tc = decode_tile(P, tile);
+        bwd_tile<BN, false>(P, tc, t, nullptr, sflush, rowinfo, st, [](int, float (&)[32]) {}, [] {});
+    }
+    if (st.key >= 0) bwd_flush<BN>(P, st, t, sflush);
 }
 
 template <int BN, int EPI>
@@ -561,7 +628,7 @@ int launch_bn_epi(const TapGemmParams& p, int num_sms, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Cfg<BN>::kSmemBytes);
+                                             Cfg<BN, EPI>::kSmemBytes);
         if (e != cudaSuccess) return static_cast<int>(e);
         attr_set = true;
     }
@@ -570,7 +637,7 @@ int launch_bn_epi(const TapGemmParams& p, int num_sms, cudaStream_t stream) {
     if (grid <= 0) return 0;
     for (int i = 0; i < p.nprob; ++i)
         if (p.prob[i].ntaps <= 0) return static_cast<int>(cudaErrorInvalidValue);   // accumulator would be undefined
-    tapgemm_kernel<BN, EPI><<<grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(p);
+    tapgemm_kernel<BN, EPI><<<grid, kThreads, Cfg<BN, EPI>::kSmemBytes, stream>>>(p);
     return static_cast<int>(cudaGetLastError());
 }
 
@@ -588,7 +655,7 @@ int launch_bn(const TapGemmParams& p, int num_sms, cudaStream_t stream) {
 template <int BN, int EPI>
 int launch_simt_bn_epi(const TapGemmParams& p, const TapSimtOperands& ops, cudaStream_t stream) {
     const int total = p.m_tiles * p.n_blocks;
-    int grid = total < 148 * 8 ? total : 148 * 8;
+    int grid = total < 148 * 4 ? total : 148 * 4;
     if (grid <= 0) return 0;
     tapgemm_simt_kernel<BN, EPI><<<grid, kEpiThreads, 0, stream>>>(p, ops);
     return static_cast<int>(cudaGetLastError());
@@ -605,7 +672,26 @@ int launch_simt_bn(const TapGemmParams& p, const TapSimtOperands& ops, cudaStrea
     }
 }
 
+template <int BN>
+int launch_seed_bn(const TapGemmParams& p, int num_sms, cudaStream_t stream) {
+    const int total = p.m_tiles * p.n_blocks;
+    int grid = total < num_sms * 6 ? total : num_sms * 6;
+    if (grid <= 0) return 0;
+    tapgemm_seed_kernel<BN><<<grid, kEpiThreads, 0, stream>>>(p);
+    return static_cast<int>(cudaGetLastError());
+}
+
 }  // namespace
+
+int launch_tapgemm_seed(const TapGemmParams& p, int num_sms, cudaStream_t stream) {
+    if (p.epilogue != kEpiBwd) return static_cast<int>(cudaErrorInvalidValue);
+    switch (p.n_total / p.n_blocks) {
+        case 256: return launch_seed_bn<256>(p, num_sms, stream);
+        case 128: return launch_seed_bn<128>(p, num_sms, stream);
+        case 64: return launch_seed_bn<64>(p, num_sms, stream);
+        default: return static_cast<int>(cudaErrorInvalidValue);
+    }
+}
 
 int launch_tapgemm(const TapGemmParams& p, int num_sms, cudaStream_t stream) {
     const int bn = p.n_total / p.n_blocks;

@@ -72,7 +72,7 @@ struct TapGemmParams {
     void* x_hi; void* x_lo;            // bf16 [batch, OH, OW, N]  activation (saved for backward)
     void* xs_hi; void* xs_lo;          // bf16 [batch, OH, OW, N]  x * s_next (A operand of the consumer)
     const float4* rgbw;                // [batch, N] (W_rgb[c][col] * s_rgb[n][col], c = x,y,z) or null
-    float4* rgb_part;                  // [n_blocks][batch, OH, OW] per-column-block toRGB partial sums
+    float4* rgb_part;                  // [2*n_blocks][batch, OH, OW] toRGB partial sums per (column block, epilogue group)
 
     // ---- kEpiBwd: this GEMM is the data gradient of layer l; columns = channels of x_{l-1}
     const float* s_cur;                // [batch, N] style of layer l
@@ -94,8 +94,8 @@ struct TapGemmParams {
     // ---- kEpiTopK: acc[query, code] = <x, y>
     const float* code_sqnorm;          // [n_codes] |y_j|^2
     int n_codes, n_queries, topk;      // topk <= 8
-    float* cand_score;                 // [n_queries][n_blocks][topk]
-    int* cand_idx;                     // [n_queries][n_blocks][topk]
+    float* cand_score;                 // [n_queries][n_blocks][2][topk]  (two epilogue groups per tile)
+    int* cand_idx;                     // [n_queries][n_blocks][2][topk]
 
     int* err_flag;
 };
@@ -103,8 +103,10 @@ struct TapGemmParams {
 // tcgen05 path.  Returns cudaError_t as int.
 int launch_tapgemm(const TapGemmParams& p, int num_sms, cudaStream_t stream);
 
-// SIMT evaluation of the same contraction with the SAME epilogue code.  Used (a) with
-// ntaps == 0 as the "seed" of the backward chain (acc == 0), (b) as the debug cross-check
+// Seed of the backward chain: the kEpiBwd epilogue with a zero accumulator (no GEMM).
+int launch_tapgemm_seed(const TapGemmParams& p, int num_sms, cudaStream_t stream);
+
+// SIMT evaluation of the same contraction with the SAME epilogue code: the debug cross-check
 // of the tensor-core path in tests.  `a_ptrs[i]` / `a_dims` describe what a_map[i] maps
 // (dims = {C, W, H, N}, strides in elements {sW, sH, sN}); `w` is the weight stack.
 struct TapSimtOperands {
