@@ -365,46 +365,65 @@ __device__ __forceinline__ void bwd_tile(const TapGemmParams& P, const TileCoord
 #pragma unroll
         for (int k = 0; k < 10; ++k) r[k] = 0.f;
         if (n_ok) {
-#pragma unroll 4
-            for (int i = 0; i < 16; ++i) {
-                const int rr = rg * 16 + i;
-                const int pxi = rowinfo[rr];
-                if (pxi < 0) continue;
-                float2 a = make_float2(0.f, 0.f);
-                if (kHaveAcc) a = *reinterpret_cast<const float2*>(stile + rr * kStileStride + 2 * cp);
-                const long long xoff = (static_cast<long long>(n_rg) * P.xp_stride_n + static_cast<long long>(pxi) * P.n_total + col) >> 1;
-                const unsigned xu = __ldg(xph + xoff);
-                float x0 = bf16lo_f(xu), x1 = bf16hi_f(xu);
-                if (xpl) { const unsigned xl = __ldg(xpl + xoff); x0 += bf16lo_f(xl); x1 += bf16hi_f(xl); }
-                r[0] = fmaf(a.x, x0, r[0]);
-                r[1] = fmaf(a.y, x1, r[1]);
-                if (!P.bwd_last) {
-                    const long long pix = static_cast<long long>(n_rg) * img_px + pxi;
-                    float g0 = a.x * sc.x, g1 = a.y * sc.y;
-                    if (P.g_rgb) {
-                        const float4 g = __ldg(P.g_rgb + pix);
-                        g0 += g.x * rw0.x + g.y * rw0.y + g.z * rw0.z;
-                        g1 += g.x * rw1.x + g.y * rw1.y + g.z * rw1.z;
-                        r[4] = fmaf(x0, g.x, r[4]); r[5] = fmaf(x1, g.x, r[5]);
-                        r[6] = fmaf(x0, g.y, r[6]); r[7] = fmaf(x1, g.y, r[7]);
-                        r[8] = fmaf(x0, g.z, r[8]); r[9] = fmaf(x1, g.z, r[9]);
+            // rows in batches of 8: all global loads of a batch are issued before any use (memory-level parallelism)
+            const unsigned* xbase_h = xph + ((static_cast<long long>(n_rg) * P.xp_stride_n + col) >> 1);
+            const unsigned* xbase_l = xpl ? xpl + ((static_cast<long long>(n_rg) * P.xp_stride_n + col) >> 1) : nullptr;
+            const float4* gbase = P.g_rgb ? P.g_rgb + static_cast<long long>(n_rg) * img_px : nullptr;
+            const float* nbase = (P.noise_prev && !P.bwd_last) ? P.noise_prev + n_rg * P.noise_prev_stride_n : nullptr;
+            const long long gybase = (static_cast<long long>(n_rg) * img_px * P.n_total + col) >> 1;
+            const int half_n = P.n_total >> 1;
+#pragma unroll
+            for (int b8 = 0; b8 < 2; ++b8) {
+                int pxi[8];
+                unsigned xu[8], xl[8];
+                float nzv[8];
+                float4 gv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) pxi[i] = rowinfo[rg * 16 + b8 * 8 + i];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int p = pxi[i] < 0 ? 0 : pxi[i];
+                    xu[i] = __ldg(xbase_h + static_cast<long long>(p) * half_n);
+                    xl[i] = xbase_l ? __ldg(xbase_l + static_cast<long long>(p) * half_n) : 0u;
+                    nzv[i] = nbase ? __ldg(nbase + p) : 0.f;
+                    gv[i] = gbase ? __ldg(gbase + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (pxi[i] < 0) continue;
+                    const int rr = rg * 16 + b8 * 8 + i;
+                    float2 a = make_float2(0.f, 0.f);
+                    if (kHaveAcc) a = *reinterpret_cast<const float2*>(stile + rr * kStileStride + 2 * cp);
+                    const float x0 = bf16lo_f(xu[i]) + bf16lo_f(xl[i]), x1 = bf16hi_f(xu[i]) + bf16hi_f(xl[i]);
+                    r[0] = fmaf(a.x, x0, r[0]);
+                    r[1] = fmaf(a.y, x1, r[1]);
+                    if (!P.bwd_last) {
+                        float g0 = a.x * sc.x, g1 = a.y * sc.y;
+                        if (P.g_rgb) {
+                            const float4 g = gv[i];
+                            g0 += g.x * rw0.x + g.y * rw0.y + g.z * rw0.z;
+                            g1 += g.x * rw1.x + g.y * rw1.y + g.z * rw1.z;
+                            r[4] = fmaf(x0, g.x, r[4]); r[5] = fmaf(x1, g.x, r[5]);
+                            r[6] = fmaf(x0, g.y, r[6]); r[7] = fmaf(x1, g.y, r[7]);
+                            r[8] = fmaf(x0, g.z, r[8]); r[9] = fmaf(x1, g.z, r[9]);
+                        }
+                        const float nz = nzv[i] * P.noise_prev_scale;
+                        // activation backward of layer l-1 decided by its saved output; y recovered from it
+                        const bool p0 = x0 > 0.f, p1 = x1 > 0.f;
+                        float gz0 = g0 * P.act_gain * (p0 ? 1.f : P.act_slope);
+                        float gz1 = g1 * P.act_gain * (p1 ? 1.f : P.act_slope);
+                        if (P.act_clamp >= 0.f) {
+                            if (!(fabsf(x0) < P.act_clamp)) gz0 = 0.f;
+                            if (!(fabsf(x1) < P.act_clamp)) gz1 = 0.f;
+                        }
+                        const float z0 = x0 * (p0 ? inv_gain : inv_gain_slope), z1 = x1 * (p1 ? inv_gain : inv_gain_slope);
+                        r[2] = fmaf(gz0, z0 - nz - bs.x, r[2]);
+                        r[3] = fmaf(gz1, z1 - nz - bs.y, r[3]);
+                        const float y0 = gz0 * dm.x, y1 = gz1 * dm.y;
+                        const long long goff = gybase + static_cast<long long>(pxi[i]) * half_n;
+                        gyh[goff] = pack_bf16(y0, y1);
+                        if (gyl) gyl[goff] = pack_bf16(y0 - bf16_round(y0), y1 - bf16_round(y1));
                     }
-                    const float nz = P.noise_prev ? __ldg(P.noise_prev + n_rg * P.noise_prev_stride_n + pxi) * P.noise_prev_scale : 0.f;
-                    // activation backward of layer l-1 decided by its saved output; y recovered from it
-                    const bool p0 = x0 > 0.f, p1 = x1 > 0.f;
-                    float gz0 = g0 * P.act_gain * (p0 ? 1.f : P.act_slope);
-                    float gz1 = g1 * P.act_gain * (p1 ? 1.f : P.act_slope);
-                    if (P.act_clamp >= 0.f) {
-                        if (!(fabsf(x0) < P.act_clamp)) gz0 = 0.f;
-                        if (!(fabsf(x1) < P.act_clamp)) gz1 = 0.f;
-                    }
-                    const float z0 = x0 * (p0 ? inv_gain : inv_gain_slope), z1 = x1 * (p1 ? inv_gain : inv_gain_slope);
-                    r[2] = fmaf(gz0, z0 - nz - bs.x, r[2]);
-                    r[3] = fmaf(gz1, z1 - nz - bs.y, r[3]);
-                    const float y0 = gz0 * dm.x, y1 = gz1 * dm.y;
-                    const long long goff = (pix * P.n_total + col) >> 1;
-                    gyh[goff] = pack_bf16(y0, y1);
-                    if (gyl) gyl[goff] = pack_bf16(y0 - bf16_round(y0), y1 - bf16_round(y1));
                 }
             }
         }
@@ -608,7 +627,7 @@ __global__ void __launch_bounds__(kEpiThreads) tapgemm_simt_kernel(const __grid_
 // Seed of the backward chain: the backward epilogue with a zero accumulator (activation backward
 // of the top layer from the toRGB gradient alone).  Memory-bound elementwise pass.
 template <int BN>
-__global__ void __launch_bounds__(kEpiThreads) tapgemm_seed_kernel(const __grid_constant__ TapGemmParams P) {
+__global__ void __launch_bounds__(kEpiThreads, 2) tapgemm_seed_kernel(const __grid_constant__ TapGemmParams P) {
     __shared__ float sflush[5 * BN];
     __shared__ int rowinfo[kBlockM];
     const int t = threadIdx.x;
