@@ -284,11 +284,11 @@ def main():
         roof = {'bound': 'tensor', 'kernel': 'tapgemm_kernel (26 launches of one Adam step: 13 forward + 13 data-gradient)',
                 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'traffic': None,
                 'peak_source': peak_src, 'executed_tflops': exe / (tot_ms * 1e-3) / 1e12,
-                'launch_ms_sum': tot_ms, 'seed_ms': t['seed'],
+                'launch_ms_sum': tot_ms, 'seed_ms': t['seed'], 'fir_pass_ms_sum': sum(t['fir_forward']) + sum(t['fir_backward']),
                 'whole_path_frac': (value / world) * (2 * steps + 1) * f_syn(res, C, channel_base=c.get('channel_base', 32768),
                                                                             channel_max=c.get('channel_max', 512)) / (peak_tf * 1e12)}
         if args.layers_out:
-            tab = [dict(r, fwd_ms=t['forward'][i], dgrad_ms=t['dgrad'][i],
+            tab = [dict(r, fwd_ms=t['forward'][i], dgrad_ms=t['dgrad'][i], fir_fwd_ms=t['fir_forward'][i], fir_bwd_ms=t['fir_backward'][i],
                         fwd_alg_tflops=2.0 * B * r['alg_macs'] / (t['forward'][i] * 1e-3) / 1e12,
                         dgrad_alg_tflops=2.0 * B * r['alg_macs'] / (t['dgrad'][i] * 1e-3) / 1e12) for i, r in enumerate(rows)]
             json.dump({'config': args.config, 'precision': args.precision, 'batch': B, 'layers': tab, 'seed_ms': t['seed']},

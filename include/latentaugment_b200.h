@@ -152,7 +152,8 @@ int la_merge_topk(const float* d_dist, const long long* d_idx, int shards, int n
 int la_debug_set_simt(la_engine* e, int use_simt);
 int la_debug_check(la_engine* e, la_stream stream);
 /* Times each tap-GEMM launch of one optimisation step alone (CUDA events, `reps` launches each).
- * h_ms: HOST array [2*L + 1] = forward[0..L), data gradient[0..L), backward seed.  Synchronous. */
+ * h_ms: HOST array [4*L + 1] = forward GEMM[0..L), data-gradient GEMM[0..L), FIR pass forward[0..L),
+ * FIR pass backward[0..L) (0 where the layer has none), backward seed.  Synchronous. */
 int la_debug_time_gemms(la_engine* e, int reps, float* h_ms, int* n_layers);   /* synchronises; non-zero if a pipeline wait timed out */
 long long la_debug_launch_count(const la_engine* e);
 

@@ -206,9 +206,9 @@ int la_nearest_codes(const float* d_X, int n, const float* d_Y, const void* d_ba
     TapGemmParams P;
     memset(&P, 0, sizeof P);
     P.th = 8; P.tw = 16; P.nb = 1;
-    P.tiles_h = L.Hq / 8; P.tiles_w = 1; P.tiles_n = 1;
-    P.vh = L.Hq; P.vw = 16; P.batch = 1; P.nprob = 1;
-    P.m_tiles = P.tiles_h;
+    P.tiles_n = 1; P.batch = 1; P.nprob = 1;
+    P.prob[0].tiles_h = L.Hq / 8; P.prob[0].tiles_w = 1; P.prob[0].vh = L.Hq; P.prob[0].vw = 16;
+    P.m_tiles = P.prob[0].tiles_h;
     P.kchunks = K / 64;
     P.n_blocks = L.n_blocks; P.n_total = L.n_blocks * 256;
     P.epilogue = kEpiTopK;
@@ -234,7 +234,8 @@ int la_nearest_codes(const float* d_X, int n, const float* d_Y, const void* d_ba
     if (getenv("LA_DEBUG_SIMT_DIST")) {
         TapSimtOperands ops{};
         ops.a_ptrs[0] = xhi; ops.a_ptrs[1] = xlo;
-        ops.a_sw = K; ops.a_sh = 16LL * K; ops.a_sn = 16LL * K * L.Hq; ops.a_w = 16; ops.a_h = L.Hq;
+        ops.a_sw = K; ops.a_sh = 16LL * K; ops.a_sn = 16LL * K * L.Hq;
+        for (int i = 0; i < 2; ++i) { ops.a_ws[i] = 16; ops.a_hs[i] = L.Hq; }
         ops.w = d_bank_bf16;
         int r = launch_tapgemm_simt(P, ops, s);
         if (r) return la_fail_msg(r, "launch_tapgemm_simt failed");

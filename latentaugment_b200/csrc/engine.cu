@@ -62,6 +62,8 @@ struct Conv {
     float *w2, *w2t;
     bf16 *x_hi, *x_lo;
     long long noise_off;     // offset of this layer's slice in a random-noise buffer
+    int split_up;            // x2 layer run as transposed-conv GEMM + FIR pass (vs FIR folded into 36 taps)
+    UpFirParams fir;
     TapGemmParams fwd, bwd;
     TapSimtOperands fwd_ops, bwd_ops;
 };
@@ -87,6 +89,9 @@ struct la_engine {
     float4* rgbw;
     int *chunk_soff, *chunk_cin;
     bf16 *xs_hi[2], *xs_lo[2], *gy_hi[2], *gy_lo[2];
+    bf16 *t_hi, *t_lo;       // transposed-conv intermediate T / g_T of the split up-sampling layers
+    int split_min_res;
+    float fir_host[16];      // resample filter (host copy)
     // criteria
     float4* bank_mean; float* bank_m2; float* loss_parts; int n_loss_parts; int has_img_bank, has_lat_bank;
     float *w_sum, *lat_m2;
@@ -104,6 +109,13 @@ struct la_engine {
 };
 
 namespace {
+
+// x2 layers with output resolution >= this run as transposed-conv GEMM + FIR pass (9 taps, the
+// algorithmic MAC count); smaller ones keep the FIR folded into 36 taps (one launch, latency-bound anyway).
+int upconv_split_min_res() {
+    const char* v = getenv("LA_UPCONV_SPLIT_MIN_RES");
+    return v ? atoi(v) : 64;
+}
 
 void tile_geometry(int g, int& th, int& tw, int& nb) {
     if (g >= 16) { th = 8; tw = 16; nb = 1; }
@@ -126,6 +138,10 @@ int make_b_map(CUtensorMap* m, const void* base, int K, int rows, int nmat, int 
     return encode_tmap_bf16(m, base, 3, dims, strides, box);
 }
 
+void set_ops_dims(TapSimtOperands& o, int w, int h) {
+    for (int i = 0; i < kMaxAMaps; ++i) { o.a_ws[i] = w; o.a_hs[i] = h; }
+}
+
 void add_tap(TapGemmParams& P, int& nt, int dy, int dx, int widx, int src_hi, int src_lo, int nmat, int split) {
     P.taps[nt++] = Tap{static_cast<int8_t>(dy), static_cast<int8_t>(dx), static_cast<uint8_t>(widx), static_cast<uint8_t>(src_hi)};
     if (split) {
@@ -134,16 +150,22 @@ void add_tap(TapGemmParams& P, int& nt, int dy, int dx, int widx, int src_hi, in
     }
 }
 
-void set_grid(TapGemmParams& P, int g, int batch, int nprob) {
+// Tile box from the grid resolution g; problem i covers a gh[i] x gw[i] grid (all = g unless given).
+void set_grid(TapGemmParams& P, int g, int batch, int nprob, const int* gh = nullptr, const int* gw = nullptr) {
     tile_geometry(g, P.th, P.tw, P.nb);
-    P.tiles_h = (g + P.th - 1) / P.th;
-    P.tiles_w = (g + P.tw - 1) / P.tw;
     P.tiles_n = (batch + P.nb - 1) / P.nb;
-    P.vh = P.vw = g;
     P.batch = batch;
     P.nprob = nprob;
-    P.m_tiles = nprob * P.tiles_n * P.tiles_h * P.tiles_w;
-    for (int i = 0; i < nprob; ++i) P.prob[i].tile_begin = i * P.tiles_n * P.tiles_h * P.tiles_w;
+    P.m_tiles = 0;
+    for (int i = 0; i < nprob; ++i) {
+        TapProblem& pr = P.prob[i];
+        pr.vh = gh ? gh[i] : g;
+        pr.vw = gw ? gw[i] : g;
+        pr.tiles_h = (pr.vh + P.th - 1) / P.th;
+        pr.tiles_w = (pr.vw + P.tw - 1) / P.tw;
+        pr.tile_begin = P.m_tiles;
+        P.m_tiles += P.tiles_n * pr.tiles_h * pr.tiles_w;
+    }
 }
 
 // Plans layers and carves the workspace.  With ws == nullptr only sizes are computed.
@@ -166,6 +188,7 @@ int plan(la_engine* e, char* ws, size_t* bytes_out) {
         if (b > 0) {
             Conv c{};
             c.res_in = res / 2; c.res = res; c.cin = g.channels[b - 1]; c.cout = C; c.up = 2; c.block = b; c.ws_idx = widx++;
+            c.split_up = res >= e->split_min_res;
             e->conv.push_back(c);
         }
         Conv c{};
@@ -189,10 +212,14 @@ int plan(la_engine* e, char* ws, size_t* bytes_out) {
 
     Bump bp;
     bp.base = ws;
-    size_t max_xs = 0, max_gy = 0;
+    size_t max_xs = 0, max_gy = 0, max_t = 0;
     int max_n = 0;
     for (Conv& c : e->conv) {
-        const int nmat = (c.up == 2 ? 36 : 9) * (split ? 2 : 1);
+        const int nmat = ((c.up == 2 && !c.split_up) ? 36 : 9) * (split ? 2 : 1);
+        if (c.split_up) {
+            const size_t tsz = static_cast<size_t>(B) * (c.res + 1) * (c.res + 2) * c.cout;
+            max_t = tsz > max_t ? tsz : max_t;
+        }
         const size_t wsz = static_cast<size_t>(nmat) * c.cout * c.cin;
         c.wf = bp.take<bf16>(wsz);
         c.wb = bp.take<bf16>(wsz);
@@ -212,6 +239,8 @@ int plan(la_engine* e, char* ws, size_t* bytes_out) {
         e->gy_hi[i] = bp.take<bf16>(max_gy);
         e->gy_lo[i] = split ? bp.take<bf16>(max_gy) : nullptr;
     }
+    e->t_hi = max_t ? bp.take<bf16>(max_t) : nullptr;
+    e->t_lo = (max_t && split) ? bp.take<bf16>(max_t) : nullptr;
     const int C0 = g.channels[0];
     e->c_f32 = bp.take<float>(16 * C0);
     e->c_hi = bp.take<bf16>(16 * C0);
@@ -267,11 +296,17 @@ int build_params(la_engine* e) {
         const Conv* next = l + 1 < L ? &e->conv[l + 1] : nullptr;
         const Conv* prev = l > 0 ? &e->conv[l - 1] : nullptr;
         const Rgb* rgb = c.last_in_block ? &e->rgb[c.block] : nullptr;
-        const int nmat = c.up == 2 ? 36 : 9;
+        const int nmat = (c.up == 2 && !c.split_up) ? 36 : 9;
         // ---------------------------------------------------------------- forward
         TapGemmParams& F = c.fwd;
         memset(&F, 0, sizeof F);
-        set_grid(F, c.res_in, B, c.up == 2 ? 4 : 1);
+        if (c.split_up) {       // T[2m+py, 2n+px]: even phases have one more row / column (T is (2H+1) x (2W+1))
+            const int gh[4] = {c.res_in + 1, c.res_in + 1, c.res_in, c.res_in};
+            const int gw[4] = {c.res_in + 1, c.res_in, c.res_in + 1, c.res_in};
+            set_grid(F, c.res_in, B, 4, gh, gw);
+        } else {
+            set_grid(F, c.res_in, B, c.up == 2 ? 4 : 1);
+        }
         const bf16* a_hi = e->xs_hi[l & 1];
         const bf16* a_lo = e->xs_lo[l & 1];
         const long long sW = c.cin, sH = static_cast<long long>(c.res_in) * c.cin, sN = sH * c.res_in;
@@ -279,14 +314,20 @@ int build_params(la_engine* e) {
         if (split) LA(make_a_map(&F.a_map[1], a_lo, c.cin, c.res_in, c.res_in, B, sW, sH, sN, F.tw, F.th, F.nb));
         c.fwd_ops = TapSimtOperands{};
         c.fwd_ops.a_ptrs[0] = a_hi; c.fwd_ops.a_ptrs[1] = a_lo;
-        c.fwd_ops.a_sw = sW; c.fwd_ops.a_sh = sH; c.fwd_ops.a_sn = sN; c.fwd_ops.a_w = c.res_in; c.fwd_ops.a_h = c.res_in;
+        c.fwd_ops.a_sw = sW; c.fwd_ops.a_sh = sH; c.fwd_ops.a_sn = sN;
+        set_ops_dims(c.fwd_ops, c.res_in, c.res_in);
         c.fwd_ops.w = c.wf;
         const int bn = pick_bn(c.cout);
         LA(make_b_map(&F.b_map, c.wf, c.cin, c.cout, nmat * (split ? 2 : 1), bn));
         int nt = 0;
         for (int ph = 0; ph < F.nprob; ++ph) {
             F.prob[ph].tap_begin = nt;
-            for (int t = 0; t < 9; ++t) add_tap(F, nt, t / 3 - 1, t % 3 - 1, ph * 9 + t, 0, 1, nmat, split);
+            if (c.split_up) {   // transposed conv, stride 2: T[2i+a] += x[i] W[a]  ->  taps with a = phase (mod 2), x offset -(a >> 1)
+                for (int ay = ph / 2; ay < 3; ay += 2)
+                    for (int ax = ph % 2; ax < 3; ax += 2) add_tap(F, nt, -(ay >> 1), -(ax >> 1), ay * 3 + ax, 0, 1, nmat, split);
+            } else {
+                for (int t = 0; t < 9; ++t) add_tap(F, nt, t / 3 - 1, t % 3 - 1, ph * 9 + t, 0, 1, nmat, split);
+            }
             F.prob[ph].ntaps = nt - F.prob[ph].tap_begin;
             F.prob[ph].oy0 = c.up == 2 ? ph / 2 : 0;
             F.prob[ph].ox0 = c.up == 2 ? ph % 2 : 0;
@@ -304,6 +345,33 @@ int build_params(la_engine* e) {
         F.rgbw = rgb ? e->rgbw + static_cast<size_t>(B) * rgb->roff : nullptr;
         F.rgb_part = rgb ? rgb->parts : nullptr;
         F.err_flag = e->err_flag;
+        const int TH = c.res + 1, TWp = c.res + 2;      // T rows / row pitch of the split up-sampling layers
+        if (c.split_up) {
+            UpFirParams& U = c.fir;
+            memset(&U, 0, sizeof U);
+            U.t_hi = e->t_hi; U.t_lo = e->t_lo;
+            U.B = B; U.OH = U.OW = c.res; U.C = c.cout; U.TH = TH; U.TWp = TWp; U.split = split;
+            U.demod = F.demod; U.bias = F.bias; U.noise = F.noise; U.noise_stride_n = 0; U.noise_scale = F.noise_scale;
+            U.s_next = F.s_next; U.x_hi = F.x_hi; U.x_lo = F.x_lo; U.xs_hi = F.xs_hi; U.xs_lo = F.xs_lo;
+            U.act_gain = F.act_gain; U.act_clamp = F.act_clamp; U.act_slope = F.act_slope;
+            for (int jy = 0; jy < 4; ++jy)       // true convolution (flipped filter), gain up^2 = 4 (upfirdn2d.py:196-199)
+                for (int jx = 0; jx < 4; ++jx) U.fk[jy * 4 + jx] = e->fir_host[(3 - jy) * 4 + (3 - jx)] * 4.f;
+            {   // rank-1 test: fk = fy (x) fx with fy = column of the largest entry / that entry, fx = its row
+                int bi = 0;
+                for (int k = 1; k < 16; ++k) if (fabsf(U.fk[k]) > fabsf(U.fk[bi])) bi = k;
+                const int by = bi / 4, bx = bi % 4;
+                U.separable = U.fk[bi] != 0.f;
+                for (int k = 0; k < 4 && U.separable; ++k) { U.fy[k] = U.fk[k * 4 + bx] / U.fk[bi]; U.fx[k] = U.fk[by * 4 + k]; }
+                for (int k = 0; k < 16 && U.separable; ++k)
+                    if (fabsf(U.fy[k / 4] * U.fx[k % 4] - U.fk[k]) > 1e-6f * fabsf(U.fk[bi])) U.separable = 0;
+            }
+            U.gy_hi = e->gy_hi[l & 1]; U.gy_lo = e->gy_lo[l & 1]; U.gt_hi = e->t_hi; U.gt_lo = e->t_lo;
+            // the GEMM only stores T
+            F.epilogue = kEpiStoreBf16;
+            F.OH = TH; F.OW = TWp;
+            F.x_hi = e->t_hi; F.x_lo = e->t_lo;
+            F.xs_hi = F.xs_lo = nullptr; F.s_next = nullptr; F.rgbw = nullptr;
+        }
 
         // ---------------------------------------------------------------- data gradient
         TapGemmParams& G = c.bwd;
@@ -320,8 +388,31 @@ int build_params(la_engine* e) {
             LA(make_a_map(&G.a_map[0], gy_hi, c.cout, c.res, c.res, B, gW, gH, gN, G.tw, G.th, G.nb));
             if (split) LA(make_a_map(&G.a_map[1], gy_lo, c.cout, c.res, c.res, B, gW, gH, gN, G.tw, G.th, G.nb));
             c.bwd_ops.a_ptrs[0] = gy_hi; c.bwd_ops.a_ptrs[1] = gy_lo;
-            c.bwd_ops.a_sw = gW; c.bwd_ops.a_sh = gH; c.bwd_ops.a_sn = gN; c.bwd_ops.a_w = c.res; c.bwd_ops.a_h = c.res;
+            c.bwd_ops.a_sw = gW; c.bwd_ops.a_sh = gH; c.bwd_ops.a_sn = gN;
+            set_ops_dims(c.bwd_ops, c.res, c.res);
             for (int t = 0; t < 9; ++t) add_tap(G, nt, 1 - t / 3, 1 - t % 3, t, 0, 1, nmat, split);
+        } else if (c.split_up) {
+            // g_xs[i] = sum_a g_T[2i + a] W[a]^T : four phase-strided views of g_T, 9 taps
+            const long long gW = 2LL * c.cout, gH = 2LL * TWp * c.cout, gN = static_cast<long long>(TH) * TWp * c.cout;
+            c.bwd_ops.a_sw = gW; c.bwd_ops.a_sh = gH; c.bwd_ops.a_sn = gN;
+            for (int ph = 0; ph < 4; ++ph) {
+                const int py = ph / 2, px = ph % 2;
+                const int ph_h = c.res_in + (py == 0), ph_w = c.res_in + (px == 0);
+                const long long off = (static_cast<long long>(py) * TWp + px) * c.cout;
+                LA(make_a_map(&G.a_map[ph], e->t_hi + off, c.cout, ph_w, ph_h, B, gW, gH, gN, G.tw, G.th, G.nb));
+                c.bwd_ops.a_ptrs[ph] = e->t_hi + off;
+                c.bwd_ops.a_ws[ph] = ph_w; c.bwd_ops.a_hs[ph] = ph_h;
+                if (split) {
+                    LA(make_a_map(&G.a_map[4 + ph], e->t_lo + off, c.cout, ph_w, ph_h, B, gW, gH, gN, G.tw, G.th, G.nb));
+                    c.bwd_ops.a_ptrs[4 + ph] = e->t_lo + off;
+                    c.bwd_ops.a_ws[4 + ph] = ph_w; c.bwd_ops.a_hs[4 + ph] = ph_h;
+                }
+            }
+            for (int ay = 0; ay < 3; ++ay)
+                for (int ax = 0; ax < 3; ++ax) {
+                    const int ph = (ay & 1) * 2 + (ax & 1);
+                    add_tap(G, nt, ay >> 1, ax >> 1, ay * 3 + ax, ph, 4 + ph, nmat, split);
+                }
         } else {
             const long long gW = 2LL * c.cout, gH = 2LL * c.res * c.cout, gN = static_cast<long long>(c.res) * c.res * c.cout;
             for (int ph = 0; ph < 4; ++ph) {
@@ -333,7 +424,8 @@ int build_params(la_engine* e) {
                     c.bwd_ops.a_ptrs[4 + ph] = gy_lo + off;
                 }
             }
-            c.bwd_ops.a_sw = gW; c.bwd_ops.a_sh = gH; c.bwd_ops.a_sn = gN; c.bwd_ops.a_w = c.res_in; c.bwd_ops.a_h = c.res_in;
+            c.bwd_ops.a_sw = gW; c.bwd_ops.a_sh = gH; c.bwd_ops.a_sn = gN;
+            set_ops_dims(c.bwd_ops, c.res_in, c.res_in);
             for (int ph = 0; ph < 4; ++ph)
                 for (int t = 0; t < 9; ++t) add_tap(G, nt, -(t / 3 - 1), -(t % 3 - 1), ph * 9 + t, ph, 4 + ph, nmat, split);
         }
@@ -413,7 +505,7 @@ int prepare_weights(la_engine* e, cudaStream_t s) {
     std::vector<int> csoff(e->nchunks), ccin(e->nchunks);
     const float aff_gain = 1.f / sqrtf(static_cast<float>(g.w_dim));
     for (Conv& c : e->conv) {
-        LA(prep_conv_weights(c.p.d_weight, c.cout, c.cin, c.up, g.d_resample_filter, split, c.wf, c.wb, c.w2, c.w2t, s));
+        LA(prep_conv_weights(c.p.d_weight, c.cout, c.cin, c.split_up ? 1 : c.up, g.d_resample_filter, split, c.wf, c.wb, c.w2, c.w2t, s));
         LA(prep_affine(c.p.d_affine_weight, c.p.d_affine_bias, c.cin, g.w_dim, aff_gain, 1.f,
                        e->a_cat + static_cast<size_t>(c.soff) * g.w_dim, e->b_cat + c.soff, s));
         for (int r = 0; r < c.cin / 64; ++r) { csoff[c.soff / 64 + r] = c.soff; ccin[c.soff / 64 + r] = c.cin; }
@@ -454,7 +546,14 @@ int run_forward(la_engine* e, const float* ws, long long sn, long long si, int n
     const int L = static_cast<int>(e->conv.size());
     for (int l = 0; l < L; ++l) {
         Conv& c = e->conv[l];
-        if (noise_mode == LA_NOISE_CONST) {
+        if (c.split_up) {
+            LA(gemm(e, c.fwd, c.fwd_ops, s));
+            UpFirParams U = c.fir;
+            if (noise_mode == LA_NOISE_NONE || c.p.noise_strength == 0.f) U.noise = nullptr;
+            else if (noise_mode == LA_NOISE_RANDOM) { U.noise = d_noise + c.noise_off; U.noise_stride_n = static_cast<long long>(c.res) * c.res; }
+            LA(upfir_forward(U, s));
+            e->launches++;
+        } else if (noise_mode == LA_NOISE_CONST) {
             LA(gemm(e, c.fwd, c.fwd_ops, s));
         } else {
             TapGemmParams P = c.fwd;
@@ -489,7 +588,10 @@ int run_backward(la_engine* e, const la_augment_options& /*opt*/, cudaStream_t s
     }
     LA(launch_tapgemm_seed(e->seed, e->num_sms, s));
     e->launches += 2 + g.num_blocks;
-    for (int l = L - 1; l >= 0; --l) LA(gemm(e, e->conv[l].bwd, e->conv[l].bwd_ops, s));
+    for (int l = L - 1; l >= 0; --l) {
+        if (e->conv[l].split_up) { LA(upfir_backward(e->conv[l].fir, s)); e->launches++; }
+        LA(gemm(e, e->conv[l].bwd, e->conv[l].bwd_ops, s));
+    }
     LA(style_grad(e->table, B, e->s_cat, e->d_cat, e->red_s, e->red_d, e->red_rgb, e->g_s, s));
     LA(gw_partial(e->g_s, e->a_cat, e->chunk_soff, e->chunk_cin, e->nchunks, B, g.w_dim, e->partial, s));
     e->launches += 3;
@@ -534,6 +636,7 @@ LA_API int la_engine_workspace_bytes(const la_generator_desc* g, int batch, int 
     if (!g || !bytes || batch < 1) return fail(-2, "bad arguments");
     la_engine tmp{};
     tmp.g = *g; tmp.batch = batch; tmp.split = precision == LA_PRECISION_FP32_PARITY;
+    tmp.split_min_res = upconv_split_min_res();
     return plan(&tmp, nullptr, bytes);
 }
 
@@ -547,6 +650,7 @@ LA_API int la_engine_create(const la_generator_desc* g, int batch, int precision
     if (major != 10) return fail(-4, "latentaugment_b200 needs an sm_100 device (found compute capability %d.x); there is no fallback", major);
     la_engine* e = new la_engine{};
     e->g = *g; e->batch = batch; e->split = precision == LA_PRECISION_FP32_PARITY; e->num_sms = sms;
+    e->split_min_res = upconv_split_min_res();
     size_t need = 0;
     int r = plan(e, static_cast<char*>(d_workspace), &need);
     if (!r && need > workspace_bytes) r = fail(-2, "workspace too small: %zu < %zu", workspace_bytes, need);
@@ -555,6 +659,11 @@ LA_API int la_engine_create(const la_generator_desc* g, int batch, int precision
     e->crop_size = static_cast<int>(sqrt(static_cast<double>(res) * res / 2.0));          // util_dataset.py:317-323
     e->crop_off = static_cast<int>(nearbyint((res - e->crop_size) / 2.0));               // torchvision CenterCrop
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!r) {
+        cudaError_t ce = cudaMemcpyAsync(e->fir_host, g->d_resample_filter, sizeof e->fir_host, cudaMemcpyDeviceToHost, s);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+        if (ce != cudaSuccess) r = fail(static_cast<int>(ce), "reading the resample filter: %s", cudaGetErrorString(ce));
+    }
     if (!r) r = build_params(e);
     if (!r) r = prepare_weights(e, s);
     if (!r) {
@@ -712,7 +821,7 @@ LA_API long long la_debug_launch_count(const la_engine* e) { return e ? e->launc
 
 // Times every tap-GEMM launch of one optimisation step in isolation (CUDA events on the launch
 // stream, `reps` back-to-back launches each; buffers hold whatever the last call left).
-// h_ms: host array [2*L + 1] = forward[0..L), data-gradient[0..L), seed.  Synchronous.
+// h_ms: host array [4*L + 1] = forward GEMM[0..L), data-gradient GEMM[0..L), FIR pass fwd[0..L), FIR pass bwd[0..L), seed.
 LA_API int la_debug_time_gemms(la_engine* e, int reps, float* h_ms, int* n_layers) {
     if (!e || !h_ms || reps < 1) return fail(-2, "bad arguments");
     const int L = static_cast<int>(e->conv.size());
@@ -733,11 +842,28 @@ LA_API int la_debug_time_gemms(la_engine* e, int reps, float* h_ms, int* n_layer
         h_ms[idx] = ms / reps;
         return 0;
     };
+    auto timed_fir = [&](int idx, const UpFirParams& U, bool fwd) -> int {
+        for (int warm = 0; warm < 2; ++warm) { int r = fwd ? upfir_forward(U, w) : upfir_backward(U, w); if (r) return r; }
+        cudaEventRecord(a, w);
+        for (int i = 0; i < reps; ++i) { int r = fwd ? upfir_forward(U, w) : upfir_backward(U, w); if (r) return r; }
+        cudaEventRecord(b, w);
+        cudaError_t ce = cudaEventSynchronize(b);
+        if (ce != cudaSuccess) return static_cast<int>(ce);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        h_ms[idx] = ms / reps;
+        return 0;
+    };
     for (int l = 0; l < L; ++l) {
         LA(timed(l, e->conv[l].fwd, e->conv[l].fwd_ops, false));
         LA(timed(L + l, e->conv[l].bwd, e->conv[l].bwd_ops, false));
+        h_ms[2 * L + l] = h_ms[3 * L + l] = 0.f;
+        if (e->conv[l].split_up) {
+            LA(timed_fir(2 * L + l, e->conv[l].fir, true));
+            LA(timed_fir(3 * L + l, e->conv[l].fir, false));
+        }
     }
-    LA(timed(2 * L, e->seed, e->seed_ops, true));   // 'simt' flag selects the seed launcher here
+    LA(timed(4 * L, e->seed, e->seed_ops, true));   // 'simt' flag selects the seed launcher here
     cudaEventDestroy(a);
     cudaEventDestroy(b);
     return 0;

@@ -172,6 +172,149 @@ __global__ void const_modulate_kernel(const float* __restrict__ c_f32, const flo
     split_store(hi, lo, idx, c_f32[p * C + c] * s0[static_cast<long long>(n) * C + c]);
 }
 
+// ------------------------------------------------------------------------- x2 up-sampling FIR passes
+__device__ __forceinline__ unsigned pack2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<unsigned*>(&v);
+}
+__device__ __forceinline__ void st_bf16x2(unsigned* hi, unsigned* lo, long long i, float a, float b) {
+    hi[i] = pack2(a, b);
+    if (lo) lo[i] = pack2(a - __bfloat162float(__float2bfloat16_rn(a)), b - __bfloat162float(__float2bfloat16_rn(b)));
+}
+
+// Sliding-window 4x4 FIR.  A block = (256 / cpb) consecutive output rows x cpb channel pairs; every thread
+// walks 32 output pixels along x keeping the 4x4 source window of its channel pair in registers, so each
+// step loads one new window column (4 coalesced 128-byte rows per warp) instead of 16 values; the 4-row
+// vertical overlap of neighbouring rows is served by L1.
+//   forward : Y[y,x]   = sum_j fk[jy][jx] * T[y+jy-1, x+jx-1]   then  z = Y*d + noise + b; x = clamp(lrelu(z)*gain); x, x*s_next
+//   backward: g_T[u]   = sum_j fk[jy][jx] * g_Y[u_y-jy+1, u_x-jx+1]                                  (adjoint)
+constexpr int kFirSeg = 32;
+template <bool FWD, bool SPLIT, bool SEP>
+__global__ void __launch_bounds__(256, SEP ? 3 : 2) upfir_slide_kernel(const __grid_constant__ UpFirParams P, int cpb, int chan_blocks) {
+    const int hc = P.C >> 1;
+    const int rows_per_block = 256 / cpb;
+    const int cb = blockIdx.z % chan_blocks, n = blockIdx.z / chan_blocks;
+    const int cp = cb * cpb + threadIdx.x % cpb;
+    const int r = blockIdx.y * rows_per_block + threadIdx.x / cpb;
+    const int x0 = blockIdx.x * kFirSeg;
+    const int TW = P.OW + 1;
+    const int out_h = FWD ? P.OH : P.TH, out_w = FWD ? P.OW : TW, out_pitch = FWD ? P.OW : P.TWp;
+    const int src_h = FWD ? P.TH : P.OH, src_w = FWD ? TW : P.OW, src_pitch = FWD ? P.TWp : P.OW;
+    if (r >= out_h) return;
+    const int org = FWD ? -1 : -2;                 // window origin relative to the output pixel
+    const unsigned* sh = reinterpret_cast<const unsigned*>(FWD ? P.t_hi : P.gy_hi);
+    const unsigned* sl = reinterpret_cast<const unsigned*>(FWD ? P.t_lo : P.gy_lo);
+    float wk[16], wy[4], wx[4];                    // SEP: fk[jy][jx] = fy[jy] * fx[jx]
+#pragma unroll
+    for (int k = 0; k < 16; ++k) wk[k] = FWD ? P.fk[k] : P.fk[15 - k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { wy[k] = FWD ? P.fy[k] : P.fy[3 - k]; wx[k] = FWD ? P.fx[k] : P.fx[3 - k]; }
+    // the 4 window rows: element offsets (channel-pair units) of column 0; invalid rows are clamped and masked
+    long long rowoff[4];
+    float rowmask[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int sr = r + org + k;
+        const bool ok = sr >= 0 && sr < src_h;
+        rowoff[k] = ((static_cast<long long>(n) * src_h + (ok ? sr : 0)) * src_pitch) * hc + cp;
+        rowmask[k] = ok ? 1.f : 0.f;
+    }
+    float2 win[SEP ? 1 : 4][7];                    // [window row][column]; 3 carried + 4 new columns per group
+                                                   // (SEP: one row of vertically filtered column sums)
+    auto load_col = [&](int slot, int sc) {        // unconditional (clamped) loads, masked afterwards: no branches
+        const bool cok = sc >= 0 && sc < src_w;
+        const long long coff = static_cast<long long>(cok ? sc : 0) * hc;
+        unsigned u[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            u[k] = __ldg(sh + rowoff[k] + coff);
+            if (SPLIT) l[k] = __ldg(sl + rowoff[k] + coff);
+        }
+        float2 colsum = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float2 v = make_float2(__uint_as_float(u[k] << 16), __uint_as_float(u[k] & 0xffff0000u));
+            if (SPLIT) { v.x += __uint_as_float(l[k] << 16); v.y += __uint_as_float(l[k] & 0xffff0000u); }
+            if (SEP) {
+                const float m = wy[k] * rowmask[k];
+                colsum.x = fmaf(m, v.x, colsum.x);
+                colsum.y = fmaf(m, v.y, colsum.y);
+            } else {
+                const float m = cok ? rowmask[k] : 0.f;
+                win[k][slot] = make_float2(v.x * m, v.y * m);
+            }
+        }
+        if (SEP) win[0][slot] = cok ? colsum : make_float2(0.f, 0.f);
+    };
+#pragma unroll
+    for (int k = 0; k < 3; ++k) load_col(k, x0 + org + k);
+
+    float2 dm = make_float2(0.f, 0.f), bs = dm, sn = dm;
+    const float* nrow = nullptr;
+    if (FWD) {
+        const int c = 2 * cp;
+        dm = __ldg(reinterpret_cast<const float2*>(P.demod + static_cast<long long>(n) * P.C + c));
+        bs = __ldg(reinterpret_cast<const float2*>(P.bias + c));
+        if (P.s_next) sn = __ldg(reinterpret_cast<const float2*>(P.s_next + static_cast<long long>(n) * P.C + c));
+        if (P.noise) nrow = P.noise + n * P.noise_stride_n + static_cast<long long>(r) * P.OW;
+    }
+    unsigned* oh = reinterpret_cast<unsigned*>(FWD ? P.x_hi : P.gt_hi);
+    unsigned* ol = SPLIT ? reinterpret_cast<unsigned*>(FWD ? P.x_lo : P.gt_lo) : nullptr;
+    unsigned* xsh = reinterpret_cast<unsigned*>(P.xs_hi);
+    unsigned* xsl = SPLIT ? reinterpret_cast<unsigned*>(P.xs_lo) : nullptr;
+    const long long obase = ((static_cast<long long>(n) * out_h + r) * out_pitch) * hc + cp;
+
+#pragma unroll 1
+    for (int xb = 0; xb < kFirSeg; xb += 4) {
+        if (x0 + xb >= out_w) break;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) load_col(3 + u, x0 + xb + org + 3 + u);      // 16 (32) independent loads in flight
+        float nzv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) nzv[u] = (FWD && nrow && x0 + xb + u < out_w) ? __ldg(nrow + x0 + xb + u) * P.noise_scale : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int x = x0 + xb + u;
+            if (x >= out_w) continue;
+            float a0 = 0.f, a1 = 0.f;
+            if (SEP) {
+#pragma unroll
+                for (int kx = 0; kx < 4; ++kx) {
+                    a0 = fmaf(wx[kx], win[0][u + kx].x, a0);
+                    a1 = fmaf(wx[kx], win[0][u + kx].y, a1);
+                }
+            } else {
+#pragma unroll
+                for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 4; ++kx) {
+                        const float2 v = win[ky][u + kx];
+                        a0 = fmaf(wk[ky * 4 + kx], v.x, a0);
+                        a1 = fmaf(wk[ky * 4 + kx], v.y, a1);
+                    }
+            }
+            const long long o = obase + static_cast<long long>(x) * hc;
+            if (FWD) {
+                float z0 = fmaf(a0, dm.x, nzv[u]) + bs.x, z1 = fmaf(a1, dm.y, nzv[u]) + bs.y;
+                z0 = (z0 > 0.f ? z0 : z0 * P.act_slope) * P.act_gain;
+                z1 = (z1 > 0.f ? z1 : z1 * P.act_slope) * P.act_gain;
+                if (P.act_clamp >= 0.f) {
+                    z0 = fminf(fmaxf(z0, -P.act_clamp), P.act_clamp);
+                    z1 = fminf(fmaxf(z1, -P.act_clamp), P.act_clamp);
+                }
+                st_bf16x2(oh, ol, o, z0, z1);
+                if (P.s_next) st_bf16x2(xsh, xsl, o, z0 * sn.x, z1 * sn.y);
+            } else {
+                st_bf16x2(oh, ol, o, a0, a1);
+            }
+        }
+#pragma unroll
+        for (int ky = 0; ky < (SEP ? 1 : 4); ++ky)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) win[ky][k] = win[ky][4 + k];
+    }
+}
+
 // ------------------------------------------------------------------------- toRGB + skip pyramid
 // upsample2d (upfirdn2d.py:313-348: zero-insert x2, pad [2,1,2,1], 4x4 FIR, gain 4) of the
 // default [1,3,3,1] filter is the separable 2-tap interpolation out[2m] = (x[m-1]+3x[m])/4,
@@ -610,6 +753,31 @@ static int max_cin(const LayerTable& T, bool conv, bool rgb) {
     if (rgb) for (int i = 0; i < T.nrgb; ++i) m = T.rgb[i].cin > m ? T.rgb[i].cin : m;
     return m;
 }
+
+static int upfir_launch(const UpFirParams& p, bool fwd, cudaStream_t s) {
+    const int hc = p.C / 2;
+    int cpb = hc < 256 ? hc : 256;
+    if (256 % cpb || hc % cpb) return static_cast<int>(cudaErrorInvalidValue);   // channel counts are 64 * 2^k
+    const int chan_blocks = hc / cpb, rows_per_block = 256 / cpb;
+    const int out_h = fwd ? p.OH : p.TH, out_w = fwd ? p.OW : p.OW + 1;
+    dim3 grid(cdiv(out_w, kFirSeg), cdiv(out_h, rows_per_block), p.B * chan_blocks);
+#define LA_FIR(F, S, Q) upfir_slide_kernel<F, S, Q><<<grid, 256, 0, s>>>(p, cpb, chan_blocks)
+    const int sel = (fwd ? 4 : 0) | (p.split ? 2 : 0) | (p.separable ? 1 : 0);
+    switch (sel) {
+        case 0: LA_FIR(false, false, false); break;
+        case 1: LA_FIR(false, false, true); break;
+        case 2: LA_FIR(false, true, false); break;
+        case 3: LA_FIR(false, true, true); break;
+        case 4: LA_FIR(true, false, false); break;
+        case 5: LA_FIR(true, false, true); break;
+        case 6: LA_FIR(true, true, false); break;
+        default: LA_FIR(true, true, true); break;
+    }
+#undef LA_FIR
+    return last_err();
+}
+int upfir_forward(const UpFirParams& p, cudaStream_t s) { return upfir_launch(p, true, s); }
+int upfir_backward(const UpFirParams& p, cudaStream_t s) { return upfir_launch(p, false, s); }
 
 int styles_forward(const LayerTable& T, const float* ws, long long sn, long long sidx, const float* a_cat, const float* b_cat,
                    int w_dim, int batch, float* s_cat, cudaStream_t s) {

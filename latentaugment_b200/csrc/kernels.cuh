@@ -39,6 +39,25 @@ int prep_affine(const float* aw, const float* ab, int cin, int w_dim, float wsca
 int prep_scale(const float* src, float scale, float* dst, long long n, cudaStream_t s);
 int prep_const(const float* cst /*[C,4,4]*/, int C, int hw, float* c_f32 /*[hw][C]*/, void* hi, void* lo, cudaStream_t s);
 
+// ---- x2 up-sampling conv, split form: transposed-conv GEMM -> T [(2H+1) x (2W+1)] -> 4x4 FIR (pad 1, gain 4)
+// (reference conv2d_resample.py:112-129 + upfirdn2d.py:167-211), fused with the layer epilogue.
+struct UpFirParams {
+    const void* t_hi; const void* t_lo;      // bf16 T / g_T  [B, TH, TWp, C]  (TH = 2H+1 rows, TWp = pitch >= 2W+1)
+    int B, OH, OW, C, TH, TWp, split;
+    float fk[16];                            // fk[jy*4+jx] = F[3-jy][3-jx] * 4   (true convolution, gain up^2)
+    float fy[4], fx[4]; int separable;       // fk = fy (x) fx when the filter is rank 1 (setup_filter([1,3,3,1]) is)
+    // forward epilogue (same meaning as TapGemmParams)
+    const float* demod; const float* bias; const float* noise; long long noise_stride_n; float noise_scale;
+    const float* s_next;
+    void* x_hi; void* x_lo; void* xs_hi; void* xs_lo;
+    float act_gain, act_clamp, act_slope;
+    // backward: g_y [B, OH, OW, C] -> g_T
+    const void* gy_hi; const void* gy_lo;
+    void* gt_hi; void* gt_lo;
+};
+int upfir_forward(const UpFirParams& p, cudaStream_t s);
+int upfir_backward(const UpFirParams& p, cudaStream_t s);
+
 // ---- per step
 int styles_forward(const LayerTable& T, const float* ws, long long ws_stride_n, long long ws_stride_idx, const float* a_cat,
                    const float* b_cat, int w_dim, int batch, float* s_cat, cudaStream_t s);

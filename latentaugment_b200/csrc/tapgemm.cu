@@ -40,21 +40,44 @@ __device__ __forceinline__ TileCoord decode_tile(const TapGemmParams& P, int t) 
     TileCoord c;
     c.nblk = t / P.m_tiles;                  // M fastest: a CTA's contiguous chunk shares the weight tile
     int m = t - c.nblk * P.m_tiles;
-    const int per_prob = P.tiles_n * P.tiles_h * P.tiles_w;
-    c.prob = m / per_prob;
-    int local = m - c.prob * per_prob;
-    int tx = local % P.tiles_w;
-    int ty = (local / P.tiles_w) % P.tiles_h;
-    int tn = local / (P.tiles_w * P.tiles_h);
+    int p = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxProblems; ++i)
+        if (i < P.nprob && m >= P.prob[i].tile_begin) p = i;
+    c.prob = p;
+    const TapProblem& pr = P.prob[p];
+    int local = m - pr.tile_begin;
+    int tx = local % pr.tiles_w;
+    int ty = (local / pr.tiles_w) % pr.tiles_h;
+    int tn = local / (pr.tiles_w * pr.tiles_h);
     c.n0 = tn * P.nb;
     c.h0 = ty * P.th;
     c.w0 = tx * P.tw;
     return c;
 }
 
-__device__ __forceinline__ void tile_range(int total, int& begin, int& end) {
-    begin = static_cast<int>(static_cast<long long>(blockIdx.x) * total / gridDim.x);
-    end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * total / gridDim.x);
+// Contiguous, COST-balanced tile range of this CTA: a tile costs max(ntaps, 1) of its problem (the
+// phases of the transposed convolution have 4 / 2 / 2 / 1 taps).  Tiles are ordered [nblk][problem][tile].
+__device__ __forceinline__ long long tiles_before(const TapGemmParams& P, long long cost_per_nblk, long long x) {
+    long long nb_full = x / cost_per_nblk;
+    if (nb_full >= P.n_blocks) return static_cast<long long>(P.n_blocks) * P.m_tiles;
+    long long rem = x - nb_full * cost_per_nblk, count = nb_full * P.m_tiles;
+    for (int p = 0; p < P.nprob; ++p) {
+        const TapProblem& pr = P.prob[p];
+        const long long c = pr.ntaps > 0 ? pr.ntaps : 1;
+        const long long tiles = static_cast<long long>(pr.tiles_h) * pr.tiles_w * P.tiles_n;
+        if (rem >= tiles * c) { count += tiles; rem -= tiles * c; }
+        else { count += (rem + c - 1) / c; break; }
+    }
+    return count;
+}
+__device__ __forceinline__ void tile_range(const TapGemmParams& P, int& begin, int& end) {
+    long long cost = 0;
+    for (int p = 0; p < P.nprob; ++p)
+        cost += static_cast<long long>(P.prob[p].tiles_h) * P.prob[p].tiles_w * P.tiles_n * (P.prob[p].ntaps > 0 ? P.prob[p].ntaps : 1);
+    const long long total = cost * P.n_blocks;
+    begin = static_cast<int>(tiles_before(P, cost, total * blockIdx.x / gridDim.x));
+    end = static_cast<int>(tiles_before(P, cost, total * (blockIdx.x + 1) / gridDim.x));
 }
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -148,9 +171,9 @@ __device__ __forceinline__ RowCtx make_row(const TapGemmParams& P, const TileCoo
     const int hi = rem / P.tw;
     const int wi = rem - hi * P.tw;
     const int n = tc.n0 + ni, h = tc.h0 + hi, w = tc.w0 + wi;
-    r.valid = (ni < P.nb) && (n < P.batch) && (h < P.vh) && (w < P.vw);
-    r.n = n;
     const TapProblem& pr = P.prob[tc.prob];
+    r.valid = (ni < P.nb) && (n < P.batch) && (h < pr.vh) && (w < pr.vw);
+    r.n = n;
     const int oh = h * P.osy + pr.oy0, ow = w * P.osx + pr.ox0;
     r.px_in_img = static_cast<long long>(oh) * P.OW + ow;
     r.pix = static_cast<long long>(n) * P.OH * P.OW + r.px_in_img;
@@ -185,6 +208,8 @@ __device__ __forceinline__ void rowowner_tile(const TapGemmParams& P, const Tile
 #pragma unroll
                 for (int j = 0; j < 8; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
             }
+        } else if constexpr (EPI == kEpiStoreBf16) {
+            if (rc.valid) store_bf16x32(P.x_hi, P.split ? P.x_lo : nullptr, eoff, acc);
         } else if constexpr (EPI == kEpiTopK) {
             if (tk_valid) {
 #pragma unroll
@@ -451,9 +476,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int total_tiles = P.m_tiles * P.n_blocks;
     int t_begin, t_end;
-    tile_range(total_tiles, t_begin, t_end);
+    tile_range(P, t_begin, t_end);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&P.a_map[0]);
@@ -582,9 +606,8 @@ __global__ void __launch_bounds__(kEpiThreads) tapgemm_simt_kernel(const __grid_
     __shared__ float sflush[EPI == kEpiBwd ? 5 * BN : 1];
     __shared__ int rowinfo[kBlockM];
     const int t = threadIdx.x;
-    const int total_tiles = P.m_tiles * P.n_blocks;
     int t_begin, t_end;
-    tile_range(total_tiles, t_begin, t_end);
+    tile_range(P, t_begin, t_end);
     BwdState<BN> st;
     if (EPI == kEpiBwd) bwd_state_init<BN>(st);
     const int K = P.kchunks * kBlockK;
@@ -605,7 +628,7 @@ __global__ void __launch_bounds__(kEpiThreads) tapgemm_simt_kernel(const __grid_
             for (int ti = 0; ti < pr.ntaps; ++ti) {
                 const Tap tap = P.taps[pr.tap_begin + ti];
                 const int hh = h + tap.dy, ww = w + tap.dx;
-                if (hh < 0 || hh >= ops.a_h || ww < 0 || ww >= ops.a_w) continue;
+                if (hh < 0 || hh >= ops.a_hs[tap.src] || ww < 0 || ww >= ops.a_ws[tap.src]) continue;
                 const __nv_bfloat16* arow = reinterpret_cast<const __nv_bfloat16*>(ops.a_ptrs[tap.src]) +
                                             n * ops.a_sn + hh * ops.a_sh + ww * ops.a_sw;
                 const __nv_bfloat16* wmat = reinterpret_cast<const __nv_bfloat16*>(ops.w) +
@@ -632,7 +655,7 @@ __global__ void __launch_bounds__(kEpiThreads, 2) tapgemm_seed_kernel(const __gr
     __shared__ int rowinfo[kBlockM];
     const int t = threadIdx.x;
     int t_begin, t_end;
-    tile_range(P.m_tiles * P.n_blocks, t_begin, t_end);
+    tile_range(P, t_begin, t_end);
     BwdState<BN> st;
     bwd_state_init<BN>(st);
     for (int tile = t_begin; tile < t_end; ++tile) {
@@ -667,6 +690,7 @@ int launch_bn(const TapGemmParams& p, int num_sms, cudaStream_t stream) {
         case kEpiFwd: return launch_bn_epi<BN, kEpiFwd>(p, num_sms, stream);
         case kEpiBwd: return launch_bn_epi<BN, kEpiBwd>(p, num_sms, stream);
         case kEpiTopK: return launch_bn_epi<BN, kEpiTopK>(p, num_sms, stream);
+        case kEpiStoreBf16: return launch_bn_epi<BN, kEpiStoreBf16>(p, num_sms, stream);
         default: return static_cast<int>(cudaErrorInvalidValue);
     }
 }
@@ -687,6 +711,7 @@ int launch_simt_bn(const TapGemmParams& p, const TapSimtOperands& ops, cudaStrea
         case kEpiFwd: return launch_simt_bn_epi<BN, kEpiFwd>(p, ops, stream);
         case kEpiBwd: return launch_simt_bn_epi<BN, kEpiBwd>(p, ops, stream);
         case kEpiTopK: return launch_simt_bn_epi<BN, kEpiTopK>(p, ops, stream);
+        case kEpiStoreBf16: return launch_simt_bn_epi<BN, kEpiStoreBf16>(p, ops, stream);
         default: return static_cast<int>(cudaErrorInvalidValue);
     }
 }

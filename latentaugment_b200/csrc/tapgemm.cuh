@@ -32,6 +32,8 @@ struct TapProblem {
     int tap_begin, ntaps;
     int oy0, ox0;                  // output pixel = (h*osy + oy0, w*osx + ox0)
     int tile_begin;                // first M-tile index of this problem
+    int tiles_h, tiles_w;          // tile grid of this problem (x tiles_n images)
+    int vh, vw;                    // valid extent (rows, cols); tile overhang is masked
 };
 
 enum TapEpilogue : int {
@@ -39,6 +41,7 @@ enum TapEpilogue : int {
     kEpiFwd = 1,       // demod + noise + bias + lrelu*gain + clamp -> x, x*s_next, toRGB partials
     kEpiBwd = 2,       // style-gradient reductions + activation backward of the producer layer -> g_y
     kEpiTopK = 3,      // rows = queries, columns = bank codes: per-tile k smallest |y|^2 - 2<x,y> per row
+    kEpiStoreBf16 = 4, // store accumulators as bf16 (hi [+ lo]) into x_hi / x_lo [pixel][n_total]
 };
 
 struct TapGemmParams {
@@ -48,8 +51,7 @@ struct TapGemmParams {
     TapProblem prob[kMaxProblems];
     int nprob;
     int th, tw, nb;        // M-tile box: nb images x th rows x tw cols (nb*th*tw <= 128)
-    int tiles_h, tiles_w, tiles_n;   // tile grid of ONE problem (all problems share the geometry)
-    int vh, vw;            // valid extent of the tile grid (rows, cols); overhang is masked
+    int tiles_n;           // ceil(batch / nb)
     int batch;             // images
     int kchunks;           // K / 64 per tap
     int n_total;           // N (columns = output channels of this GEMM)
@@ -112,7 +114,7 @@ int launch_tapgemm_seed(const TapGemmParams& p, int num_sms, cudaStream_t stream
 struct TapSimtOperands {
     const void* a_ptrs[kMaxAMaps];
     long long a_sw, a_sh, a_sn;
-    int a_w, a_h;
+    int a_ws[kMaxAMaps], a_hs[kMaxAMaps];    // spatial extent of each map
     const void* w;
 };
 int launch_tapgemm_simt(const TapGemmParams& p, const TapSimtOperands& ops, cudaStream_t stream);

@@ -196,13 +196,13 @@ class SynthesisEngine:
     def debug_time_gemms(self, reps=5):
         """Per-launch device time (ms) of every tap-GEMM of one optimisation step, timed alone."""
         n = len(self.conv_res)
-        buf = (C.c_float * (2 * n + 1))()
+        buf = (C.c_float * (4 * n + 1))()
         nl = C.c_int(0)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.la_debug_time_gemms(self.handle, reps, buf, C.byref(nl)))
         assert nl.value == n
         v = list(buf)
-        return {'forward': v[:n], 'dgrad': v[n:2 * n], 'seed': v[2 * n]}
+        return {'forward': v[:n], 'dgrad': v[n:2 * n], 'fir_forward': v[2 * n:3 * n], 'fir_backward': v[3 * n:4 * n], 'seed': v[4 * n]}
 
     @property
     def launch_count(self):

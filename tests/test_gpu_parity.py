@@ -238,3 +238,39 @@ def test_plugin_api_end_to_end():
     aug.p_thres = 1.0
     aug.forward()
     assert torch.equal(aug.get_output()['A'], data['A'])
+
+
+@pytest.mark.parametrize('split_min_res', ['8', '100000'])
+@pytest.mark.parametrize('precision', ['fp32_parity', 'bf16'])
+def test_both_upconv_formulations(monkeypatch, split_min_res, precision):
+    """x2 layers as transposed-conv GEMM + FIR pass (split) and with the FIR folded into 36 taps: both
+    must match the oracle, at every resolution (LA_UPCONV_SPLIT_MIN_RES picks per layer)."""
+    from oracle import latent_aug as ola
+    monkeypatch.setenv('LA_UPCONV_SPLIT_MIN_RES', split_min_res)
+    for cfg in ('tiny', 'small'):
+        wl = _workload(cfg)
+        G = wl['G']
+        eng = _engine(wl, precision)
+        eng.set_latent_bank(wl['W'])
+        eng.set_image_bank(wl['X'])
+        ws = wl['w0'].repeat(1, G.num_ws, 1)
+        with torch.no_grad():
+            ref = G.synthesis(ws, noise_mode='const')
+        e0 = rel_l2(eng.synthesis(ws, noise_mode='const').cpu(), ref)
+        orc = ola.LatentAugOracle(G, wl['W'], wl['X'], num_epochs=2)
+        random.seed(0)
+        img_ref, w_ref = orc.forward(wl['w0'].clone())
+        with torch.no_grad():
+            img_ref = G.synthesis(w_ref, noise_mode='const')
+        img, w_aug = eng.augment(wl['w0'], num_steps=2, final_noise_mode='const')
+        eng.debug_check()
+        ew, ei = rel_l2(w_aug.cpu(), w_ref[:, 0]), rel_l2(img.cpu(), img_ref)
+        print(f'\n[upconv split_min_res={split_min_res} {cfg} {precision}] synth={e0:.3e} rel_w={ew:.3e} rel_img={ei:.3e}')
+        assert e0 < (1e-4 if precision == 'fp32_parity' else 1e-2)
+        assert ew < TOL[precision] and ei < TOL[precision]
+        # tensor-core path against the SIMT twin on this formulation
+        a = eng.synthesis(ws, noise_mode='const').cpu()
+        eng.debug_set_simt(1)
+        b = eng.synthesis(ws, noise_mode='const').cpu()
+        eng.debug_set_simt(0)
+        assert rel_l2(a, b) < (2e-5 if precision == 'fp32_parity' else 5e-3)   # bf16: roundings of intermediates differ
