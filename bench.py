@@ -198,8 +198,13 @@ def main():
             '--synthetic_img_bank', str(c['img_bank']), '--synthetic_codes', str(max(4 * B, 256)), '--precision', args.precision,
             '--opt_num_epochs', str(steps), '--no_log',
             '--synthetic_channel_base', str(c.get('channel_base', 32768)), '--synthetic_channel_max', str(c.get('channel_max', 512))]
-    real_stdout = sys.stdout
-    sys.stdout = sys.stderr                        # the plugin prints banners like the reference does
+    # stdout carries exactly ONE JSON line: everything else (plugin banners, the NCCL version line that
+    # the C library writes to fd 1) goes to stderr -- at the file-descriptor level.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = os.fdopen(json_fd, 'w')
+    sys.stdout = sys.stderr
     opt = AugOptions().parse(args={'p_thres': 0.0, 'w_lpips': 0.0, 'w_disc': 0.0, 'init_w': 'inv', 'n_imgs': 0}, argv=argv)
     aug = create_augment(opt)
     core = aug.latent_aug.module
@@ -244,10 +249,10 @@ def main():
     # ---- end to end through the plugin API: host dict in, host dict out
     if args.profile:
         clocks.stop(mark)
-        sys.stdout = real_stdout
         if rank == 0:
             print(json.dumps({'metric': 'augmented images/sec', 'value': value, 'unit': 'img/s', 'ms_per_step': ms,
-                              'gpu_launches': int(launches), 'note': 'profile mode (no e2e / roofline / cpu_baseline legs)'}))
+                              'gpu_launches': int(launches), 'note': 'profile mode (no e2e / roofline / cpu_baseline legs)'}),
+                  file=real_stdout, flush=True)
         return
     for i in range(2):
         aug.set_input(batch_data(i)); aug.forward(); aug.get_output()
@@ -304,9 +309,8 @@ def main():
                            'l2': 'working set >> L2: ~2 GB of activations written and re-read per Adam step',
                            'parallelism': f'batch-sharded x{world}, no data-path collective'},
                 'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cb}
-    sys.stdout = real_stdout
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

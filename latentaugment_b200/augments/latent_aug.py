@@ -92,7 +92,6 @@ class LatentAugment(BaseAugment):
         self.init_w = opt.init_w
         self.verbose_log = opt.verbose_log
         self.stats_time = []
-        self._pinned = None
         if self.phase == 'train':
             print('\nTrain phase.')
             if self.rand_aug:                                # :126-137
@@ -124,14 +123,13 @@ class LatentAugment(BaseAugment):
         self.real_AB = torch.cat((self.real_A, self.real_B), dim=1)
 
     def _to_host(self, t):
-        """D2H through a reused pinned buffer -- same values as ``.detach().cpu()``."""
+        """D2H into pinned host memory -- same values as ``.detach().cpu()``."""
         if not t.is_cuda:
             return t.detach()
-        if self._pinned is None or self._pinned.shape != t.shape:
-            self._pinned = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-        self._pinned.copy_(t.detach(), non_blocking=True)
+        out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)     # torch's caching host allocator recycles these
+        out.copy_(t.detach(), non_blocking=True)
         torch.cuda.current_stream(t.device).synchronize()
-        return self._pinned.clone()
+        return out
 
     def get_output(self):
         real_AB_aug = self._to_host(self.real_AB_aug)
