@@ -219,6 +219,7 @@ int la_nearest_codes(const float* d_X, int n, const float* d_Y, const void* d_ba
     P.taps[1] = Tap{0, 0, 0, 1};      // x_lo . y_hi
     P.taps[2] = Tap{0, 0, 1, 0};      // x_hi . y_lo
     P.prob[0].tap_begin = 0; P.prob[0].ntaps = 3;
+    if (tapgemm_finalize(P)) return la_fail_msg(-5, "tap grouping failed");
     uint64_t adims[4] = {static_cast<uint64_t>(K), 16, static_cast<uint64_t>(L.Hq), 1};
     uint64_t astr[3] = {static_cast<uint64_t>(K) * 2, static_cast<uint64_t>(K) * 32, static_cast<uint64_t>(K) * 32 * L.Hq};
     uint32_t abox[4] = {64, 16, 8, 1};

@@ -83,7 +83,7 @@ struct la_engine {
     std::vector<Rgb> rgb;
     LayerTable table;
     // parameters / coefficients
-    float *c_f32; bf16 *c_hi, *c_lo;
+    float *c_f32; bf16 *c_hi, *c_lo, *c_rep_hi, *c_rep_lo;
     float *a_cat, *b_cat, *s_cat, *d_cat, *g_s, *partial, *red_all, *red_s, *red_d, *red_rgb, *dummy_red;
     size_t red_bytes;
     float4* rgbw;
@@ -117,12 +117,28 @@ int upconv_split_min_res() {
     return v ? atoi(v) : 64;
 }
 
-void tile_geometry(int g, int& th, int& tw, int& nb) {
-    if (g >= 16) { th = 8; tw = 16; nb = 1; }
-    else if (g == 8) { th = 8; tw = 8; nb = 2; }
-    else { th = g; tw = g; nb = 128 / (g * g); }
+// M tile of a grid of resolution g: 16 rows x 8 pixels with a 2-row halo (the three vertical taps share
+// one TMA box) from 16^2 up; whole small images below that.
+void tile_geometry(int g, int& th, int& tw, int& nb, int& halo) {
+    if (g >= 16) { th = 16; tw = 8; nb = 1; halo = 2; }
+    else if (g == 8) { th = 8; tw = 8; nb = 2; halo = 0; }
+    else { th = g; tw = g; nb = 128 / (g * g); halo = 0; }
 }
-int pick_bn(int n) { return n % 256 == 0 ? 256 : (n == 128 ? 128 : (n == 64 ? 64 : 0)); }
+long long grid_m_tiles(int g, int batch) {
+    int th, tw, nb, halo;
+    tile_geometry(g, th, tw, nb, halo);
+    return static_cast<long long>((batch + nb - 1) / nb) * ((g + th - 1) / th) * ((g + tw - 1) / tw);
+}
+// Column block: 128 (two M tiles share each weight tile), 64 when the layer has 64 channels or the grid is
+// too small to occupy the SMs with 128-wide blocks.
+int pick_bn(int n, long long m_tiles = 1 << 30) {
+    if (n % 64) return 0;
+    if (n == 64) return 64;
+    if (n % 128) return 0;
+    static const int force = getenv("LA_BN") ? atoi(getenv("LA_BN")) : 0;      // tuning switch
+    if (force && n % force == 0) return force;
+    return m_tiles * (n / 128) <= 74 ? 64 : 128;
+}
 
 int make_a_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, long long sW, long long sH, long long sN, int tw, int th,
                int nb) {
@@ -152,7 +168,7 @@ void add_tap(TapGemmParams& P, int& nt, int dy, int dx, int widx, int src_hi, in
 
 // Tile box from the grid resolution g; problem i covers a gh[i] x gw[i] grid (all = g unless given).
 void set_grid(TapGemmParams& P, int g, int batch, int nprob, const int* gh = nullptr, const int* gw = nullptr) {
-    tile_geometry(g, P.th, P.tw, P.nb);
+    tile_geometry(g, P.th, P.tw, P.nb, P.halo);
     P.tiles_n = (batch + P.nb - 1) / P.nb;
     P.batch = batch;
     P.nprob = nprob;
@@ -176,7 +192,7 @@ int plan(la_engine* e, char* ws, size_t* bytes_out) {
     if (g.img_channels < 1 || g.img_channels > 3) return fail(-2, "img_channels must be 1..3");
     if (g.w_dim > 1024 || g.w_dim % 4) return fail(-2, "w_dim must be <= 1024");
     for (int b = 0; b < g.num_blocks; ++b)
-        if (!pick_bn(g.channels[b]) || g.channels[b] > 1024) return fail(-2, "channels[%d]=%d unsupported (64, 128 or a multiple of 256 up to 1024)", b, g.channels[b]);
+        if (!pick_bn(g.channels[b]) || g.channels[b] > 1024) return fail(-2, "channels[%d]=%d unsupported (64 or a multiple of 128 up to 1024)", b, g.channels[b]);
     const int B = e->batch, split = e->split;
     e->num_ws = 2 * g.num_blocks;
     e->conv.clear();
@@ -196,7 +212,7 @@ int plan(la_engine* e, char* ws, size_t* bytes_out) {
         e->conv.push_back(c);
         Rgb r{};
         r.res = res; r.cin = C; r.ws_idx = widx; r.p = g.torgb[b];
-        r.nparts = 2 * (C / pick_bn(C));      // one toRGB partial per (column block, epilogue group)
+        r.nparts = 2 * (C / pick_bn(C, grid_m_tiles(res, e->batch)));      // two toRGB partial slots per column block
         e->rgb.push_back(r);
     }
     for (size_t l = 0; l < e->conv.size(); ++l) {
@@ -245,6 +261,8 @@ int plan(la_engine* e, char* ws, size_t* bytes_out) {
     e->c_f32 = bp.take<float>(16 * C0);
     e->c_hi = bp.take<bf16>(16 * C0);
     e->c_lo = bp.take<bf16>(16 * C0);
+    e->c_rep_hi = bp.take<bf16>(static_cast<size_t>(B) * 16 * C0);
+    e->c_rep_lo = bp.take<bf16>(static_cast<size_t>(B) * 16 * C0);
     e->a_cat = bp.take<float>(static_cast<size_t>(S) * g.w_dim);
     e->b_cat = bp.take<float>(S);
     e->s_cat = bp.take<float>(static_cast<size_t>(B) * S);
@@ -310,14 +328,14 @@ int build_params(la_engine* e) {
         const bf16* a_hi = e->xs_hi[l & 1];
         const bf16* a_lo = e->xs_lo[l & 1];
         const long long sW = c.cin, sH = static_cast<long long>(c.res_in) * c.cin, sN = sH * c.res_in;
-        LA(make_a_map(&F.a_map[0], a_hi, c.cin, c.res_in, c.res_in, B, sW, sH, sN, F.tw, F.th, F.nb));
-        if (split) LA(make_a_map(&F.a_map[1], a_lo, c.cin, c.res_in, c.res_in, B, sW, sH, sN, F.tw, F.th, F.nb));
+        LA(make_a_map(&F.a_map[0], a_hi, c.cin, c.res_in, c.res_in, B, sW, sH, sN, F.tw, F.th + F.halo, F.nb));
+        if (split) LA(make_a_map(&F.a_map[1], a_lo, c.cin, c.res_in, c.res_in, B, sW, sH, sN, F.tw, F.th + F.halo, F.nb));
         c.fwd_ops = TapSimtOperands{};
         c.fwd_ops.a_ptrs[0] = a_hi; c.fwd_ops.a_ptrs[1] = a_lo;
         c.fwd_ops.a_sw = sW; c.fwd_ops.a_sh = sH; c.fwd_ops.a_sn = sN;
         set_ops_dims(c.fwd_ops, c.res_in, c.res_in);
         c.fwd_ops.w = c.wf;
-        const int bn = pick_bn(c.cout);
+        const int bn = pick_bn(c.cout, F.m_tiles);
         LA(make_b_map(&F.b_map, c.wf, c.cin, c.cout, nmat * (split ? 2 : 1), bn));
         int nt = 0;
         for (int ph = 0; ph < F.nprob; ++ph) {
@@ -385,8 +403,8 @@ int build_params(la_engine* e) {
         G.prob[0].tap_begin = 0;
         if (c.up == 1) {
             const long long gW = c.cout, gH = static_cast<long long>(c.res) * c.cout, gN = gH * c.res;
-            LA(make_a_map(&G.a_map[0], gy_hi, c.cout, c.res, c.res, B, gW, gH, gN, G.tw, G.th, G.nb));
-            if (split) LA(make_a_map(&G.a_map[1], gy_lo, c.cout, c.res, c.res, B, gW, gH, gN, G.tw, G.th, G.nb));
+            LA(make_a_map(&G.a_map[0], gy_hi, c.cout, c.res, c.res, B, gW, gH, gN, G.tw, G.th + G.halo, G.nb));
+            if (split) LA(make_a_map(&G.a_map[1], gy_lo, c.cout, c.res, c.res, B, gW, gH, gN, G.tw, G.th + G.halo, G.nb));
             c.bwd_ops.a_ptrs[0] = gy_hi; c.bwd_ops.a_ptrs[1] = gy_lo;
             c.bwd_ops.a_sw = gW; c.bwd_ops.a_sh = gH; c.bwd_ops.a_sn = gN;
             set_ops_dims(c.bwd_ops, c.res, c.res);
@@ -399,11 +417,11 @@ int build_params(la_engine* e) {
                 const int py = ph / 2, px = ph % 2;
                 const int ph_h = c.res_in + (py == 0), ph_w = c.res_in + (px == 0);
                 const long long off = (static_cast<long long>(py) * TWp + px) * c.cout;
-                LA(make_a_map(&G.a_map[ph], e->t_hi + off, c.cout, ph_w, ph_h, B, gW, gH, gN, G.tw, G.th, G.nb));
+                LA(make_a_map(&G.a_map[ph], e->t_hi + off, c.cout, ph_w, ph_h, B, gW, gH, gN, G.tw, G.th + G.halo, G.nb));
                 c.bwd_ops.a_ptrs[ph] = e->t_hi + off;
                 c.bwd_ops.a_ws[ph] = ph_w; c.bwd_ops.a_hs[ph] = ph_h;
                 if (split) {
-                    LA(make_a_map(&G.a_map[4 + ph], e->t_lo + off, c.cout, ph_w, ph_h, B, gW, gH, gN, G.tw, G.th, G.nb));
+                    LA(make_a_map(&G.a_map[4 + ph], e->t_lo + off, c.cout, ph_w, ph_h, B, gW, gH, gN, G.tw, G.th + G.halo, G.nb));
                     c.bwd_ops.a_ptrs[4 + ph] = e->t_lo + off;
                     c.bwd_ops.a_ws[4 + ph] = ph_w; c.bwd_ops.a_hs[4 + ph] = ph_h;
                 }
@@ -417,10 +435,10 @@ int build_params(la_engine* e) {
             const long long gW = 2LL * c.cout, gH = 2LL * c.res * c.cout, gN = static_cast<long long>(c.res) * c.res * c.cout;
             for (int ph = 0; ph < 4; ++ph) {
                 const long long off = (static_cast<long long>(ph / 2) * c.res + (ph % 2)) * c.cout;
-                LA(make_a_map(&G.a_map[ph], gy_hi + off, c.cout, c.res_in, c.res_in, B, gW, gH, gN, G.tw, G.th, G.nb));
+                LA(make_a_map(&G.a_map[ph], gy_hi + off, c.cout, c.res_in, c.res_in, B, gW, gH, gN, G.tw, G.th + G.halo, G.nb));
                 c.bwd_ops.a_ptrs[ph] = gy_hi + off;
                 if (split) {
-                    LA(make_a_map(&G.a_map[4 + ph], gy_lo + off, c.cout, c.res_in, c.res_in, B, gW, gH, gN, G.tw, G.th, G.nb));
+                    LA(make_a_map(&G.a_map[4 + ph], gy_lo + off, c.cout, c.res_in, c.res_in, B, gW, gH, gN, G.tw, G.th + G.halo, G.nb));
                     c.bwd_ops.a_ptrs[4 + ph] = gy_lo + off;
                 }
             }
@@ -430,7 +448,9 @@ int build_params(la_engine* e) {
                 for (int t = 0; t < 9; ++t) add_tap(G, nt, -(t / 3 - 1), -(t % 3 - 1), ph * 9 + t, ph, 4 + ph, nmat, split);
         }
         G.prob[0].ntaps = nt;
-        const int bnb = pick_bn(c.cin);
+        if (tapgemm_finalize(F) || tapgemm_finalize(G)) return fail(-2, "tap grouping failed");
+        F.no_pair = G.no_pair = getenv("LA_NO_PAIR") != nullptr;
+        const int bnb = pick_bn(c.cin, G.m_tiles);
         LA(make_b_map(&G.b_map, c.wb, c.cout, c.cin, nmat * (split ? 2 : 1), bnb));
         G.kchunks = c.cout / 64; G.n_total = c.cin; G.n_blocks = c.cin / bnb;
         G.epilogue = kEpiBwd;
@@ -453,7 +473,7 @@ int build_params(la_engine* e) {
             G.red_d = e->red_d + static_cast<size_t>(B) * prev->doff;
         } else {
             G.bwd_last = 1;
-            G.xp_hi = e->c_hi; G.xp_lo = e->c_lo; G.xp_stride_n = 0;
+            G.xp_hi = e->c_rep_hi; G.xp_lo = e->c_rep_lo; G.xp_stride_n = 16LL * c.cin;      // the constant, replicated per sample
         }
     }
     // ---- seed of the backward chain: activation backward of the top layer from the toRGB gradient only
@@ -464,7 +484,7 @@ int build_params(la_engine* e) {
         memset(&Sd, 0, sizeof Sd);
         set_grid(Sd, top.res, B, 1);
         Sd.prob[0].ntaps = 0;
-        const int bn = pick_bn(top.cout);
+        const int bn = pick_bn(top.cout, Sd.m_tiles);
         Sd.kchunks = 1; Sd.n_total = top.cout; Sd.n_blocks = top.cout / bn;
         Sd.epilogue = kEpiBwd;
         Sd.OH = Sd.OW = top.res; Sd.osy = Sd.osx = 1; Sd.split = split;
@@ -517,6 +537,11 @@ int prepare_weights(la_engine* e, cudaStream_t s) {
         for (int q = 0; q < r.cin / 64; ++q) { csoff[r.soff / 64 + q] = r.soff; ccin[r.soff / 64 + q] = r.cin; }
     }
     LA(prep_const(g.d_const, g.channels[0], 16, e->c_f32, e->c_hi, e->c_lo, s));
+    for (int n = 0; n < e->batch; ++n) {
+        const size_t cn = static_cast<size_t>(16) * g.channels[0];
+        CU(cudaMemcpyAsync(e->c_rep_hi + n * cn, e->c_hi, cn * sizeof(bf16), cudaMemcpyDeviceToDevice, s));
+        CU(cudaMemcpyAsync(e->c_rep_lo + n * cn, e->c_lo, cn * sizeof(bf16), cudaMemcpyDeviceToDevice, s));
+    }
     CU(cudaMemcpyAsync(e->chunk_soff, csoff.data(), sizeof(int) * e->nchunks, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(e->chunk_cin, ccin.data(), sizeof(int) * e->nchunks, cudaMemcpyHostToDevice, s));
     CU(cudaMemsetAsync(e->err_flag, 0, sizeof(int), s));

@@ -5,6 +5,8 @@
 #include <cuda_bf16.h>
 #include <stdio.h>
 
+#include <type_traits>
+
 #include "sm100.cuh"
 
 namespace la {
@@ -13,23 +15,32 @@ namespace {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                       // 64 bf16 = one 128-byte swizzle row
-constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
+constexpr int kASubBytes = 18 * 1024;             // A box of one M tile: (16 + 2 halo) rows x 8 pixels x 128 B (16 KB without halo)
 constexpr int kThreads = 384;                     // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-11 epilogue
-constexpr int kEpiThreads = 256;                  // two epilogue warpgroups; warp w owns TMEM lanes 32*(w%4)..+31
-constexpr int kStileStride = 68;                  // floats per row of the 128x64 transpose tile (272 B: conflict-free both ways)
+constexpr int kEpiThreads = 256;                  // 8 epilogue warps; warp e owns TMEM lanes 32*(e%4)..+31
+constexpr unsigned kRowMasked = 0xffffffffu;
+constexpr int kTransStride = 36;                  // floats per row of a warp's 32x32 transpose tile (144 B: conflict-free both ways)
 constexpr int kRegsProducer = 56, kRegsEpilogue = 224;   // setmaxnreg: 128*56 + 256*224 = 64512 <= 65536
+
+// Per-warp scratch of the backward epilogue.
+struct WarpSmem {
+    float trans[32 * kTransStride];   // accumulator chunk, row-owner write -> column-owner read
+    float4 grgb[32];                  // per row: gradient wrt the toRGB output
+    float nz[32];                     // per row: noise * strength of the producer layer
+    unsigned off[32];                 // per row: pixel index * N/2 (offset of the row in bf16x2 units), kRowMasked = masked
+};
 
 template <int BN, int EPI>
 struct Cfg {
+    static constexpr int kMtMax = BN == 256 ? 1 : 2;             // M tiles per unit (they share every weight tile)
+    static constexpr int kASlotBytes = kMtMax * kASubBytes;
     static constexpr int kBBytes = BN * kBlockK * 2;
-    static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = EPI == kEpiBwd ? (BN == 256 ? 3 : (BN == 128 ? 5 : 7)) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
-    static constexpr int kTmemCols = 2 * BN;      // two accumulator stages
-    static constexpr int kStileBytes = EPI == kEpiBwd ? kBlockM * kStileStride * 4 : 0;
-    static constexpr int kFlushBytes = EPI == kEpiBwd ? 5 * BN * 4 : 0;
-    static constexpr int kRowInfoBytes = EPI == kEpiBwd ? kBlockM * 4 : 0;
-    static constexpr int kEpiSmemBytes = kStileBytes + kFlushBytes + kRowInfoBytes;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiSmemBytes + 256 /*barriers*/ + 1024 /*align slack*/;
+    static constexpr int kAStages = BN == 256 ? 4 : 3;
+    static constexpr int kBStages = EPI == kEpiBwd ? (BN == 256 ? 3 : (BN == 128 ? 4 : 6)) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
+    static constexpr int kTmemCols = 2 * kMtMax * BN;            // two accumulator stages
+    static constexpr int kEpiSmemBytes = EPI == kEpiBwd ? 8 * static_cast<int>(sizeof(WarpSmem)) : 0;
+    static constexpr int kSmemBytes = kAStages * kASlotBytes + kBStages * kBBytes + kEpiSmemBytes + 256 /*barriers*/ + 1024 /*align slack*/;
+    static constexpr int kBwdSteps = BN == 64 ? 2 : 4;           // 32-column steps one warp walks per tile (all of BN, or half of it)
 };
 
 struct TileCoord {
@@ -56,6 +67,25 @@ __device__ __forceinline__ TileCoord decode_tile(const TapGemmParams& P, int t) 
     return c;
 }
 
+// A unit = one or two consecutive M tiles of the same (column block, problem).
+struct Unit {
+    TileCoord tc0, tc1;      // (no array: a dynamic index would put the struct in local memory)
+    int mt;
+    __device__ __forceinline__ const TileCoord& tile(int s) const { return s ? tc1 : tc0; }
+};
+template <int MTMAX>
+__device__ __forceinline__ Unit get_unit(const TapGemmParams& P, int t, int t_end) {
+    Unit u;
+    u.tc0 = decode_tile(P, t);
+    u.tc1 = u.tc0;
+    u.mt = 1;
+    if (MTMAX == 2 && t + 1 < t_end && !P.no_pair) {
+        const TileCoord c = decode_tile(P, t + 1);
+        if (c.nblk == u.tc0.nblk && c.prob == u.tc0.prob) { u.tc1 = c; u.mt = 2; }
+    }
+    return u;
+}
+
 // Contiguous, COST-balanced tile range of this CTA: a tile costs max(ntaps, 1) of its problem (the
 // phases of the transposed convolution have 4 / 2 / 2 / 1 taps).  Tiles are ordered [nblk][problem][tile].
 __device__ __forceinline__ long long tiles_before(const TapGemmParams& P, long long cost_per_nblk, long long x) {
@@ -79,8 +109,6 @@ __device__ __forceinline__ void tile_range(const TapGemmParams& P, int& begin, i
     begin = static_cast<int>(tiles_before(P, cost, total * blockIdx.x / gridDim.x));
     end = static_cast<int>(tiles_before(P, cost, total * (blockIdx.x + 1) / gridDim.x));
 }
-
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -119,29 +147,6 @@ __device__ __forceinline__ void store_bf16x32(void* hi, void* lo, long long off,
     }
 }
 
-__device__ __forceinline__ void load_bf16x32(const void* hi, const void* lo, long long off, float (&v)[32]) {
-    const uint4* sh = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(hi) + off);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        uint4 a = __ldg(sh + j);
-        v[8 * j + 0] = bf16lo_f(a.x); v[8 * j + 1] = bf16hi_f(a.x);
-        v[8 * j + 2] = bf16lo_f(a.y); v[8 * j + 3] = bf16hi_f(a.y);
-        v[8 * j + 4] = bf16lo_f(a.z); v[8 * j + 5] = bf16hi_f(a.z);
-        v[8 * j + 6] = bf16lo_f(a.w); v[8 * j + 7] = bf16hi_f(a.w);
-    }
-    if (lo) {
-        const uint4* sl = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(lo) + off);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            uint4 a = __ldg(sl + j);
-            v[8 * j + 0] += bf16lo_f(a.x); v[8 * j + 1] += bf16hi_f(a.x);
-            v[8 * j + 2] += bf16lo_f(a.y); v[8 * j + 3] += bf16hi_f(a.y);
-            v[8 * j + 4] += bf16lo_f(a.z); v[8 * j + 5] += bf16hi_f(a.z);
-            v[8 * j + 6] += bf16lo_f(a.w); v[8 * j + 7] += bf16hi_f(a.w);
-        }
-    }
-}
-
 __device__ __forceinline__ void load_f32x32(const float* p, float (&v)[32]) {
     const float4* s = reinterpret_cast<const float4*>(p);
 #pragma unroll
@@ -151,10 +156,10 @@ __device__ __forceinline__ void load_f32x32(const float* p, float (&v)[32]) {
     }
 }
 
-
 // ------------------------------------------------------------------------------------
-// Epilogues shared by the tensor-core kernel and its SIMT twin.  256 threads: thread t owns
-// accumulator row (t & 127) of the 32-column chunks with (chunk & 1) == (t >> 7).
+// Epilogues shared by the tensor-core kernel, its SIMT twin and the seed kernel.  They are written
+// per WARP: epilogue warp e (0..7) owns accumulator rows 32*(e & 3)..+31 (its TMEM lane quarter) of
+// one M tile and a range of 32-column chunks; no barrier wider than a warp is ever taken.
 
 struct RowCtx {
     bool valid;
@@ -180,12 +185,14 @@ __device__ __forceinline__ RowCtx make_row(const TapGemmParams& P, const TileCoo
     return r;
 }
 
-// ---- row-owner epilogues: raw store, forward activation, top-k
+// ---- row-owner epilogues: raw store, bf16 store, forward activation, top-k.
+// The lane owns row 32*q + lane and walks chunks [ch_begin, ch_end); `part` selects the per-column-block
+// slot (0 / 1) of the per-row outputs (toRGB partial, top-k candidates); with `fill_other` the other slot is
+// written as empty (the warp covered the whole column block).
 template <int BN, int EPI, class LoadChunk>
-__device__ __forceinline__ void rowowner_tile(const TapGemmParams& P, const TileCoord& tc, int t, LoadChunk&& load_chunk) {
-    constexpr int NCH = BN / 32;
-    const int eg = t >> 7;
-    const RowCtx rc = make_row(P, tc, t & 127);
+__device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const TileCoord& tc, int q, int lane, int ch_begin, int ch_end,
+                                                   int part, bool fill_other, LoadChunk&& load_chunk) {
+    const RowCtx rc = make_row(P, tc, q * 32 + lane);
     float nz = 0.f;
     if (EPI == kEpiFwd && rc.valid && P.noise) nz = __ldg(P.noise + rc.n * P.noise_stride_n + rc.px_in_img) * P.noise_scale;
     float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
@@ -196,7 +203,7 @@ __device__ __forceinline__ void rowowner_tile(const TapGemmParams& P, const Tile
     const bool tk_valid = rc.valid && rc.pix < P.n_queries;
 
 #pragma unroll 1
-    for (int ch = eg; ch < NCH; ch += 2) {
+    for (int ch = ch_begin; ch < ch_end; ++ch) {
         float acc[32];
         load_chunk(ch, acc);
         const int col0 = tc.nblk * BN + ch * 32;
@@ -264,198 +271,232 @@ __device__ __forceinline__ void rowowner_tile(const TapGemmParams& P, const Tile
         }
     }
     if (EPI == kEpiTopK && tk_valid) {
-        const long long base = ((rc.pix * P.n_blocks + tc.nblk) * 2 + eg) * P.topk;
+        const long long base = ((rc.pix * P.n_blocks + tc.nblk) * 2 + part) * P.topk;
+        const long long other = ((rc.pix * P.n_blocks + tc.nblk) * 2 + (part ^ 1)) * P.topk;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-            if (k < P.topk) { P.cand_score[base + k] = best_s[k]; P.cand_idx[base + k] = best_i[k]; }
+            if (k < P.topk) {
+                P.cand_score[base + k] = best_s[k]; P.cand_idx[base + k] = best_i[k];
+                if (fill_other) { P.cand_score[other + k] = __int_as_float(0x7f800000); P.cand_idx[other + k] = -1; }
+            }
     }
-    if (EPI == kEpiFwd && P.rgbw && rc.valid)     // one partial per (column block, epilogue group): summed in fixed order later
-        P.rgb_part[static_cast<long long>(tc.nblk * 2 + eg) * P.batch * P.OH * P.OW + rc.pix] = make_float4(rgb0, rgb1, rgb2, 0.f);
+    if (EPI == kEpiFwd && P.rgbw && rc.valid) {   // one partial per (column block, slot): summed in fixed order later
+        const long long plane = static_cast<long long>(P.batch) * P.OH * P.OW;
+        P.rgb_part[(tc.nblk * 2 + part) * plane + rc.pix] = make_float4(rgb0, rgb1, rgb2, 0.f);
+        if (fill_other) P.rgb_part[(tc.nblk * 2 + (part ^ 1)) * plane + rc.pix] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 }
 
-// ---- column-owner backward epilogue.
-// Phase A (row owners): TMEM -> registers -> 128x64 fp32 tile in shared memory.  Phase B: thread
-// (cp = t & 31, rg = t >> 5) owns columns 2cp, 2cp+1 of the chunk and rows rg*16..+15, so the
-// per-column coefficients sit in registers, global accesses are 128-byte coalesced rows and the
-// style-gradient column sums are plain per-thread accumulations (10 registers per 64-column chunk).
-template <int BN>
+// ---- column-owner backward epilogue, per warp.
+// Per 32-column step: the lane (= row) moves its accumulator chunk TMEM -> registers -> the warp's
+// 32x32 transpose tile; then lane (half = lane >> 4, cp = lane & 15) owns columns 2cp, 2cp+1 of the
+// step and rows 16*half..+15, so the per-column coefficients sit in registers, global accesses are
+// 64-byte row segments and the style-gradient column sums are plain per-thread accumulations that
+// survive across tiles until the (sample, column block) key changes.  x_{l-1} of the NEXT step is
+// prefetched into registers before the current step is computed.
+template <int NSTEP>
 struct BwdState {
-    float racc[BN / 64][10];     // (red_s, red_d, red_rgb0..2) x 2 columns, per 64-column chunk
-    int key;                      // (sample, column block) the accumulators belong to, -1 = empty
+    float racc[NSTEP][10];        // (red_s, red_d, red_rgb0..2) x 2 columns, per step slot
+    int key;                      // ((sample * n_blocks + column block) * 8 + first step) of the accumulators, -1 = empty
+    int nsteps;
 };
 
-template <int BN>
-__device__ __forceinline__ void bwd_state_init(BwdState<BN>& st) {
+template <int NSTEP>
+__device__ __forceinline__ void bwd_state_init(BwdState<NSTEP>& st) {
 #pragma unroll
-    for (int c = 0; c < BN / 64; ++c)
+    for (int c = 0; c < NSTEP; ++c)
 #pragma unroll
         for (int k = 0; k < 10; ++k) st.racc[c][k] = 0.f;
     st.key = -1;
+    st.nsteps = 0;
 }
 
 __device__ __forceinline__ float* red_base(const TapGemmParams& P, int kind) {
     return kind == 0 ? P.red_s : (kind == 1 ? P.red_d : P.red_rgb + static_cast<long long>(kind - 2) * P.batch * P.n_total);
 }
 
-template <int BN>
-__device__ __forceinline__ void bwd_flush(const TapGemmParams& P, BwdState<BN>& st, int t, float* sflush) {
-    constexpr int NCH = BN / 64;
-    const int cp = t & 31, rg = t >> 5;
-    const int kinds = P.bwd_last ? 1 : (P.g_rgb ? 5 : 2);
-    const int n = st.key / P.n_blocks, nblk = st.key - n * P.n_blocks;
-    if (P.nb == 1) {
-        // every thread of the CTA holds the same key: reduce the 8 row groups through shared memory
-#pragma unroll 1
-        for (int round = 0; round < 8; ++round) {
-            if (rg == round) {
+template <int BN, int NSTEP>
+__device__ __forceinline__ void bwd_flush(const TapGemmParams& P, BwdState<NSTEP>& st, int lane) {
+    if (st.key >= 0) {
+        const int cp = lane & 15;
+        const int kinds = P.bwd_last ? 1 : (P.g_rgb ? 5 : 2);
+        const int step0 = st.key & 7, nn = st.key >> 3;
+        const int n = nn / P.n_blocks, nblk = nn - n * P.n_blocks;
 #pragma unroll
-                for (int c = 0; c < NCH; ++c)
+        for (int c = 0; c < NSTEP; ++c)
 #pragma unroll
-                    for (int k = 0; k < 10; ++k) {
-                        if ((k >> 1) < kinds) {
-                            float* p = sflush + (k >> 1) * BN + c * 64 + 2 * cp + (k & 1);
-                            *p = (round == 0 ? 0.f : *p) + st.racc[c][k];
-                        }
-                    }
+            for (int k = 0; k < 10; ++k) {
+                if (c < st.nsteps && (k >> 1) < kinds)
+                    atomicAdd(red_base(P, k >> 1) + static_cast<long long>(n) * P.n_total + nblk * BN + (step0 + c) * 32 + 2 * cp + (k & 1),
+                              st.racc[c][k]);
+                st.racc[c][k] = 0.f;
             }
-            epi_bar();
-        }
-        for (int e = t; e < kinds * BN; e += kEpiThreads) {
-            const int kind = e / BN, col = e - kind * BN;
-            atomicAdd(red_base(P, kind) + static_cast<long long>(n) * P.n_total + nblk * BN + col, sflush[e]);
-        }
-        epi_bar();
-    } else if (n < P.batch) {
-#pragma unroll
-        for (int c = 0; c < NCH; ++c)
-#pragma unroll
-            for (int k = 0; k < 10; ++k)
-                if ((k >> 1) < kinds)
-                    atomicAdd(red_base(P, k >> 1) + static_cast<long long>(n) * P.n_total + nblk * BN + c * 64 + 2 * cp + (k & 1), st.racc[c][k]);
     }
-#pragma unroll
-    for (int c = 0; c < NCH; ++c)
-#pragma unroll
-        for (int k = 0; k < 10; ++k) st.racc[c][k] = 0.f;
+    st.key = -1;
 }
 
-template <int BN, bool kHaveAcc, class LoadChunk, class Release>
-__device__ __forceinline__ void bwd_tile(const TapGemmParams& P, const TileCoord& tc, int t, float* stile, float* sflush, int* rowinfo,
-                                         BwdState<BN>& st, LoadChunk&& load_chunk, Release&& release_acc) {
-    constexpr int NCH = BN / 64;
-    const int row = t & 127, eg = t >> 7;        // phase A
-    const int cp = t & 31, rg = t >> 5;          // phase B
+template <int BN, int NSTEP, bool kHaveAcc, class LoadChunk, class Release>
+__device__ __forceinline__ void bwd_warp_tile(const TapGemmParams& P, const TileCoord& tc, int q, int lane, int step0, int nsteps,
+                                              WarpSmem* ws, BwdState<NSTEP>& st, LoadChunk&& load_chunk, Release&& release_acc) {
+    const int half = lane >> 4, cp = lane & 15;
+    // ---- phase 0 (lane = row): pixel index, noise and toRGB gradient of the warp's 32 rows
+    const RowCtx rc = make_row(P, tc, q * 32 + lane);
+    __syncwarp();                    // previous tile's readers are done with ws
+    ws->off[lane] = rc.valid ? static_cast<unsigned>(rc.pix) * static_cast<unsigned>(P.n_total >> 1) : kRowMasked;
+    ws->nz[lane] = (rc.valid && P.noise_prev && !P.bwd_last)
+                       ? __ldg(P.noise_prev + rc.n * P.noise_prev_stride_n + rc.px_in_img) * P.noise_prev_scale : 0.f;
+    ws->grgb[lane] = (rc.valid && P.g_rgb) ? __ldg(P.g_rgb + rc.pix) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // sample of this half-warp's 16 rows (a half never straddles two samples: box_px is 16, 64 or 128)
     const int box_px = P.th * P.tw;
-    const int ni_rg = (rg * 16) / box_px;
-    const int n_rg = tc.n0 + ni_rg;
-    const bool n_ok = ni_rg < P.nb && n_rg < P.batch;
-    const int new_key = (P.nb == 1 ? tc.n0 : n_rg) * P.n_blocks + tc.nblk;
+    const int ni_h = (q * 32 + half * 16) / box_px;
+    const int n_h = tc.n0 + ni_h;
+    const bool n_ok = ni_h < P.nb && n_h < P.batch;
+    const int new_key = n_ok ? ((n_h * P.n_blocks + tc.nblk) * 8 + step0) : -1;
     if (new_key != st.key) {
-        if (st.key >= 0) bwd_flush<BN>(P, st, t, sflush);
+        bwd_flush<BN, NSTEP>(P, st, lane);
         st.key = new_key;
     }
-    if (eg == 0) {
-        const RowCtx rc = make_row(P, tc, row);
-        rowinfo[row] = rc.valid ? static_cast<int>(rc.px_in_img) : -1;
-    }
+    if (n_ok) st.nsteps = nsteps;
+    __syncwarp();
+
     const float inv_gain = 1.f / P.act_gain, inv_gain_slope = 1.f / (P.act_gain * P.act_slope);
-    const long long img_px = static_cast<long long>(P.OH) * P.OW;
+    const float clampv = P.act_clamp >= 0.f ? P.act_clamp : __int_as_float(0x7f800000);
     const unsigned* xph = reinterpret_cast<const unsigned*>(P.xp_hi);
     const unsigned* xpl = P.split ? reinterpret_cast<const unsigned*>(P.xp_lo) : nullptr;
     unsigned* gyh = reinterpret_cast<unsigned*>(P.gy_hi);
     unsigned* gyl = P.split ? reinterpret_cast<unsigned*>(P.gy_lo) : nullptr;
+    const int colw0 = (tc.nblk * BN + step0 * 32 + 2 * cp) >> 1;      // column pair index of step slot 0
+    const bool any_invalid = __any_sync(0xffffffffu, !rc.valid);
+    const unsigned* soff = ws->off + half * 16;
 
+    unsigned xa[16], xb[16];
+    auto prefetch = [&](int slot, unsigned (&xu)[16]) {
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-        if (kHaveAcc) {
-            float acc[32];
-            load_chunk(c * 2 + eg, acc);
-            float4* dst = reinterpret_cast<float4*>(stile + row * kStileStride + eg * 32);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-            if (c == NCH - 1) release_acc();
+        for (int i = 0; i < 16; ++i) {
+            const unsigned o = soff[i];
+            xu[i] = __ldg(xph + (o == kRowMasked ? 0u : o) + (colw0 + slot * 16));
+            if (o == kRowMasked) xu[i] = 0u;
         }
-        epi_bar();
-        const int col = tc.nblk * BN + c * 64 + 2 * cp;
-        const long long coff = static_cast<long long>(n_rg) * P.n_total + col;
+    };
+    prefetch(0, xa);
+
+    // One 32-column step, branch-free over its 16 rows (masked rows carry a == x == g_rgb == 0 and only
+    // their store is predicated off), so the compiler interleaves the rows.
+    const bool last = P.bwd_last != 0;        // x_{l-1} is the constant input: only red_s is wanted (coefficients stay 0, no store)
+    auto step_body = [&](auto rgb_tag, int c, float (&r)[10]) {
+        constexpr bool kRgb = decltype(rgb_tag)::value;
+        const int col = tc.nblk * BN + (step0 + c) * 32 + 2 * cp;
+        const long long coff = static_cast<long long>(n_h) * P.n_total + col;
         float2 sc = make_float2(0.f, 0.f), dm = sc, bs = sc;
         float4 rw0 = make_float4(0.f, 0.f, 0.f, 0.f), rw1 = rw0;
-        if (n_ok && !P.bwd_last) {
+        if (!last && n_ok) {
             sc = __ldg(reinterpret_cast<const float2*>(P.s_cur + coff));
             dm = __ldg(reinterpret_cast<const float2*>(P.demod_prev + coff));
             bs = __ldg(reinterpret_cast<const float2*>(P.bias_prev + col));
-            if (P.g_rgb) { rw0 = __ldg(P.rgbw_prev + coff); rw1 = __ldg(P.rgbw_prev + coff + 1); }
+            sc.x *= P.act_gain; sc.y *= P.act_gain;               // activation gain folded into the coefficients
+            if (kRgb) {
+                rw0 = __ldg(P.rgbw_prev + coff); rw1 = __ldg(P.rgbw_prev + coff + 1);
+                rw0.x *= P.act_gain; rw0.y *= P.act_gain; rw0.z *= P.act_gain;
+                rw1.x *= P.act_gain; rw1.y *= P.act_gain; rw1.z *= P.act_gain;
+            }
         }
-        float r[10];
+        unsigned xl[16];
 #pragma unroll
-        for (int k = 0; k < 10; ++k) r[k] = 0.f;
-        if (n_ok) {
-            // rows in batches of 8: all global loads of a batch are issued before any use (memory-level parallelism)
-            const unsigned* xbase_h = xph + ((static_cast<long long>(n_rg) * P.xp_stride_n + col) >> 1);
-            const unsigned* xbase_l = xpl ? xpl + ((static_cast<long long>(n_rg) * P.xp_stride_n + col) >> 1) : nullptr;
-            const float4* gbase = P.g_rgb ? P.g_rgb + static_cast<long long>(n_rg) * img_px : nullptr;
-            const float* nbase = (P.noise_prev && !P.bwd_last) ? P.noise_prev + n_rg * P.noise_prev_stride_n : nullptr;
-            const long long gybase = (static_cast<long long>(n_rg) * img_px * P.n_total + col) >> 1;
-            const int half_n = P.n_total >> 1;
+        for (int i = 0; i < 16; ++i) xl[i] = 0u;
+        if (xpl) {
 #pragma unroll
-            for (int b8 = 0; b8 < 2; ++b8) {
-                int pxi[8];
-                unsigned xu[8], xl[8];
-                float nzv[8];
-                float4 gv[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) pxi[i] = rowinfo[rg * 16 + b8 * 8 + i];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int p = pxi[i] < 0 ? 0 : pxi[i];
-                    xu[i] = __ldg(xbase_h + static_cast<long long>(p) * half_n);
-                    xl[i] = xbase_l ? __ldg(xbase_l + static_cast<long long>(p) * half_n) : 0u;
-                    nzv[i] = nbase ? __ldg(nbase + p) : 0.f;
-                    gv[i] = gbase ? __ldg(gbase + p) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (pxi[i] < 0) continue;
-                    const int rr = rg * 16 + b8 * 8 + i;
-                    float2 a = make_float2(0.f, 0.f);
-                    if (kHaveAcc) a = *reinterpret_cast<const float2*>(stile + rr * kStileStride + 2 * cp);
-                    const float x0 = bf16lo_f(xu[i]) + bf16lo_f(xl[i]), x1 = bf16hi_f(xu[i]) + bf16hi_f(xl[i]);
-                    r[0] = fmaf(a.x, x0, r[0]);
-                    r[1] = fmaf(a.y, x1, r[1]);
-                    if (!P.bwd_last) {
-                        float g0 = a.x * sc.x, g1 = a.y * sc.y;
-                        if (P.g_rgb) {
-                            const float4 g = gv[i];
-                            g0 += g.x * rw0.x + g.y * rw0.y + g.z * rw0.z;
-                            g1 += g.x * rw1.x + g.y * rw1.y + g.z * rw1.z;
-                            r[4] = fmaf(x0, g.x, r[4]); r[5] = fmaf(x1, g.x, r[5]);
-                            r[6] = fmaf(x0, g.y, r[6]); r[7] = fmaf(x1, g.y, r[7]);
-                            r[8] = fmaf(x0, g.z, r[8]); r[9] = fmaf(x1, g.z, r[9]);
-                        }
-                        const float nz = nzv[i] * P.noise_prev_scale;
-                        // activation backward of layer l-1 decided by its saved output; y recovered from it
-                        const bool p0 = x0 > 0.f, p1 = x1 > 0.f;
-                        float gz0 = g0 * P.act_gain * (p0 ? 1.f : P.act_slope);
-                        float gz1 = g1 * P.act_gain * (p1 ? 1.f : P.act_slope);
-                        if (P.act_clamp >= 0.f) {
-                            if (!(fabsf(x0) < P.act_clamp)) gz0 = 0.f;
-                            if (!(fabsf(x1) < P.act_clamp)) gz1 = 0.f;
-                        }
-                        const float z0 = x0 * (p0 ? inv_gain : inv_gain_slope), z1 = x1 * (p1 ? inv_gain : inv_gain_slope);
-                        r[2] = fmaf(gz0, z0 - nz - bs.x, r[2]);
-                        r[3] = fmaf(gz1, z1 - nz - bs.y, r[3]);
-                        const float y0 = gz0 * dm.x, y1 = gz1 * dm.y;
-                        const long long goff = gybase + static_cast<long long>(pxi[i]) * half_n;
-                        gyh[goff] = pack_bf16(y0, y1);
-                        if (gyl) gyl[goff] = pack_bf16(y0 - bf16_round(y0), y1 - bf16_round(y1));
-                    }
-                }
+            for (int i = 0; i < 16; ++i) {
+                const unsigned o = soff[i];
+                xl[i] = __ldg(xpl + (o == kRowMasked ? 0u : o) + (colw0 + c * 16));
+                if (o == kRowMasked) xl[i] = 0u;
             }
         }
 #pragma unroll
-        for (int k = 0; k < 10; ++k) st.racc[c][k] += r[k];
-        epi_bar();           // the tile / rowinfo may be overwritten from here on
+        for (int i = 0; i < 16; ++i) {
+            const int row = half * 16 + i;
+            const unsigned o = soff[i];
+            float2 a = make_float2(0.f, 0.f);
+            if (kHaveAcc) a = *reinterpret_cast<const float2*>(ws->trans + row * kTransStride + 2 * cp);
+            const float x0 = bf16lo_f(xa[i]) + bf16lo_f(xl[i]), x1 = bf16hi_f(xa[i]) + bf16hi_f(xl[i]);
+            r[0] = fmaf(a.x, x0, r[0]);
+            r[1] = fmaf(a.y, x1, r[1]);
+            {
+                float g0 = a.x * sc.x, g1 = a.y * sc.y;
+                if (kRgb) {
+                    const float4 g = ws->grgb[row];
+                    g0 = fmaf(g.x, rw0.x, fmaf(g.y, rw0.y, fmaf(g.z, rw0.z, g0)));
+                    g1 = fmaf(g.x, rw1.x, fmaf(g.y, rw1.y, fmaf(g.z, rw1.z, g1)));
+                    r[4] = fmaf(x0, g.x, r[4]); r[5] = fmaf(x1, g.x, r[5]);
+                    r[6] = fmaf(x0, g.y, r[6]); r[7] = fmaf(x1, g.y, r[7]);
+                    r[8] = fmaf(x0, g.z, r[8]); r[9] = fmaf(x1, g.z, r[9]);
+                }
+                const float nz = ws->nz[row];
+                // activation backward of layer l-1 decided by its saved output; y recovered from it
+                const bool p0 = x0 > 0.f, p1 = x1 > 0.f;
+                float gz0 = g0 * (p0 ? 1.f : P.act_slope);
+                float gz1 = g1 * (p1 ? 1.f : P.act_slope);
+                gz0 = fabsf(x0) < clampv ? gz0 : 0.f;
+                gz1 = fabsf(x1) < clampv ? gz1 : 0.f;
+                const float z0 = x0 * (p0 ? inv_gain : inv_gain_slope), z1 = x1 * (p1 ? inv_gain : inv_gain_slope);
+                r[2] = fmaf(gz0, z0 - nz - bs.x, r[2]);
+                r[3] = fmaf(gz1, z1 - nz - bs.y, r[3]);
+                const float y0 = gz0 * dm.x, y1 = gz1 * dm.y;
+                if (o != kRowMasked && !last) {
+                    gyh[o + (colw0 + c * 16)] = pack_bf16(y0, y1);
+                    if (gyl) gyl[o + (colw0 + c * 16)] = pack_bf16(y0 - bf16_round(y0), y1 - bf16_round(y1));
+                }
+            }
+        }
+    };
+
+#pragma unroll 1
+    for (int c = 0; c < nsteps; ++c) {       // (a runtime loop: unrolled, the epilogue outgrows the instruction cache)
+        if (kHaveAcc) {
+            float acc[32];
+            load_chunk(step0 + c, acc);
+            if (c == nsteps - 1) release_acc();
+            if (any_invalid && !rc.valid) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+            }
+            float4* dst = reinterpret_cast<float4*>(ws->trans + lane * kTransStride);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        }
+        __syncwarp();
+        if (c + 1 < nsteps) prefetch(c + 1, xb);
+        float r[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) r[k] = 0.f;
+        if (P.g_rgb && !P.bwd_last) step_body(std::true_type{}, c, r);
+        else step_body(std::false_type{}, c, r);
+#pragma unroll
+        for (int cc = 0; cc < NSTEP; ++cc)
+            if (cc == c) {
+#pragma unroll
+                for (int k = 0; k < 10; ++k) st.racc[cc][k] += r[k];
+            }
+        __syncwarp();           // the transpose tile may be overwritten from here on
+#pragma unroll
+        for (int i = 0; i < 16; ++i) xa[i] = xb[i];
     }
+}
+
+// Work split of the 8 epilogue warps over a unit: with two M tiles, warps 0-3 take tile 0 and warps 4-7
+// tile 1 (all columns); with one, the two warp groups split its columns.
+template <int BN>
+struct EpiSplit {
+    int st;            // which M tile of the unit
+    int ch_begin, ch_end;   // 32-column chunks
+    bool whole;        // the warp covers the whole column block
+};
+template <int BN>
+__device__ __forceinline__ EpiSplit<BN> epi_split(int mt, int sub) {
+    constexpr int NCH = BN / 32;
+    EpiSplit<BN> s;
+    if (mt == 2) { s.st = sub; s.ch_begin = 0; s.ch_end = NCH; s.whole = true; }
+    else { s.st = 0; s.ch_begin = sub * (NCH / 2); s.ch_end = (sub + 1) * (NCH / 2); s.whole = false; }
+    return s;
 }
 
 // ------------------------------------------------------------------------------------
@@ -463,16 +504,18 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams P) {
     using C = Cfg<BN, EPI>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* epi_smem = smem + C::kStages * C::kStageBytes;
-    float* stile = reinterpret_cast<float*>(epi_smem);
-    float* sflush = reinterpret_cast<float*>(epi_smem + C::kStileBytes);
-    int* rowinfo = reinterpret_cast<int*>(epi_smem + C::kStileBytes + C::kFlushBytes);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + C::kEpiSmemBytes);
-    uint64_t* empty_bar = full_bar + C::kStages;
-    uint64_t* tfull_bar = empty_bar + C::kStages;
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
+    uint8_t* a_smem = smem;
+    uint8_t* b_smem = smem + C::kAStages * C::kASlotBytes;
+    uint8_t* epi_smem = b_smem + C::kBStages * C::kBBytes;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(epi_smem + C::kEpiSmemBytes);
+    uint64_t* a_empty = a_full + C::kAStages;
+    uint64_t* b_full = a_empty + C::kAStages;
+    uint64_t* b_empty = b_full + C::kBStages;
+    uint64_t* tfull_bar = b_empty + C::kBStages;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    static_assert((2 * C::kAStages + 2 * C::kBStages + 4) * 8 + 4 <= 256, "barrier area");
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -484,10 +527,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
         prefetch_tmap(&P.b_map);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < C::kStages; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
-        }
+        for (int s = 0; s < C::kAStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < C::kBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
             mbar_init(&tempty_bar[a], kEpiThreads / 32);
@@ -500,80 +541,113 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const uint32_t a_tx_bytes = static_cast<uint32_t>(P.nb * P.th * P.tw) * 128u;
+    const uint32_t a_tx_bytes = static_cast<uint32_t>(P.nb * (P.th + P.halo) * P.tw) * 128u;
+    const uint32_t dy_bytes = static_cast<uint32_t>(P.tw) * 128u;      // one tile row of pixels (1024 B when halo > 0)
 
     if (warp < 4) {
         setmaxnreg_dec<kRegsProducer>();
         if (warp == 0 && lane == 0) {
             // ---------------------------------------------------------------- TMA producer
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int t = t_begin; t < t_end; ++t) {
-                const TileCoord tc = decode_tile(P, t);
-                const TapProblem& pr = P.prob[tc.prob];
-                for (int ti = 0; ti < pr.ntaps; ++ti) {
-                    const Tap tap = P.taps[pr.tap_begin + ti];
-                    const CUtensorMap* amap = &P.a_map[tap.src];
+            int as = 0, bs = 0;
+            uint32_t aph = 0, bph = 0;
+            for (int t = t_begin; t < t_end;) {
+                const Unit u = get_unit<C::kMtMax>(P, t, t_end);
+                t += u.mt;
+                const TapProblem& pr = P.prob[u.tc0.prob];
+                for (int g = 0; g < pr.ngroups; ++g) {
+                    const TapGroup grp = P.groups[pr.grp_begin + g];
+                    const CUtensorMap* amap = &P.a_map[grp.src];
                     for (int kc = 0; kc < P.kchunks; ++kc) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1, P.err_flag, 1);
-                        uint8_t* sa = smem + stage * C::kStageBytes;
-                        mbar_expect_tx(&full_bar[stage], a_tx_bytes + C::kBBytes);
-                        tma_load_4d(sa, amap, &full_bar[stage], kc * kBlockK, tc.w0 + tap.dx, tc.h0 + tap.dy, tc.n0);
-                        tma_load_3d(sa + kABytes, &P.b_map, &full_bar[stage], kc * kBlockK, tc.nblk * BN, tap.widx);
-                        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                        mbar_wait(&a_empty[as], aph ^ 1, P.err_flag, 1);
+                        uint8_t* sa = a_smem + as * C::kASlotBytes;
+                        mbar_expect_tx(&a_full[as], a_tx_bytes * u.mt);
+                        tma_load_4d(sa, amap, &a_full[as], kc * kBlockK, u.tc0.w0 + grp.dx, u.tc0.h0 + grp.dy0, u.tc0.n0);
+                        if (u.mt == 2)
+                            tma_load_4d(sa + kASubBytes, amap, &a_full[as], kc * kBlockK, u.tc1.w0 + grp.dx, u.tc1.h0 + grp.dy0, u.tc1.n0);
+                        if (++as == C::kAStages) { as = 0; aph ^= 1; }
+                        for (int j = 0; j < grp.ntaps; ++j) {
+                            mbar_wait(&b_empty[bs], bph ^ 1, P.err_flag, 5);
+                            mbar_expect_tx(&b_full[bs], C::kBBytes);
+                            tma_load_3d(b_smem + bs * C::kBBytes, &P.b_map, &b_full[bs], kc * kBlockK, u.tc0.nblk * BN,
+                                        P.gwidx[grp.tap_begin + j]);
+                            if (++bs == C::kBStages) { bs = 0; bph ^= 1; }
+                        }
                     }
                 }
             }
         } else if (warp == 1 && lane == 0) {
             // ---------------------------------------------------------------- MMA issuer
             constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN);
-            int stage = 0;
-            uint32_t phase = 0;
+            int as = 0, bs = 0;
+            uint32_t aph = 0, bph = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int t = t_begin; t < t_end; ++t) {
-                const TileCoord tc = decode_tile(P, t);
-                const int ksteps = P.prob[tc.prob].ntaps * P.kchunks;
+            for (int t = t_begin; t < t_end;) {
+                const Unit u = get_unit<C::kMtMax>(P, t, t_end);
+                t += u.mt;
+                const TapProblem& pr = P.prob[u.tc0.prob];
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1, P.err_flag, 2);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    mbar_wait(&full_bar[stage], phase, P.err_flag, 3);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
-                    const uint64_t adesc = make_sw128_kmajor_desc(sa);
-                    const uint64_t bdesc = make_sw128_kmajor_desc(sa + kABytes);
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * C::kMtMax * BN);
+                bool first = true;
+                for (int g = 0; g < pr.ngroups; ++g) {
+                    const TapGroup grp = P.groups[pr.grp_begin + g];
+                    for (int kc = 0; kc < P.kchunks; ++kc) {
+                        mbar_wait(&a_full[as], aph, P.err_flag, 3);
+                        const uint32_t sa = smem_u32(a_smem + as * C::kASlotBytes);
+                        for (int j = 0; j < grp.ntaps; ++j) {
+                            mbar_wait(&b_full[bs], bph, P.err_flag, 6);
+                            tc_fence_after();
+                            const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(b_smem + bs * C::kBBytes));
+                            const uint32_t a_tap = sa + P.gdyrel[grp.tap_begin + j] * dy_bytes;
+                            for (int s = 0; s < u.mt; ++s) {
+                                const uint64_t adesc = make_sw128_kmajor_desc(a_tap + s * kASubBytes);
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k)
-                        umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
-                                  (ks | k) != 0 ? 1u : 0u);
-                    umma_commit(&empty_bar[stage]);
-                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                                for (int k = 0; k < kBlockK / 16; ++k)
+                                    umma_bf16(d_tmem + static_cast<uint32_t>(s * BN), adesc + static_cast<uint64_t>(k * 2),
+                                              bdesc + static_cast<uint64_t>(k * 2), idesc, (first && k == 0) ? 0u : 1u);
+                            }
+                            first = false;
+                            umma_commit(&b_empty[bs]);
+                            if (++bs == C::kBStages) { bs = 0; bph ^= 1; }
+                        }
+                        umma_commit(&a_empty[as]);
+                        if (++as == C::kAStages) { as = 0; aph ^= 1; }
+                    }
                 }
                 umma_commit(&tfull_bar[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
-        // -------------------------------------------------------------------- epilogue (256 threads)
+        // -------------------------------------------------------------------- epilogue (8 independent warps)
         setmaxnreg_inc<kRegsEpilogue>();
-        const int t = threadIdx.x - 128;
-        const int q = warp & 3;               // TMEM lane quarter
+        const int e = warp - 4;
+        const int q = e & 3, sub = e >> 2;          // TMEM lane quarter (= warp % 4), warp group
         int acc = 0;
         uint32_t acc_phase = 0;
-        BwdState<BN> st;
-        if (EPI == kEpiBwd) bwd_state_init<BN>(st);
-        for (int tile = t_begin; tile < t_end; ++tile) {
-            const TileCoord tc = decode_tile(P, tile);
-            mbar_wait(&tfull_bar[acc], acc_phase, P.err_flag, 4);
-            tc_fence_after();
-            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+        BwdState<C::kBwdSteps> st;
+        if (EPI == kEpiBwd) bwd_state_init(st);
+        WarpSmem* ws = reinterpret_cast<WarpSmem*>(epi_smem) + e;
+        for (int t = t_begin; t < t_end;) {
+            const Unit u = get_unit<C::kMtMax>(P, t, t_end);
+            t += u.mt;
+            const EpiSplit<BN> sp = epi_split<BN>(u.mt, sub);
+            const TileCoord tc = u.tile(sp.st);
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                    static_cast<uint32_t>((acc * C::kMtMax + sp.st) * BN);
+            bool waited = false;
             auto load_chunk = [&](int ch, float (&v)[32]) {
-                uint32_t u[32];
-                tmem_ld32(t_addr + ch * 32, u);
+                if (!waited) {       // the row-info phase of the backward epilogue runs before this wait
+                    mbar_wait(&tfull_bar[acc], acc_phase, P.err_flag, 4);
+                    tc_fence_after();
+                    waited = true;
+                }
+                uint32_t r[32];
+                tmem_ld32(t_addr + ch * 32, r);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]);
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             };
             auto release = [&]() {
                 tc_fence_before();
@@ -581,14 +655,14 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             };
             if constexpr (EPI == kEpiBwd) {
-                bwd_tile<BN, true>(P, tc, t, stile, sflush, rowinfo, st, load_chunk, release);
+                bwd_warp_tile<BN, C::kBwdSteps, true>(P, tc, q, lane, sp.ch_begin, sp.ch_end - sp.ch_begin, ws, st, load_chunk, release);
             } else {
-                rowowner_tile<BN, EPI>(P, tc, t, load_chunk);
+                rowowner_warp_tile<BN, EPI>(P, tc, q, lane, sp.ch_begin, sp.ch_end, sp.whole ? 0 : sub, sp.whole, load_chunk);
                 release();
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (EPI == kEpiBwd && st.key >= 0) bwd_flush<BN>(P, st, t, sflush);
+        if (EPI == kEpiBwd) bwd_flush<BN, C::kBwdSteps>(P, st, lane);
     }
 
     tc_fence_before();
@@ -597,25 +671,29 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
 }
 
 // ------------------------------------------------------------------------------------
-// SIMT twin: 256 threads, same tile walk and the same epilogue code; the accumulator chunk is
-// computed by brute force.  Debug cross-check of the tensor-core path (tests), never a fallback.
+// SIMT twin: 8 warps with the SAME roles and the same epilogue code as the epilogue warps of the
+// tensor-core kernel; the accumulator chunk is computed by brute force from the flat tap list.
+// Debug cross-check of the tensor-core path (tests), never a fallback.
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kEpiThreads) tapgemm_simt_kernel(const __grid_constant__ TapGemmParams P,
                                                                    const TapSimtOperands ops) {
-    __shared__ __align__(16) float stile[EPI == kEpiBwd ? kBlockM * kStileStride : 4];
-    __shared__ float sflush[EPI == kEpiBwd ? 5 * BN : 1];
-    __shared__ int rowinfo[kBlockM];
-    const int t = threadIdx.x;
+    using C = Cfg<BN, EPI>;
+    __shared__ WarpSmem wsm[EPI == kEpiBwd ? 8 : 1];
+    const int e = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = e & 3, sub = e >> 2;
     int t_begin, t_end;
     tile_range(P, t_begin, t_end);
-    BwdState<BN> st;
-    if (EPI == kEpiBwd) bwd_state_init<BN>(st);
+    BwdState<C::kBwdSteps> st;
+    if (EPI == kEpiBwd) bwd_state_init(st);
     const int K = P.kchunks * kBlockK;
     const int box_px = P.th * P.tw;
-    for (int tile = t_begin; tile < t_end; ++tile) {
-        const TileCoord tc = decode_tile(P, tile);
+    for (int t = t_begin; t < t_end;) {
+        const Unit u = get_unit<C::kMtMax>(P, t, t_end);
+        t += u.mt;
+        const EpiSplit<BN> sp = epi_split<BN>(u.mt, sub);
+        const TileCoord tc = u.tile(sp.st);
         const TapProblem& pr = P.prob[tc.prob];
-        const int row = t & 127;
+        const int row = q * 32 + lane;
         const int ni = row / box_px, rem = row - ni * box_px;
         const int n = tc.n0 + ni, h = tc.h0 + rem / P.tw, w = tc.w0 + rem % P.tw;
         const bool in_box = ni < P.nb && n < P.batch;
@@ -641,28 +719,100 @@ __global__ void __launch_bounds__(kEpiThreads) tapgemm_simt_kernel(const __grid_
                 }
             }
         };
-        if constexpr (EPI == kEpiBwd) bwd_tile<BN, true>(P, tc, t, stile, sflush, rowinfo, st, load_chunk, [] {});
-        else rowowner_tile<BN, EPI>(P, tc, t, load_chunk);
+        if constexpr (EPI == kEpiBwd)
+            bwd_warp_tile<BN, C::kBwdSteps, true>(P, tc, q, lane, sp.ch_begin, sp.ch_end - sp.ch_begin, &wsm[e], st, load_chunk, [] {});
+        else
+            rowowner_warp_tile<BN, EPI>(P, tc, q, lane, sp.ch_begin, sp.ch_end, sp.whole ? 0 : sub, sp.whole, load_chunk);
     }
-    if (EPI == kEpiBwd && st.key >= 0) bwd_flush<BN>(P, st, t, sflush);
+    if (EPI == kEpiBwd) bwd_flush<BN, C::kBwdSteps>(P, st, lane);
 }
 
-// Seed of the backward chain: the backward epilogue with a zero accumulator (activation backward
-// of the top layer from the toRGB gradient alone).  Memory-bound elementwise pass.
-template <int BN>
-__global__ void __launch_bounds__(kEpiThreads, 2) tapgemm_seed_kernel(const __grid_constant__ TapGemmParams P) {
-    __shared__ float sflush[5 * BN];
-    __shared__ int rowinfo[kBlockM];
-    const int t = threadIdx.x;
-    int t_begin, t_end;
-    tile_range(P, t_begin, t_end);
-    BwdState<BN> st;
-    bwd_state_init<BN>(st);
-    for (int tile = t_begin; tile < t_end; ++tile) {
-        const TileCoord tc = decode_tile(P, tile);
-        bwd_tile<BN, false>(P, tc, t, nullptr, sflush, rowinfo, st, [](int, float (&)[32]) {}, [] {});
+// Seed of the backward chain: activation backward of the top layer from the toRGB gradient alone (the
+// backward epilogue with a zero accumulator).  Streaming kernel: a block owns one sample, up to 128
+// columns and a run of pixels; thread (cp, rl) owns a column pair and every (256 / pairs)-th pixel, so
+// coefficients and the five column sums live in registers, each pixel row is one coalesced segment and
+// many blocks fit an SM (HBM-bound: reads x, writes g_y).
+constexpr int kSeedPixels = 2048;
+__global__ void __launch_bounds__(256) seed_stream_kernel(const __grid_constant__ TapGemmParams P, int cpairs) {
+    __shared__ float red[256 * 8];
+    const int rlanes = 256 / cpairs;
+    const int cp = threadIdx.x % cpairs, rl = threadIdx.x / cpairs;
+    const int n = blockIdx.z;
+    const int col = blockIdx.y * (2 * cpairs) + 2 * cp;
+    const int img_px = P.OH * P.OW;
+    const int p_begin = blockIdx.x * kSeedPixels;
+    const int p_end = min(p_begin + kSeedPixels, img_px);
+    const int half_n = P.n_total >> 1;
+    const long long coff = static_cast<long long>(n) * P.n_total + col;
+    const float2 dm = __ldg(reinterpret_cast<const float2*>(P.demod_prev + coff));
+    const float2 bs = __ldg(reinterpret_cast<const float2*>(P.bias_prev + col));
+    float4 rw0 = __ldg(P.rgbw_prev + coff), rw1 = __ldg(P.rgbw_prev + coff + 1);
+    rw0.x *= P.act_gain; rw0.y *= P.act_gain; rw0.z *= P.act_gain;
+    rw1.x *= P.act_gain; rw1.y *= P.act_gain; rw1.z *= P.act_gain;
+    const float inv_gain = 1.f / P.act_gain, inv_gain_slope = 1.f / (P.act_gain * P.act_slope);
+    const float clampv = P.act_clamp >= 0.f ? P.act_clamp : __int_as_float(0x7f800000);
+    const long long base = static_cast<long long>(n) * img_px;
+    const unsigned* xh = reinterpret_cast<const unsigned*>(P.xp_hi) + base * half_n + (col >> 1);
+    const unsigned* xl = P.split ? reinterpret_cast<const unsigned*>(P.xp_lo) + base * half_n + (col >> 1) : nullptr;
+    unsigned* gh = reinterpret_cast<unsigned*>(P.gy_hi) + base * half_n + (col >> 1);
+    unsigned* gl = P.split ? reinterpret_cast<unsigned*>(P.gy_lo) + base * half_n + (col >> 1) : nullptr;
+    const float4* grgb = P.g_rgb + base;
+    const float* nzp = P.noise_prev ? P.noise_prev + n * P.noise_prev_stride_n : nullptr;
+    float r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = 0.f;
+    constexpr int U = 4;                       // pixels in flight per thread
+    for (int p0 = p_begin + rl; p0 < p_end; p0 += U * rlanes) {
+        unsigned xu[U], xv[U];
+        float4 g[U];
+        float nz[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int p = p0 + u * rlanes;
+            const bool ok = p < p_end;
+            const long long o = static_cast<long long>(ok ? p : p_begin) * half_n;
+            xu[u] = __ldg(xh + o);
+            xv[u] = xl ? __ldg(xl + o) : 0u;
+            g[u] = ok ? __ldg(grgb + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+            nz[u] = (nzp && ok) ? __ldg(nzp + p) * P.noise_prev_scale : 0.f;
+            if (!ok) { xu[u] = 0u; xv[u] = 0u; }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int p = p0 + u * rlanes;
+            const float x0 = bf16lo_f(xu[u]) + bf16lo_f(xv[u]), x1 = bf16hi_f(xu[u]) + bf16hi_f(xv[u]);
+            const float g0 = fmaf(g[u].x, rw0.x, fmaf(g[u].y, rw0.y, g[u].z * rw0.z));
+            const float g1 = fmaf(g[u].x, rw1.x, fmaf(g[u].y, rw1.y, g[u].z * rw1.z));
+            r[2] = fmaf(x0, g[u].x, r[2]); r[3] = fmaf(x1, g[u].x, r[3]);
+            r[4] = fmaf(x0, g[u].y, r[4]); r[5] = fmaf(x1, g[u].y, r[5]);
+            r[6] = fmaf(x0, g[u].z, r[6]); r[7] = fmaf(x1, g[u].z, r[7]);
+            const bool q0 = x0 > 0.f, q1 = x1 > 0.f;
+            float gz0 = g0 * (q0 ? 1.f : P.act_slope), gz1 = g1 * (q1 ? 1.f : P.act_slope);
+            gz0 = fabsf(x0) < clampv ? gz0 : 0.f;
+            gz1 = fabsf(x1) < clampv ? gz1 : 0.f;
+            const float z0 = x0 * (q0 ? inv_gain : inv_gain_slope), z1 = x1 * (q1 ? inv_gain : inv_gain_slope);
+            r[0] = fmaf(gz0, z0 - nz[u] - bs.x, r[0]);
+            r[1] = fmaf(gz1, z1 - nz[u] - bs.y, r[1]);
+            if (p < p_end) {
+                const float y0 = gz0 * dm.x, y1 = gz1 * dm.y;
+                const long long o = static_cast<long long>(p) * half_n;
+                gh[o] = pack_bf16(y0, y1);
+                if (gl) gl[o] = pack_bf16(y0 - bf16_round(y0), y1 - bf16_round(y1));
+            }
+        }
     }
-    if (st.key >= 0) bwd_flush<BN>(P, st, t, sflush);
+    // reduce the row lanes of each column pair, then one atomic per (sum, column)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[k * 256 + threadIdx.x] = r[k];
+    __syncthreads();
+    for (int e = threadIdx.x; e < 8 * cpairs; e += 256) {
+        const int k = e / cpairs, c = e - k * cpairs;
+        float v = 0.f;
+        for (int j = 0; j < rlanes; ++j) v += red[k * 256 + j * cpairs + c];
+        const int kind = k >> 1;                   // 0: red_d, 1..3: red_rgb
+        float* dst = kind == 0 ? P.red_d : P.red_rgb + static_cast<long long>(kind - 1) * P.batch * P.n_total;
+        atomicAdd(dst + static_cast<long long>(n) * P.n_total + blockIdx.y * (2 * cpairs) + 2 * c + (k & 1), v);
+    }
 }
 
 template <int BN, int EPI>
@@ -674,11 +824,14 @@ int launch_bn_epi(const TapGemmParams& p, int num_sms, cudaStream_t stream) {
         if (e != cudaSuccess) return static_cast<int>(e);
         attr_set = true;
     }
+    static_assert(Cfg<BN, EPI>::kSmemBytes <= 232448, "shared memory budget");
     const int total = p.m_tiles * p.n_blocks;
     int grid = total < num_sms ? total : num_sms;
     if (grid <= 0) return 0;
     for (int i = 0; i < p.nprob; ++i)
-        if (p.prob[i].ntaps <= 0) return static_cast<int>(cudaErrorInvalidValue);   // accumulator would be undefined
+        if (p.prob[i].ntaps <= 0 || p.prob[i].ngroups <= 0) return static_cast<int>(cudaErrorInvalidValue);   // accumulator would be undefined
+    if (p.halo != 0 && (p.halo != 2 || p.tw != 8 || p.nb != 1 || p.th != 16)) return static_cast<int>(cudaErrorInvalidValue);
+    if (p.nb * (p.th + p.halo) * p.tw * 128 > kASubBytes) return static_cast<int>(cudaErrorInvalidValue);
     tapgemm_kernel<BN, EPI><<<grid, kThreads, Cfg<BN, EPI>::kSmemBytes, stream>>>(p);
     return static_cast<int>(cudaGetLastError());
 }
@@ -716,25 +869,55 @@ int launch_simt_bn(const TapGemmParams& p, const TapSimtOperands& ops, cudaStrea
     }
 }
 
-template <int BN>
-int launch_seed_bn(const TapGemmParams& p, int num_sms, cudaStream_t stream) {
-    const int total = p.m_tiles * p.n_blocks;
-    int grid = total < num_sms * 6 ? total : num_sms * 6;
-    if (grid <= 0) return 0;
-    tapgemm_seed_kernel<BN><<<grid, kEpiThreads, 0, stream>>>(p);
-    return static_cast<int>(cudaGetLastError());
-}
-
 }  // namespace
 
-int launch_tapgemm_seed(const TapGemmParams& p, int num_sms, cudaStream_t stream) {
-    if (p.epilogue != kEpiBwd) return static_cast<int>(cudaErrorInvalidValue);
-    switch (p.n_total / p.n_blocks) {
-        case 256: return launch_seed_bn<256>(p, num_sms, stream);
-        case 128: return launch_seed_bn<128>(p, num_sms, stream);
-        case 64: return launch_seed_bn<64>(p, num_sms, stream);
-        default: return static_cast<int>(cudaErrorInvalidValue);
+int tapgemm_finalize(TapGemmParams& p) {
+    int ng = 0, nt = 0;
+    for (int i = 0; i < p.nprob; ++i) {
+        TapProblem& pr = p.prob[i];
+        pr.grp_begin = ng;
+        bool used[kMaxTaps] = {};
+        for (int a = 0; a < pr.ntaps; ++a) {
+            while (!used[a]) {       // groups keyed on (dx, src) of tap a; its lowest unused dy anchors the box
+                const Tap ta = p.taps[pr.tap_begin + a];
+                if (ng >= kMaxTaps) return -1;
+                TapGroup g{};
+                g.dx = ta.dx; g.src = ta.src; g.tap_begin = static_cast<uint16_t>(nt);
+                int dy0 = ta.dy;
+                if (p.halo > 0)
+                    for (int b = a; b < pr.ntaps; ++b) {
+                        const Tap tb = p.taps[pr.tap_begin + b];
+                        if (!used[b] && tb.dx == ta.dx && tb.src == ta.src && tb.dy < dy0) dy0 = tb.dy;
+                    }
+                g.dy0 = static_cast<int8_t>(dy0);
+                int cnt = 0;
+                for (int b = a; b < pr.ntaps; ++b) {
+                    const Tap tb = p.taps[pr.tap_begin + b];
+                    const bool same = p.halo > 0 ? (tb.dx == ta.dx && tb.src == ta.src) : (b == a);
+                    if (used[b] || !same) continue;
+                    const int rel = tb.dy - dy0;
+                    if (rel < 0 || rel > p.halo) continue;      // does not fit this box: a later group takes it
+                    used[b] = true;
+                    p.gdyrel[nt] = static_cast<uint8_t>(rel);
+                    p.gwidx[nt] = tb.widx;
+                    ++nt; ++cnt;
+                }
+                g.ntaps = static_cast<uint8_t>(cnt);
+                p.groups[ng++] = g;
+            }
+        }
+        pr.ngroups = ng - pr.grp_begin;
     }
+    return 0;
+}
+
+int launch_tapgemm_seed(const TapGemmParams& p, int /*num_sms*/, cudaStream_t stream) {
+    if (p.epilogue != kEpiBwd || !p.g_rgb || !p.rgbw_prev || p.n_total % 64) return static_cast<int>(cudaErrorInvalidValue);
+    const int pairs = p.n_total / 2;
+    const int cpairs = pairs >= 64 ? 64 : 32;
+    dim3 grid((p.OH * p.OW + kSeedPixels - 1) / kSeedPixels, pairs / cpairs, p.batch);
+    seed_stream_kernel<<<grid, 256, 0, stream>>>(p, cpairs);
+    return static_cast<int>(cudaGetLastError());
 }
 
 int launch_tapgemm(const TapGemmParams& p, int num_sms, cudaStream_t stream) {

@@ -9,8 +9,12 @@
 // instances of this contraction; split-bf16 ("fp32-parity") precision is three taps per
 // geometric tap: (A_hi,W_hi) + (A_lo,W_hi) + (A_hi,W_lo).   See DESIGN.md §3.
 //
-// M tile = nb images x th rows x tw cols (<= 128 pixels) fetched by one TMA box load per
-// (tap, 64-channel chunk); zero padding is TMA out-of-bounds fill.
+// M tile = nb images x th rows x tw cols (<= 128 pixels); zero padding is TMA out-of-bounds
+// fill.  Taps that share (source map, dx) and differ only in dy form a GROUP: with `halo` = 2
+// (tw == 8, nb == 1) one TMA box of th + 2 rows per (group, 64-channel chunk) feeds all of
+// them -- a row of 8 pixels is one 1024-byte swizzle atom, so the tap (dy) is just a start
+// offset of the UMMA descriptor -- and two consecutive M tiles share every weight tile
+// (operand traffic from L2 is the bound of this kernel: DESIGN.md §3.1).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -28,8 +32,17 @@ struct Tap {
     uint8_t src;         // which A tensor map
 };
 
+struct TapGroup {
+    int8_t dx, dy0;      // box origin offset of the group (dy0 = smallest dy of its taps)
+    uint8_t src;         // A tensor map
+    uint8_t ntaps;
+    uint16_t tap_begin;  // first entry of gdyrel / gwidx
+    uint16_t pad;
+};
+
 struct TapProblem {
     int tap_begin, ntaps;
+    int grp_begin, ngroups;
     int oy0, ox0;                  // output pixel = (h*osy + oy0, w*osx + ox0)
     int tile_begin;                // first M-tile index of this problem
     int tiles_h, tiles_w;          // tile grid of this problem (x tiles_n images)
@@ -47,7 +60,12 @@ enum TapEpilogue : int {
 struct TapGemmParams {
     alignas(64) CUtensorMap a_map[kMaxAMaps];
     alignas(64) CUtensorMap b_map;
-    Tap taps[kMaxTaps];
+    Tap taps[kMaxTaps];              // flat tap list (host bookkeeping + the SIMT twin)
+    TapGroup groups[kMaxTaps];       // the same taps grouped for the tensor-core kernel (tapgemm_finalize)
+    uint8_t gdyrel[kMaxTaps];        // per grouped tap: dy - dy0 of its group (0..halo)
+    uint8_t gwidx[kMaxTaps];         // per grouped tap: weight matrix
+    int halo;                        // extra rows of the A box (0 or 2); 2 needs tw == 8 and nb == 1
+    int no_pair;                     // 1: never pair M tiles (tuning switch)
     TapProblem prob[kMaxProblems];
     int nprob;
     int th, tw, nb;        // M-tile box: nb images x th rows x tw cols (nb*th*tw <= 128)
@@ -79,7 +97,7 @@ struct TapGemmParams {
     // ---- kEpiBwd: this GEMM is the data gradient of layer l; columns = channels of x_{l-1}
     const float* s_cur;                // [batch, N] style of layer l
     const void* xp_hi; const void* xp_lo;   // bf16 x_{l-1} [batch(or 1), OH, OW, N]
-    long long xp_stride_n;             // OH*OW*N, or 0 when x_{l-1} is the learned constant
+    long long xp_stride_n;             // must be OH*OW*N (the learned constant is replicated per sample)
     const float4* g_rgb;               // [batch, OH, OW] gradient wrt the toRGB output fed by x_{l-1}, or null
     const float4* rgbw_prev;           // [batch, N]
     const float* demod_prev;           // [batch, N]   (layer l-1)
@@ -101,6 +119,12 @@ struct TapGemmParams {
 
     int* err_flag;
 };
+
+// Groups the flat taps of every problem (call after taps / prob[].tap_begin / ntaps are set).  Returns 0 on success.
+int tapgemm_finalize(TapGemmParams& p);
+
+// Column block width the kernel is instantiated for: 64, 128 or 256.
+inline int tapgemm_bn(const TapGemmParams& p) { return p.n_total / p.n_blocks; }
 
 // tcgen05 path.  Returns cudaError_t as int.
 int launch_tapgemm(const TapGemmParams& p, int num_sms, cudaStream_t stream);
