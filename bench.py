@@ -281,7 +281,7 @@ def main():
         peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
         peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1.4 PFLOP/s sustained'
         rows, rgb_macs = layer_table(res, C, c.get('channel_base', 32768), c.get('channel_max', 512))
-        t = eng.debug_time_gemms(reps=3)
+        t = eng.debug_time_gemms(reps=10)
         tot_ms = sum(t['forward']) + sum(t['dgrad'])
         alg = 2.0 * 2.0 * B * sum(r['alg_macs'] for r in rows)          # fwd + dgrad launches of one step
         exe = 2.0 * 2.0 * B * sum(r['exe_macs'] for r in rows) * (3 if args.precision == 'fp32_parity' else 1)

@@ -114,7 +114,7 @@ namespace {
 // algorithmic MAC count); smaller ones keep the FIR folded into 36 taps (one launch, latency-bound anyway).
 int upconv_split_min_res() {
     const char* v = getenv("LA_UPCONV_SPLIT_MIN_RES");
-    return v ? atoi(v) : 64;
+    return v ? atoi(v) : 8;
 }
 
 // M tile of a grid of resolution g: 16 rows x 8 pixels with a 2-row halo (the three vertical taps share
@@ -129,15 +129,17 @@ long long grid_m_tiles(int g, int batch) {
     tile_geometry(g, th, tw, nb, halo);
     return static_cast<long long>((batch + nb - 1) / nb) * ((g + th - 1) / th) * ((g + tw - 1) / tw);
 }
-// Column block: 128 (two M tiles share each weight tile), 64 when the layer has 64 channels or the grid is
-// too small to occupy the SMs with 128-wide blocks.
+// Column block: 256 where the channel count allows (N = 256 MMAs run at the full tensor rate, N = 128 ones at
+// about 80 % of it), 128 with two M tiles sharing each weight tile otherwise, 64 when the layer has 64 channels
+// or the grid is too small to occupy the SMs with wider blocks.
 int pick_bn(int n, long long m_tiles = 1 << 30) {
     if (n % 64) return 0;
     if (n == 64) return 64;
     if (n % 128) return 0;
     static const int force = getenv("LA_BN") ? atoi(getenv("LA_BN")) : 0;      // tuning switch
     if (force && n % force == 0) return force;
-    return m_tiles * (n / 128) <= 74 ? 64 : 128;
+    if (m_tiles * (n / 128) <= 74) return 64;
+    return n % 256 == 0 ? 256 : 128;
 }
 
 int make_a_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, long long sW, long long sH, long long sN, int tw, int th,
@@ -146,6 +148,14 @@ int make_a_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, lon
     uint64_t strides[3] = {static_cast<uint64_t>(sW) * 2, static_cast<uint64_t>(sH) * 2, static_cast<uint64_t>(sN) * 2};
     uint32_t box[4] = {64, static_cast<uint32_t>(tw), static_cast<uint32_t>(th), static_cast<uint32_t>(nb)};
     return encode_tmap_bf16(m, base, 4, dims, strides, box);
+}
+// Output map of the row-owner epilogues: box = 32 channels x the 32 tile rows one epilogue warp owns, SWIZZLE_64B.
+int make_o_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, long long sW, long long sH, long long sN, int tw, int th) {
+    uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(N)};
+    uint64_t strides[3] = {static_cast<uint64_t>(sW) * 2, static_cast<uint64_t>(sH) * 2, static_cast<uint64_t>(sN) * 2};
+    const int px = th * tw;
+    uint32_t box[4] = {32, static_cast<uint32_t>(tw), static_cast<uint32_t>(px >= 32 ? 32 / tw : th), static_cast<uint32_t>(px >= 32 ? 1 : 32 / px)};
+    return encode_tmap_bf16(m, base, 4, dims, strides, box, 64);
 }
 int make_b_map(CUtensorMap* m, const void* base, int K, int rows, int nmat, int bn) {
     uint64_t dims[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(rows), static_cast<uint64_t>(nmat)};
@@ -384,11 +394,45 @@ int build_params(la_engine* e) {
                     if (fabsf(U.fy[k / 4] * U.fx[k % 4] - U.fk[k]) > 1e-6f * fabsf(U.fk[bi])) U.separable = 0;
             }
             U.gy_hi = e->gy_hi[l & 1]; U.gy_lo = e->gy_lo[l & 1]; U.gt_hi = e->t_hi; U.gt_lo = e->t_lo;
+            static const bool no_fir_tma = getenv("LA_NO_FIR_TMA") != nullptr;
+            if (!split && U.separable && c.res >= 32 && c.cout % 64 == 0 && !no_fir_tma) {
+                const uint64_t C = c.cout, R = c.res;
+                const uint64_t tdims[4] = {C, R + 1, R + 1, static_cast<uint64_t>(B)};          // T: (2H+1) x (2W+1), row pitch TWp
+                const uint64_t tstr[3] = {C * 2, static_cast<uint64_t>(TWp) * C * 2, static_cast<uint64_t>(TH) * TWp * C * 2};
+                const uint64_t ydims[4] = {C, R, R, static_cast<uint64_t>(B)};
+                const uint64_t ystr[3] = {C * 2, R * C * 2, R * R * C * 2};
+                const uint32_t lbox[4] = {64, 35, 1, 1}, sbox[4] = {64, 8, 1, 1};
+                int r = encode_tmap_bf16(&U.fwd_in, e->t_hi, 4, tdims, tstr, lbox, 0);
+                r |= encode_tmap_bf16(&U.fwd_out_x, c.x_hi, 4, ydims, ystr, sbox, 0);
+                if (next) r |= encode_tmap_bf16(&U.fwd_out_xs, e->xs_hi[(l + 1) & 1], 4, ydims, ystr, sbox, 0);
+                r |= encode_tmap_bf16(&U.bwd_in, e->gy_hi[l & 1], 4, ydims, ystr, lbox, 0);
+                r |= encode_tmap_bf16(&U.bwd_out, e->t_hi, 4, tdims, tstr, sbox, 0);
+                if (r) return fail(-5, "tensor map encoding failed (FIR pass)");
+                U.use_tma = 1;
+            }
             // the GEMM only stores T
             F.epilogue = kEpiStoreBf16;
             F.OH = TH; F.OW = TWp;
             F.x_hi = e->t_hi; F.x_lo = e->t_lo;
             F.xs_hi = F.xs_lo = nullptr; F.s_next = nullptr; F.rgbw = nullptr;
+        }
+
+        // tensor stores of the forward epilogue (bf16 mode; the folded x2 layers keep per-thread stores)
+        static const bool no_tma_store = getenv("LA_NO_TMA_STORE") != nullptr;
+        if (!split && !no_tma_store) {
+            if (c.split_up) {
+                for (int ph = 0; ph < 4; ++ph) {
+                    const int py = ph / 2, px = ph % 2;
+                    LA(make_o_map(&F.o_map[ph], e->t_hi + (static_cast<long long>(py) * TWp + px) * c.cout, c.cout, F.prob[ph].vw, F.prob[ph].vh, B,
+                                  2LL * c.cout, 2LL * TWp * c.cout, static_cast<long long>(TH) * TWp * c.cout, F.tw, F.th));
+                }
+                F.tma_store = 1;
+            } else if (c.up == 1) {
+                const long long oW = c.cout, oH = static_cast<long long>(c.res) * c.cout, oN = oH * c.res;
+                LA(make_o_map(&F.o_map[0], c.x_hi, c.cout, c.res, c.res, B, oW, oH, oN, F.tw, F.th));
+                if (next) LA(make_o_map(&F.o_map[1], e->xs_hi[(l + 1) & 1], c.cout, c.res, c.res, B, oW, oH, oN, F.tw, F.th));
+                F.tma_store = 1;
+            }
         }
 
         // ---------------------------------------------------------------- data gradient

@@ -3,6 +3,8 @@
 
 #include <cuda_bf16.h>
 
+#include "sm100.cuh"
+
 namespace la {
 
 namespace {
@@ -313,6 +315,128 @@ __global__ void __launch_bounds__(256, SEP ? 3 : 2) upfir_slide_kernel(const __g
 #pragma unroll
             for (int k = 0; k < 3; ++k) win[ky][k] = win[ky][4 + k];
     }
+}
+
+// TMA-pipelined 4x4 separable FIR (the same two operators as upfir_slide_kernel).  A CTA owns a strip of
+// 32 output columns x 64 channels of one sample and walks down a run of output rows; a producer warp
+// streams the source rows (35 pixels x 128 B, zero-filled outside the tensor) into a ring of kFirRing
+// slots, four consumer warps (8 output pixels each, lane = channel pair) keep the vertical window in
+// the ring, and each warp writes its pixels through a double-buffered staging tile with tensor stores.
+// Every source element is read from global memory once (+ the 3-pixel strip halo).
+constexpr int kFirRing = 8, kFirStrip = 32, kFirSlotBytes = 4608, kFirInPx = 35;
+template <bool FWD>
+__global__ void __launch_bounds__(160) upfir_tma_kernel(const __grid_constant__ UpFirParams P, int rows_per_cta, int nslabs) {
+    extern __shared__ __align__(128) uint8_t fsm[];
+    uint8_t* ring = fsm;                                         // kFirRing x 4608
+    uint8_t* stage = fsm + kFirRing * kFirSlotBytes;             // 4 warps x 2 buffers x 2 tensors x 1 KB
+    uint64_t* full = reinterpret_cast<uint64_t*>(stage + 4 * 2 * 2 * 1024);
+    uint64_t* empty = full + kFirRing;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slab = blockIdx.y % nslabs, rblk = blockIdx.y / nslabs;
+    const int n = blockIdx.z;
+    const int x0 = blockIdx.x * kFirStrip;
+    const int out_h = FWD ? P.OH : P.TH;
+    const int r0 = rblk * rows_per_cta, r1 = min(r0 + rows_per_cta, out_h);
+    const int org = FWD ? -1 : -2;
+    const int c0 = slab * 64;
+    const CUtensorMap* in_map = FWD ? &P.fwd_in : &P.bwd_in;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kFirRing; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
+        fence_barrier_init();
+        prefetch_tmap(in_map);
+    }
+    __syncthreads();
+    const int nrows_in = (r1 - r0) + 3;
+    if (warp == 4) {
+        if (lane == 0) {
+            for (int j = 0; j < nrows_in; ++j) {
+                const int s = j % kFirRing;
+                mbar_wait(&empty[s], ((j / kFirRing) & 1) ^ 1, nullptr, 0);
+                mbar_expect_tx(&full[s], kFirInPx * 128);
+                tma_load_4d(ring + s * kFirSlotBytes, in_map, &full[s], c0, x0 + org, r0 + org + j, n);
+            }
+        }
+        return;
+    }
+    float wy[4], wx[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { wy[k] = FWD ? P.fy[k] : P.fy[3 - k]; wx[k] = FWD ? P.fx[k] : P.fx[3 - k]; }
+    float2 dm = make_float2(0.f, 0.f), bs = dm, sn = dm;
+    const int c = c0 + 2 * lane;
+    if (FWD) {
+        dm = __ldg(reinterpret_cast<const float2*>(P.demod + static_cast<long long>(n) * P.C + c));
+        bs = __ldg(reinterpret_cast<const float2*>(P.bias + c));
+        if (P.s_next) sn = __ldg(reinterpret_cast<const float2*>(P.s_next + static_cast<long long>(n) * P.C + c));
+    }
+    const float clampv = P.act_clamp >= 0.f ? P.act_clamp : __int_as_float(0x7f800000);
+    const int px0 = warp * 8;                                    // this warp's first output pixel inside the strip
+    uint8_t* my_stage = stage + warp * 4096;
+    for (int j = 0; j < 3; ++j) mbar_wait(&full[j % kFirRing], (j / kFirRing) & 1, nullptr, 0);
+    for (int r = r0; r < r1; ++r) {
+        const int j0 = r - r0;
+        mbar_wait(&full[(j0 + 3) % kFirRing], ((j0 + 3) / kFirRing) & 1, nullptr, 0);
+        // vertical pass: 11 window columns, 2 channels each
+        float2 cs[11];
+#pragma unroll
+        for (int q = 0; q < 11; ++q) cs[q] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned* row = reinterpret_cast<const unsigned*>(ring + ((j0 + k) % kFirRing) * kFirSlotBytes) + px0 * 32 + lane;
+#pragma unroll
+            for (int q = 0; q < 11; ++q) {
+                const unsigned u = row[q * 32];
+                cs[q].x = fmaf(wy[k], __uint_as_float(u << 16), cs[q].x);
+                cs[q].y = fmaf(wy[k], __uint_as_float(u & 0xffff0000u), cs[q].y);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[j0 % kFirRing]);       // the oldest row of the window is done
+        float nzv[8];
+        if (FWD && P.noise) {
+            const float4* np = reinterpret_cast<const float4*>(P.noise + n * P.noise_stride_n + static_cast<long long>(r) * P.OW + x0 + px0);
+            const bool in = x0 + px0 + 8 <= P.OW;
+            const float4 a = in ? __ldg(np) : make_float4(0.f, 0.f, 0.f, 0.f), b = in ? __ldg(np + 1) : a;
+            nzv[0] = a.x; nzv[1] = a.y; nzv[2] = a.z; nzv[3] = a.w; nzv[4] = b.x; nzv[5] = b.y; nzv[6] = b.z; nzv[7] = b.w;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) nzv[i] *= P.noise_scale;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) nzv[i] = 0.f;
+        }
+        uint8_t* sx = my_stage + (j0 & 1) * 2048;                // [x | xs] x 1 KB, double-buffered by row parity
+        if (lane == 0) bulk_wait_read<1>();                       // the stores of two rows ago have read this buffer
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { a0 = fmaf(wx[k], cs[i + k].x, a0); a1 = fmaf(wx[k], cs[i + k].y, a1); }
+            if (FWD) {
+                float z0 = fmaf(a0, dm.x, nzv[i]) + bs.x, z1 = fmaf(a1, dm.y, nzv[i]) + bs.y;
+                z0 = (z0 > 0.f ? z0 : z0 * P.act_slope) * P.act_gain;
+                z1 = (z1 > 0.f ? z1 : z1 * P.act_slope) * P.act_gain;
+                z0 = fminf(fmaxf(z0, -clampv), clampv);
+                z1 = fminf(fmaxf(z1, -clampv), clampv);
+                reinterpret_cast<unsigned*>(sx)[i * 32 + lane] = pack2(z0, z1);
+                reinterpret_cast<unsigned*>(sx + 1024)[i * 32 + lane] = pack2(z0 * sn.x, z1 * sn.y);
+            } else {
+                reinterpret_cast<unsigned*>(sx)[i * 32 + lane] = pack2(a0, a1);
+            }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            if (FWD) {
+                tma_store_4d(&P.fwd_out_x, sx, c0, x0 + px0, r, n);
+                if (P.s_next) tma_store_4d(&P.fwd_out_xs, sx + 1024, c0, x0 + px0, r, n);
+            } else {
+                tma_store_4d(&P.bwd_out, sx, c0, x0 + px0, r, n);
+            }
+            bulk_commit();
+        }
+    }
+    // the last three window rows were never released: nobody waits for them
+    if (lane == 0) bulk_wait_read<0>();
 }
 
 // ------------------------------------------------------------------------- toRGB + skip pyramid
@@ -755,6 +879,27 @@ static int max_cin(const LayerTable& T, bool conv, bool rgb) {
 }
 
 static int upfir_launch(const UpFirParams& p, bool fwd, cudaStream_t s) {
+    if (p.use_tma) {
+        const int smem = kFirRing * kFirSlotBytes + 4 * 2 * 2 * 1024 + 2 * kFirRing * 8;
+        const int out_h = fwd ? p.OH : p.TH, out_w = fwd ? p.OW : p.OW + 1;
+        const int nslabs = p.C / 64;
+        const int strips = cdiv(out_w, kFirStrip);
+        // enough CTAs for ~4 per SM, but runs of at least 32 rows (3 halo rows are re-read per run)
+        int rblocks = 1;
+        while (static_cast<long long>(strips) * nslabs * p.B * rblocks < 148 * 6 && out_h / (rblocks * 2) >= 32) rblocks *= 2;
+        const int rows_per_cta = cdiv(out_h, rblocks);
+        dim3 grid(strips, nslabs * cdiv(out_h, rows_per_cta), p.B);
+        if (fwd) {
+            static bool a = false;
+            if (!a) { cudaFuncSetAttribute(upfir_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); a = true; }
+            upfir_tma_kernel<true><<<grid, 160, smem, s>>>(p, rows_per_cta, nslabs);
+        } else {
+            static bool a = false;
+            if (!a) { cudaFuncSetAttribute(upfir_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); a = true; }
+            upfir_tma_kernel<false><<<grid, 160, smem, s>>>(p, rows_per_cta, nslabs);
+        }
+        return last_err();
+    }
     const int hc = p.C / 2;
     int cpb = hc < 256 ? hc : 256;
     if (256 % cpb || hc % cpb) return static_cast<int>(cudaErrorInvalidValue);   // channel counts are 64 * 2^k

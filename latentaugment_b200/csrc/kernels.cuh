@@ -2,6 +2,7 @@
 // coefficients, toRGB + skip pyramid (forward and backward), criteria, style gradients,
 // the fused Adam step on w, the mapping network and bank statistics.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -54,6 +55,11 @@ struct UpFirParams {
     // backward: g_y [B, OH, OW, C] -> g_T
     const void* gy_hi; const void* gy_lo;
     void* gt_hi; void* gt_lo;
+    // TMA-pipelined variant (bf16 mode, separable filter, OW >= 32, C % 64 == 0): tensor maps over
+    // [C, width, height, B] with boxes [64, 35, 1, 1] (loads, no swizzle) and [64, 8, 1, 1] (stores).
+    int use_tma;
+    alignas(64) CUtensorMap fwd_in, fwd_out_x, fwd_out_xs;     // T -> x, x * s_next
+    alignas(64) CUtensorMap bwd_in, bwd_out;                   // g_y -> g_T
 };
 int upfir_forward(const UpFirParams& p, cudaStream_t s);
 int upfir_backward(const UpFirParams& p, cudaStream_t s);

@@ -35,11 +35,14 @@ struct Cfg {
     static constexpr int kMtMax = BN == 256 ? 1 : 2;             // M tiles per unit (they share every weight tile)
     static constexpr int kASlotBytes = kMtMax * kASubBytes;
     static constexpr int kBBytes = BN * kBlockK * 2;
-    static constexpr int kAStages = BN == 256 ? 4 : 3;
-    static constexpr int kBStages = EPI == kEpiBwd ? (BN == 256 ? 3 : (BN == 128 ? 4 : 6)) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
+    static constexpr int kAStages = (BN == 256 && EPI == kEpiBwd) ? 4 : 3;
+    static constexpr int kBStages = EPI == kEpiBwd ? (BN == 256 ? 3 : (BN == 128 ? 4 : 6)) : (BN == 256 ? 4 : (BN == 128 ? 5 : 8));
     static constexpr int kTmemCols = 2 * kMtMax * BN;            // two accumulator stages
-    static constexpr int kEpiSmemBytes = EPI == kEpiBwd ? 8 * static_cast<int>(sizeof(WarpSmem)) : 0;
-    static constexpr int kSmemBytes = kAStages * kASlotBytes + kBStages * kBBytes + kEpiSmemBytes + 256 /*barriers*/ + 1024 /*align slack*/;
+    // per-warp staging of the tensor stores: 32 rows x 32 channels bf16 = 2 KB per output tensor
+    static constexpr int kStageTensors = EPI == kEpiFwd ? 2 : (EPI == kEpiStoreBf16 ? 1 : 0);
+    static constexpr int kEpiSmemBytes = EPI == kEpiBwd ? 8 * static_cast<int>(sizeof(WarpSmem)) : 8 * 2048 * kStageTensors;
+    static constexpr int kABytes = kAStages * kASlotBytes;       // unpaired launches cut this region into kASubBytes slots
+    static constexpr int kSmemBytes = kABytes + kBStages * kBBytes + kEpiSmemBytes + 320 /*barriers*/ + 1024 /*align slack*/;
     static constexpr int kBwdSteps = BN == 64 ? 2 : 4;           // 32-column steps one warp walks per tile (all of BN, or half of it)
 };
 
@@ -185,13 +188,30 @@ __device__ __forceinline__ RowCtx make_row(const TapGemmParams& P, const TileCoo
     return r;
 }
 
+// Stage one 32-value row chunk as bf16 into the warp's [32 rows x 64 B] SWIZZLE_64B staging tile.
+__device__ __forceinline__ void stage_bf16x32(uint8_t* stg, int lane, const float (&v)[32]) {
+    uint8_t* rowp = stg + lane * 64;
+    const int sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        o.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+        o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+        o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+        o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+        *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = o;
+    }
+}
+
 // ---- row-owner epilogues: raw store, bf16 store, forward activation, top-k.
 // The lane owns row 32*q + lane and walks chunks [ch_begin, ch_end); `part` selects the per-column-block
 // slot (0 / 1) of the per-row outputs (toRGB partial, top-k candidates); with `fill_other` the other slot is
-// written as empty (the warp covered the whole column block).
-template <int BN, int EPI, class LoadChunk>
+// written as empty (the warp covered the whole column block).  With kTma the bf16 outputs go through the
+// warp's shared-memory staging tile and one tensor store per 32-channel chunk (full 64-byte row segments
+// instead of 16-byte pieces per thread); `stg` = kStageTensors x 2 KB.
+template <int BN, int EPI, bool kTma, class LoadChunk>
 __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const TileCoord& tc, int q, int lane, int ch_begin, int ch_end,
-                                                   int part, bool fill_other, LoadChunk&& load_chunk) {
+                                                   int part, bool fill_other, uint8_t* stg, LoadChunk&& load_chunk) {
     const RowCtx rc = make_row(P, tc, q * 32 + lane);
     float nz = 0.f;
     if (EPI == kEpiFwd && rc.valid && P.noise) nz = __ldg(P.noise + rc.n * P.noise_stride_n + rc.px_in_img) * P.noise_scale;
@@ -201,6 +221,13 @@ __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const
 #pragma unroll
     for (int k = 0; k < 8; ++k) { best_s[k] = __int_as_float(0x7f800000); best_i[k] = -1; }
     const bool tk_valid = rc.valid && rc.pix < P.n_queries;
+    // tensor-store coordinates of the warp's 32 rows (a box of 32 / tw image rows, or whole small images)
+    int sc1 = 0, sc2 = 0, sc3 = 0;
+    if (kTma) {
+        const int box_px = P.th * P.tw, r0 = q * 32;
+        const int ni = r0 / box_px, rem = r0 - ni * box_px;
+        sc1 = tc.w0; sc2 = tc.h0 + rem / P.tw; sc3 = tc.n0 + ni;
+    }
 
 #pragma unroll 1
     for (int ch = ch_begin; ch < ch_end; ++ch) {
@@ -216,7 +243,16 @@ __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const
                 for (int j = 0; j < 8; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
             }
         } else if constexpr (EPI == kEpiStoreBf16) {
-            if (rc.valid) store_bf16x32(P.x_hi, P.split ? P.x_lo : nullptr, eoff, acc);
+            if (kTma) {
+                if (lane == 0) bulk_wait_read<0>();       // the previous store has read the staging tile
+                __syncwarp();
+                stage_bf16x32(stg, lane, acc);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) { tma_store_4d(&P.o_map[tc.prob], stg, col0, sc1, sc2, sc3); bulk_commit(); }
+            } else if (rc.valid) {
+                store_bf16x32(P.x_hi, P.split ? P.x_lo : nullptr, eoff, acc);
+            }
         } else if constexpr (EPI == kEpiTopK) {
             if (tk_valid) {
 #pragma unroll
@@ -239,6 +275,7 @@ __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const
                 }
             }
         } else if constexpr (EPI == kEpiFwd) {
+            float xs[32];
             if (rc.valid) {
                 float dm[32], bs[32];
                 load_f32x32(P.demod + coff, dm);
@@ -250,7 +287,7 @@ __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const
                     if (P.act_clamp >= 0.f) z = fminf(fmaxf(z, -P.act_clamp), P.act_clamp);
                     acc[j] = z;
                 }
-                store_bf16x32(P.x_hi, P.split ? P.x_lo : nullptr, eoff, acc);
+                if (!kTma) store_bf16x32(P.x_hi, P.split ? P.x_lo : nullptr, eoff, acc);
                 if (P.rgbw) {
                     const float4* rw = P.rgbw + coff;
 #pragma unroll
@@ -264,8 +301,21 @@ __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const
                 if (P.s_next) {
                     load_f32x32(P.s_next + coff, dm);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[j] *= dm[j];
-                    store_bf16x32(P.xs_hi, P.split ? P.xs_lo : nullptr, eoff, acc);
+                    for (int j = 0; j < 32; ++j) xs[j] = acc[j] * dm[j];
+                    if (!kTma) store_bf16x32(P.xs_hi, P.split ? P.xs_lo : nullptr, eoff, xs);
+                }
+            }
+            if (kTma) {
+                if (lane == 0) bulk_wait_read<0>();
+                __syncwarp();
+                stage_bf16x32(stg, lane, acc);                 // masked rows stage garbage; the tensor store clips them
+                if (P.s_next) stage_bf16x32(stg + 2048, lane, xs);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_4d(&P.o_map[0], stg, col0, sc1, sc2, sc3);
+                    if (P.s_next) tma_store_4d(&P.o_map[1], stg + 2048, col0, sc1, sc2, sc3);
+                    bulk_commit();
                 }
             }
         }
@@ -508,14 +558,18 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     uint8_t* a_smem = smem;
     uint8_t* b_smem = smem + C::kAStages * C::kASlotBytes;
     uint8_t* epi_smem = b_smem + C::kBStages * C::kBBytes;
+    constexpr int kMaxAStages = 8;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(epi_smem + C::kEpiSmemBytes);
-    uint64_t* a_empty = a_full + C::kAStages;
-    uint64_t* b_full = a_empty + C::kAStages;
+    uint64_t* a_empty = a_full + kMaxAStages;
+    uint64_t* b_full = a_empty + kMaxAStages;
     uint64_t* b_empty = b_full + C::kBStages;
     uint64_t* tfull_bar = b_empty + C::kBStages;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    static_assert((2 * C::kAStages + 2 * C::kBStages + 4) * 8 + 4 <= 256, "barrier area");
+    static_assert((2 * kMaxAStages + 2 * C::kBStages + 4) * 8 + 4 <= 320, "barrier area");
+    // A ring: slots of one M tile when the launch never pairs tiles (twice as many stages in flight)
+    const int a_slot_bytes = (C::kMtMax == 2 && !P.no_pair) ? 2 * kASubBytes : kASubBytes;
+    const int a_stages = min(kMaxAStages, C::kABytes / a_slot_bytes);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -527,7 +581,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
         prefetch_tmap(&P.b_map);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < C::kAStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < kMaxAStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < C::kBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
@@ -559,12 +613,12 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
                     const CUtensorMap* amap = &P.a_map[grp.src];
                     for (int kc = 0; kc < P.kchunks; ++kc) {
                         mbar_wait(&a_empty[as], aph ^ 1, P.err_flag, 1);
-                        uint8_t* sa = a_smem + as * C::kASlotBytes;
+                        uint8_t* sa = a_smem + as * a_slot_bytes;
                         mbar_expect_tx(&a_full[as], a_tx_bytes * u.mt);
                         tma_load_4d(sa, amap, &a_full[as], kc * kBlockK, u.tc0.w0 + grp.dx, u.tc0.h0 + grp.dy0, u.tc0.n0);
                         if (u.mt == 2)
                             tma_load_4d(sa + kASubBytes, amap, &a_full[as], kc * kBlockK, u.tc1.w0 + grp.dx, u.tc1.h0 + grp.dy0, u.tc1.n0);
-                        if (++as == C::kAStages) { as = 0; aph ^= 1; }
+                        if (++as == a_stages) { as = 0; aph ^= 1; }
                         for (int j = 0; j < grp.ntaps; ++j) {
                             mbar_wait(&b_empty[bs], bph ^ 1, P.err_flag, 5);
                             mbar_expect_tx(&b_full[bs], C::kBBytes);
@@ -594,7 +648,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
                     const TapGroup grp = P.groups[pr.grp_begin + g];
                     for (int kc = 0; kc < P.kchunks; ++kc) {
                         mbar_wait(&a_full[as], aph, P.err_flag, 3);
-                        const uint32_t sa = smem_u32(a_smem + as * C::kASlotBytes);
+                        const uint32_t sa = smem_u32(a_smem + as * a_slot_bytes);
                         for (int j = 0; j < grp.ntaps; ++j) {
                             mbar_wait(&b_full[bs], bph, P.err_flag, 6);
                             tc_fence_after();
@@ -612,7 +666,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
                             if (++bs == C::kBStages) { bs = 0; bph ^= 1; }
                         }
                         umma_commit(&a_empty[as]);
-                        if (++as == C::kAStages) { as = 0; aph ^= 1; }
+                        if (++as == a_stages) { as = 0; aph ^= 1; }
                     }
                 }
                 umma_commit(&tfull_bar[acc]);
@@ -657,12 +711,17 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
             if constexpr (EPI == kEpiBwd) {
                 bwd_warp_tile<BN, C::kBwdSteps, true>(P, tc, q, lane, sp.ch_begin, sp.ch_end - sp.ch_begin, ws, st, load_chunk, release);
             } else {
-                rowowner_warp_tile<BN, EPI>(P, tc, q, lane, sp.ch_begin, sp.ch_end, sp.whole ? 0 : sub, sp.whole, load_chunk);
+                uint8_t* stg = epi_smem + e * (2048 * C::kStageTensors);
+                if (C::kStageTensors > 0 && P.tma_store)
+                    rowowner_warp_tile<BN, EPI, (C::kStageTensors > 0)>(P, tc, q, lane, sp.ch_begin, sp.ch_end, sp.whole ? 0 : sub, sp.whole, stg, load_chunk);
+                else
+                    rowowner_warp_tile<BN, EPI, false>(P, tc, q, lane, sp.ch_begin, sp.ch_end, sp.whole ? 0 : sub, sp.whole, nullptr, load_chunk);
                 release();
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (EPI == kEpiBwd) bwd_flush<BN, C::kBwdSteps>(P, st, lane);
+        if (C::kStageTensors > 0 && lane == 0) bulk_wait_read<0>();      // staging tiles stay valid until the last store has read them
     }
 
     tc_fence_before();
@@ -722,7 +781,7 @@ __global__ void __launch_bounds__(kEpiThreads) tapgemm_simt_kernel(const __grid_
         if constexpr (EPI == kEpiBwd)
             bwd_warp_tile<BN, C::kBwdSteps, true>(P, tc, q, lane, sp.ch_begin, sp.ch_end - sp.ch_begin, &wsm[e], st, load_chunk, [] {});
         else
-            rowowner_warp_tile<BN, EPI>(P, tc, q, lane, sp.ch_begin, sp.ch_end, sp.whole ? 0 : sub, sp.whole, load_chunk);
+            rowowner_warp_tile<BN, EPI, false>(P, tc, q, lane, sp.ch_begin, sp.ch_end, sp.whole ? 0 : sub, sp.whole, nullptr, load_chunk);
     }
     if (EPI == kEpiBwd) bwd_flush<BN, C::kBwdSteps>(P, st, lane);
 }
@@ -815,6 +874,114 @@ __global__ void __launch_bounds__(256) seed_stream_kernel(const __grid_constant_
     }
 }
 
+// The same seed pass as an asynchronous pipeline (bf16 mode, N <= 256): a block streams runs of 32 pixels
+// of one sample through shared memory with 1-D bulk copies -- x in, g_y out in place -- so the bytes in
+// flight live in shared memory instead of registers and HBM stays busy.
+constexpr int kSeedRows = 32, kSeedStages = 4;
+__global__ void __launch_bounds__(128) seed_bulk_kernel(const __grid_constant__ TapGemmParams P, int px_per_block) {
+    extern __shared__ __align__(128) uint8_t sraw[];
+    const int N = P.n_total, pairs = N >> 1, rlanes = 128 / pairs, rows_per_thread = kSeedRows / rlanes;
+    const uint32_t xbytes = kSeedRows * N * 2;
+    const uint32_t stage_bytes = xbytes + kSeedRows * 16 + kSeedRows * 4;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sraw + kSeedStages * stage_bytes);
+    float* red = reinterpret_cast<float*>(sraw);             // reused after the pipeline drained
+    const int n = blockIdx.y;
+    const int img_px = P.OH * P.OW;
+    const int p_begin = blockIdx.x * px_per_block;
+    const int p_end = min(p_begin + px_per_block, img_px);
+    const int nchunks = (p_end - p_begin) / kSeedRows;       // img_px and px_per_block are multiples of 32
+    const long long base = static_cast<long long>(n) * img_px;
+    const __nv_bfloat16* xg = reinterpret_cast<const __nv_bfloat16*>(P.xp_hi) + base * N;
+    __nv_bfloat16* gg = reinterpret_cast<__nv_bfloat16*>(P.gy_hi) + base * N;
+    const float4* grgb = P.g_rgb + base;
+    const float* nzp = P.noise_prev ? P.noise_prev + n * P.noise_prev_stride_n : nullptr;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < kSeedStages; ++s) mbar_init(&full[s], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    auto issue = [&](int chunk) {
+        const int s = chunk % kSeedStages;
+        uint8_t* st = sraw + s * stage_bytes;
+        const int p = p_begin + chunk * kSeedRows;
+        mbar_expect_tx(&full[s], xbytes + kSeedRows * 16 + (nzp ? kSeedRows * 4 : 0));
+        bulk_load(st, xg + static_cast<long long>(p) * N, xbytes, &full[s]);
+        bulk_load(st + xbytes, grgb + p, kSeedRows * 16, &full[s]);
+        if (nzp) bulk_load(st + xbytes + kSeedRows * 16, nzp + p, kSeedRows * 4, &full[s]);
+    };
+    if (tid == 0)
+        for (int c = 0; c < kSeedStages && c < nchunks; ++c) issue(c);
+
+    const int cp = tid % pairs, rl = tid / pairs;
+    const int col = 2 * cp;
+    const long long coff = static_cast<long long>(n) * N + col;
+    const float2 dm = __ldg(reinterpret_cast<const float2*>(P.demod_prev + coff));
+    const float2 bs = __ldg(reinterpret_cast<const float2*>(P.bias_prev + col));
+    float4 rw0 = __ldg(P.rgbw_prev + coff), rw1 = __ldg(P.rgbw_prev + coff + 1);
+    rw0.x *= P.act_gain; rw0.y *= P.act_gain; rw0.z *= P.act_gain;
+    rw1.x *= P.act_gain; rw1.y *= P.act_gain; rw1.z *= P.act_gain;
+    const float inv_gain = 1.f / P.act_gain, inv_gain_slope = 1.f / (P.act_gain * P.act_slope);
+    const float clampv = P.act_clamp >= 0.f ? P.act_clamp : __int_as_float(0x7f800000);
+    const float nscale = nzp ? P.noise_prev_scale : 0.f;
+    float r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = 0.f;
+
+    for (int it = 0; it < nchunks; ++it) {
+        const int s = it % kSeedStages;
+        uint8_t* st = sraw + s * stage_bytes;
+        mbar_wait(&full[s], (it / kSeedStages) & 1, P.err_flag, 7);
+        unsigned* xs = reinterpret_cast<unsigned*>(st);
+        const float4* gs = reinterpret_cast<const float4*>(st + xbytes);
+        const float* ns = reinterpret_cast<const float*>(st + xbytes + kSeedRows * 16);
+#pragma unroll 8
+        for (int j = 0; j < rows_per_thread; ++j) {
+            const int row = rl + j * rlanes;
+            const unsigned xu = xs[row * pairs + cp];
+            const float4 g = gs[row];
+            const float nz = nzp ? ns[row] * nscale : 0.f;
+            const float x0 = bf16lo_f(xu), x1 = bf16hi_f(xu);
+            const float g0 = fmaf(g.x, rw0.x, fmaf(g.y, rw0.y, g.z * rw0.z));
+            const float g1 = fmaf(g.x, rw1.x, fmaf(g.y, rw1.y, g.z * rw1.z));
+            r[2] = fmaf(x0, g.x, r[2]); r[3] = fmaf(x1, g.x, r[3]);
+            r[4] = fmaf(x0, g.y, r[4]); r[5] = fmaf(x1, g.y, r[5]);
+            r[6] = fmaf(x0, g.z, r[6]); r[7] = fmaf(x1, g.z, r[7]);
+            const bool q0 = x0 > 0.f, q1 = x1 > 0.f;
+            float gz0 = g0 * (q0 ? 1.f : P.act_slope), gz1 = g1 * (q1 ? 1.f : P.act_slope);
+            gz0 = fabsf(x0) < clampv ? gz0 : 0.f;
+            gz1 = fabsf(x1) < clampv ? gz1 : 0.f;
+            const float z0 = x0 * (q0 ? inv_gain : inv_gain_slope), z1 = x1 * (q1 ? inv_gain : inv_gain_slope);
+            r[0] = fmaf(gz0, z0 - nz - bs.x, r[0]);
+            r[1] = fmaf(gz1, z1 - nz - bs.y, r[1]);
+            xs[row * pairs + cp] = pack_bf16(gz0 * dm.x, gz1 * dm.y);      // g_y in place
+        }
+        fence_proxy_async();          // generic-proxy writes -> visible to the bulk store
+        __syncthreads();
+        if (tid == 0) {
+            bulk_store(gg + static_cast<long long>(p_begin + it * kSeedRows) * N, st, xbytes);
+            bulk_commit();
+            if (it >= 1 && it - 1 + kSeedStages < nchunks) {
+                bulk_wait_read<1>();  // the store of the previous stage has read its buffer
+                issue(it - 1 + kSeedStages);
+            }
+        }
+    }
+    if (tid == 0) bulk_wait_read<0>();
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[k * 128 + tid] = r[k];
+    __syncthreads();
+    for (int e = tid; e < 8 * pairs; e += 128) {
+        const int k = e / pairs, c = e - k * pairs;
+        float v = 0.f;
+        for (int j = 0; j < rlanes; ++j) v += red[k * 128 + j * pairs + c];
+        const int kind = k >> 1;                   // 0: red_d, 1..3: red_rgb
+        float* dst = kind == 0 ? P.red_d : P.red_rgb + static_cast<long long>(kind - 1) * P.batch * N;
+        atomicAdd(dst + static_cast<long long>(n) * N + 2 * c + (k & 1), v);
+    }
+}
+
 template <int BN, int EPI>
 int launch_bn_epi(const TapGemmParams& p, int num_sms, cudaStream_t stream) {
     static bool attr_set = false;
@@ -832,7 +999,13 @@ int launch_bn_epi(const TapGemmParams& p, int num_sms, cudaStream_t stream) {
         if (p.prob[i].ntaps <= 0 || p.prob[i].ngroups <= 0) return static_cast<int>(cudaErrorInvalidValue);   // accumulator would be undefined
     if (p.halo != 0 && (p.halo != 2 || p.tw != 8 || p.nb != 1 || p.th != 16)) return static_cast<int>(cudaErrorInvalidValue);
     if (p.nb * (p.th + p.halo) * p.tw * 128 > kASubBytes) return static_cast<int>(cudaErrorInvalidValue);
-    tapgemm_kernel<BN, EPI><<<grid, kThreads, Cfg<BN, EPI>::kSmemBytes, stream>>>(p);
+    if (total <= num_sms && !p.no_pair) {       // one tile per CTA: nothing to pair, so run the deeper unpaired A ring
+        TapGemmParams q = p;
+        q.no_pair = 1;
+        tapgemm_kernel<BN, EPI><<<grid, kThreads, Cfg<BN, EPI>::kSmemBytes, stream>>>(q);
+    } else {
+        tapgemm_kernel<BN, EPI><<<grid, kThreads, Cfg<BN, EPI>::kSmemBytes, stream>>>(p);
+    }
     return static_cast<int>(cudaGetLastError());
 }
 
@@ -914,6 +1087,20 @@ int tapgemm_finalize(TapGemmParams& p) {
 int launch_tapgemm_seed(const TapGemmParams& p, int /*num_sms*/, cudaStream_t stream) {
     if (p.epilogue != kEpiBwd || !p.g_rgb || !p.rgbw_prev || p.n_total % 64) return static_cast<int>(cudaErrorInvalidValue);
     const int pairs = p.n_total / 2;
+    const int img_px = p.OH * p.OW;
+    if (!p.split && (pairs == 32 || pairs == 64 || pairs == 128) && img_px % kSeedRows == 0 && !getenv("LA_SEED_STREAM")) {
+        const int smem = kSeedStages * (kSeedRows * p.n_total * 2 + kSeedRows * 20) + 64;
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(seed_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+            if (e != cudaSuccess) return static_cast<int>(e);
+            attr_set = true;
+        }
+        const int ppb = img_px < 2048 ? img_px : 2048;
+        dim3 grid((img_px + ppb - 1) / ppb, p.batch);
+        seed_bulk_kernel<<<grid, 128, smem, stream>>>(p, ppb);
+        return static_cast<int>(cudaGetLastError());
+    }
     const int cpairs = pairs >= 64 ? 64 : 32;
     dim3 grid((p.OH * p.OW + kSeedPixels - 1) / kSeedPixels, pairs / cpairs, p.batch);
     seed_stream_kernel<<<grid, 256, 0, stream>>>(p, cpairs);
@@ -941,7 +1128,7 @@ int launch_tapgemm_simt(const TapGemmParams& p, const TapSimtOperands& ops, cuda
 }
 
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                     const uint32_t* box) {
+                     const uint32_t* box, int swizzle_bytes) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -959,7 +1146,8 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
     for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides[i];
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstr,
-                    bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle_bytes == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return static_cast<int>(r);
 }

@@ -60,6 +60,10 @@ enum TapEpilogue : int {
 struct TapGemmParams {
     alignas(64) CUtensorMap a_map[kMaxAMaps];
     alignas(64) CUtensorMap b_map;
+    // Output tensor maps of the row-owner epilogues (bf16 mode): box = [32 channels, the 32 rows of one warp],
+    // SWIZZLE_64B.  kEpiFwd: o_map[0] = x, o_map[1] = x * s_next.  kEpiStoreBf16: o_map[problem].
+    alignas(64) CUtensorMap o_map[4];
+    int tma_store;                   // 1: stage through shared memory + tensor stores (o_map valid)
     Tap taps[kMaxTaps];              // flat tap list (host bookkeeping + the SIMT twin)
     TapGroup groups[kMaxTaps];       // the same taps grouped for the tensor-core kernel (tapgemm_finalize)
     uint8_t gdyrel[kMaxTaps];        // per grouped tap: dy - dy0 of its group (0..halo)
@@ -146,6 +150,6 @@ int launch_tapgemm_simt(const TapGemmParams& p, const TapSimtOperands& ops, cuda
 // Host helper: encode a bf16 tiled tensor map with 128B swizzle.  dims/box are innermost
 // first; strides (bytes) has rank-1 entries.  Returns 0 on success.
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                     const uint32_t* box);
+                     const uint32_t* box, int swizzle_bytes = 128);
 
 }  // namespace la
