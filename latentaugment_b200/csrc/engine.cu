@@ -97,7 +97,7 @@ struct la_engine {
     float *w_sum, *lat_m2;
     int crop_off, crop_size;
     // loop state
-    AdamConsts* consts; int* step; int* err_flag;
+    AdamConsts* consts; int* step; int* err_flag; unsigned long long* dbg_clock;
     float *w_opt, *m, *v, *w0, *w_aug, *loss_log, *map_a, *map_b;
     TapGemmParams seed; TapSimtOperands seed_ops;
     // execution
@@ -192,6 +192,16 @@ void set_grid(TapGemmParams& P, int g, int batch, int nprob, const int* gh = nul
         pr.tile_begin = P.m_tiles;
         P.m_tiles += P.tiles_n * pr.tiles_h * pr.tiles_w;
     }
+}
+
+// Interleaved walk of a multi-problem launch: one common tile grid (the largest), problems masked by vh / vw.
+void set_interleaved(TapGemmParams& P) {
+    int th = 0, tw = 0;
+    for (int i = 0; i < P.nprob; ++i) { th = P.prob[i].tiles_h > th ? P.prob[i].tiles_h : th; tw = P.prob[i].tiles_w > tw ? P.prob[i].tiles_w : tw; }
+    for (int i = 0; i < P.nprob; ++i) { P.prob[i].tiles_h = th; P.prob[i].tiles_w = tw; P.prob[i].tile_begin = 0; }
+    const int spatial = P.tiles_n * th * tw;
+    P.m_tiles = 2 * P.nprob * ((spatial + 1) / 2);
+    P.interleave = 1;
 }
 
 // Plans layers and carves the workspace.  With ws == nullptr only sizes are computed.
@@ -304,6 +314,7 @@ int plan(la_engine* e, char* ws, size_t* bytes_out) {
     e->consts = bp.take<AdamConsts>(1);
     e->step = bp.take<int>(1);
     e->err_flag = bp.take<int>(1);
+    e->dbg_clock = bp.take<unsigned long long>(2);
     const size_t wn = static_cast<size_t>(B) * g.w_dim;
     e->w_opt = bp.take<float>(wn); e->m = bp.take<float>(wn); e->v = bp.take<float>(wn);
     e->w0 = bp.take<float>(wn); e->w_aug = bp.take<float>(wn);
@@ -332,6 +343,7 @@ int build_params(la_engine* e) {
             const int gh[4] = {c.res_in + 1, c.res_in + 1, c.res_in, c.res_in};
             const int gw[4] = {c.res_in + 1, c.res_in, c.res_in + 1, c.res_in};
             set_grid(F, c.res_in, B, 4, gh, gw);
+            if (getenv("LA_INTERLEAVE")) set_interleaved(F);      // tuning switch: the cost-balanced contiguous split measured better
         } else {
             set_grid(F, c.res_in, B, c.up == 2 ? 4 : 1);
         }
@@ -427,7 +439,7 @@ int build_params(la_engine* e) {
                                   2LL * c.cout, 2LL * TWp * c.cout, static_cast<long long>(TH) * TWp * c.cout, F.tw, F.th));
                 }
                 F.tma_store = 1;
-            } else if (c.up == 1) {
+            } else if (c.up == 1 && F.nb == 1) {
                 const long long oW = c.cout, oH = static_cast<long long>(c.res) * c.cout, oN = oH * c.res;
                 LA(make_o_map(&F.o_map[0], c.x_hi, c.cout, c.res, c.res, B, oW, oH, oN, F.tw, F.th));
                 if (next) LA(make_o_map(&F.o_map[1], e->xs_hi[(l + 1) & 1], c.cout, c.res, c.res, B, oW, oH, oN, F.tw, F.th));
@@ -494,6 +506,7 @@ int build_params(la_engine* e) {
         G.prob[0].ntaps = nt;
         if (tapgemm_finalize(F) || tapgemm_finalize(G)) return fail(-2, "tap grouping failed");
         F.no_pair = G.no_pair = getenv("LA_NO_PAIR") != nullptr;
+        F.dbg_skip_epi = G.dbg_skip_epi = getenv("LA_DBG_SKIP_EPI") ? atoi(getenv("LA_DBG_SKIP_EPI")) : 0;
         const int bnb = pick_bn(c.cin, G.m_tiles);
         LA(make_b_map(&G.b_map, c.wb, c.cout, c.cin, nmat * (split ? 2 : 1), bnb));
         G.kchunks = c.cout / 64; G.n_total = c.cin; G.n_blocks = c.cin / bnb;
@@ -899,7 +912,10 @@ LA_API int la_debug_time_gemms(la_engine* e, int reps, float* h_ms, int* n_layer
     CU(cudaEventCreate(&a));
     CU(cudaEventCreate(&b));
     cudaStream_t w = e->work;
-    auto timed = [&](int idx, const TapGemmParams& P, const TapSimtOperands& ops, bool simt) -> int {
+    const bool dbg_clk = getenv("LA_DBG_CLK") != nullptr;
+    auto timed = [&](int idx, const TapGemmParams& P0, const TapSimtOperands& ops, bool simt) -> int {
+        TapGemmParams P = P0;
+        if (dbg_clk && !simt) P.dbg_clock = e->dbg_clock;
         for (int warm = 0; warm < 2; ++warm) { int r = simt ? launch_tapgemm_seed(P, e->num_sms, w) : launch_tapgemm(P, e->num_sms, w); if (r) return r; }
         cudaEventRecord(a, w);
         for (int i = 0; i < reps; ++i) { int r = simt ? launch_tapgemm_seed(P, e->num_sms, w) : launch_tapgemm(P, e->num_sms, w); if (r) return r; }
@@ -909,6 +925,11 @@ LA_API int la_debug_time_gemms(la_engine* e, int reps, float* h_ms, int* n_layer
         float ms = 0.f;
         cudaEventElapsedTime(&ms, a, b);
         h_ms[idx] = ms / reps;
+        if (dbg_clk && !simt) {
+            unsigned long long hc[2] = {0, 1};
+            cudaMemcpy(hc, e->dbg_clock, sizeof hc, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[clk] gemm %2d: %.3f ms, CTA0 %.0f MHz over %.3f ms\n", idx, h_ms[idx], 1e3 * hc[0] / hc[1], hc[1] * 1e-6);
+        }
         return 0;
     };
     auto timed_fir = [&](int idx, const UpFirParams& U, bool fwd) -> int {

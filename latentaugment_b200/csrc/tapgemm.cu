@@ -23,11 +23,11 @@ constexpr int kTransStride = 36;                  // floats per row of a warp's 
 constexpr int kRegsProducer = 56, kRegsEpilogue = 224;   // setmaxnreg: 128*56 + 256*224 = 64512 <= 65536
 
 // Per-warp scratch of the backward epilogue.
-struct WarpSmem {
+struct WarpSmem {                     // (row data is double-buffered: the next tile's rows are staged while this one computes)
     float trans[32 * kTransStride];   // accumulator chunk, row-owner write -> column-owner read
-    float4 grgb[32];                  // per row: gradient wrt the toRGB output
-    float nz[32];                     // per row: noise * strength of the producer layer
-    unsigned off[32];                 // per row: pixel index * N/2 (offset of the row in bf16x2 units), kRowMasked = masked
+    float4 grgb[2][32];               // per row: gradient wrt the toRGB output
+    float nz[2][32];                  // per row: noise * strength of the producer layer
+    unsigned off[2][32];              // per row: pixel index * N/2 (offset of the row in bf16x2 units), kRowMasked = masked
 };
 
 template <int BN, int EPI>
@@ -36,11 +36,14 @@ struct Cfg {
     static constexpr int kASlotBytes = kMtMax * kASubBytes;
     static constexpr int kBBytes = BN * kBlockK * 2;
     static constexpr int kAStages = (BN == 256 && EPI == kEpiBwd) ? 4 : 3;
-    static constexpr int kBStages = EPI == kEpiBwd ? (BN == 256 ? 3 : (BN == 128 ? 4 : 6)) : (BN == 256 ? 4 : (BN == 128 ? 5 : 8));
+    static constexpr int kBStages = EPI == kEpiBwd ? (BN == 256 ? 3 : (BN == 128 ? 4 : 6)) : (BN == 256 ? 4 : (BN == 128 ? (EPI == kEpiFwd ? 5 : 6) : 8));
     static constexpr int kTmemCols = 2 * kMtMax * BN;            // two accumulator stages
-    // per-warp staging of the tensor stores: 32 rows x 32 channels bf16 = 2 KB per output tensor
-    static constexpr int kStageTensors = EPI == kEpiFwd ? 2 : (EPI == kEpiStoreBf16 ? 1 : 0);
-    static constexpr int kEpiSmemBytes = EPI == kEpiBwd ? 8 * static_cast<int>(sizeof(WarpSmem)) : 8 * 2048 * kStageTensors;
+    // row-owner epilogues: a 2 KB staging tile per warp (32 rows x 32 channels bf16) for coalesced stores and,
+    // for the forward epilogue, one table of per-column coefficients per warp group:
+    // [demod | s_next | rgbw.x | rgbw.y | rgbw.z | bias] x BN floats of the (sample, column block) being processed
+    static constexpr int kStageTensors = (EPI == kEpiFwd || EPI == kEpiStoreBf16) ? 1 : 0;
+    static constexpr int kCoefBytes = EPI == kEpiFwd ? 2 * 6 * BN * 4 : 0;
+    static constexpr int kEpiSmemBytes = EPI == kEpiBwd ? 8 * static_cast<int>(sizeof(WarpSmem)) : 8 * 2048 * kStageTensors + kCoefBytes;
     static constexpr int kABytes = kAStages * kASlotBytes;       // unpaired launches cut this region into kASubBytes slots
     static constexpr int kSmemBytes = kABytes + kBStages * kBBytes + kEpiSmemBytes + 320 /*barriers*/ + 1024 /*align slack*/;
     static constexpr int kBwdSteps = BN == 64 ? 2 : 4;           // 32-column steps one warp walks per tile (all of BN, or half of it)
@@ -48,32 +51,42 @@ struct Cfg {
 
 struct TileCoord {
     int prob, nblk, n0, h0, w0;
+    bool empty;          // interleaved walk only: the tile lies outside its problem's valid extent
 };
 
 __device__ __forceinline__ TileCoord decode_tile(const TapGemmParams& P, int t) {
     TileCoord c;
     c.nblk = t / P.m_tiles;                  // M fastest: a CTA's contiguous chunk shares the weight tile
     int m = t - c.nblk * P.m_tiles;
-    int p = 0;
+    int local;
+    if (P.interleave) {
+        const int per = 2 * P.nprob;
+        const int grp = m / per, r = m - grp * per;
+        c.prob = r >> 1;
+        local = grp * 2 + (r & 1);
+    } else {
+        int p = 0;
 #pragma unroll
-    for (int i = 1; i < kMaxProblems; ++i)
-        if (i < P.nprob && m >= P.prob[i].tile_begin) p = i;
-    c.prob = p;
-    const TapProblem& pr = P.prob[p];
-    int local = m - pr.tile_begin;
+        for (int i = 1; i < kMaxProblems; ++i)
+            if (i < P.nprob && m >= P.prob[i].tile_begin) p = i;
+        c.prob = p;
+        local = m - P.prob[p].tile_begin;
+    }
+    const TapProblem& pr = P.prob[c.prob];
     int tx = local % pr.tiles_w;
     int ty = (local / pr.tiles_w) % pr.tiles_h;
     int tn = local / (pr.tiles_w * pr.tiles_h);
     c.n0 = tn * P.nb;
     c.h0 = ty * P.th;
     c.w0 = tx * P.tw;
+    c.empty = P.interleave && (tn >= P.tiles_n || c.h0 >= pr.vh || c.w0 >= pr.vw);
     return c;
 }
 
-// A unit = one or two consecutive M tiles of the same (column block, problem).
+// A unit = one or two consecutive M tiles of the same (column block, problem); mt == 0: nothing to do.
 struct Unit {
     TileCoord tc0, tc1;      // (no array: a dynamic index would put the struct in local memory)
-    int mt;
+    int mt, adv;
     __device__ __forceinline__ const TileCoord& tile(int s) const { return s ? tc1 : tc0; }
 };
 template <int MTMAX>
@@ -82,22 +95,38 @@ __device__ __forceinline__ Unit get_unit(const TapGemmParams& P, int t, int t_en
     u.tc0 = decode_tile(P, t);
     u.tc1 = u.tc0;
     u.mt = 1;
+    if (P.interleave) {      // ranges are aligned to whole groups: t is the first tile of a (pair, problem)
+        u.adv = 2;
+        const TileCoord c = decode_tile(P, t + 1);
+        if (u.tc0.empty) { u.tc0 = c; u.tc1 = c; u.mt = c.empty ? 0 : 1; }
+        else if (!c.empty) {
+            if (MTMAX == 2 && !P.no_pair) { u.tc1 = c; u.mt = 2; }
+            else u.adv = 1;  // unpaired kernels take the two tiles one after the other
+        }
+        return u;
+    }
     if (MTMAX == 2 && t + 1 < t_end && !P.no_pair) {
         const TileCoord c = decode_tile(P, t + 1);
         if (c.nblk == u.tc0.nblk && c.prob == u.tc0.prob) { u.tc1 = c; u.mt = 2; }
     }
+    u.adv = u.mt;
     return u;
 }
 
-// Contiguous, COST-balanced tile range of this CTA: a tile costs max(ntaps, 1) of its problem (the
-// phases of the transposed convolution have 4 / 2 / 2 / 1 taps).  Tiles are ordered [nblk][problem][tile].
+// Contiguous, COST-balanced tile range of this CTA.  The phases of the transposed convolution have 4 / 2 / 2 / 1
+// taps; a tile costs (taps x K chunks) MMA steps plus a fixed epilogue share worth about four steps (measured:
+// with taps alone the CTAs that own the one-tap phase finish 35 % after the others).  Tiles are ordered
+// [nblk][problem][tile].
+__device__ __forceinline__ long long tile_cost(const TapGemmParams& P, const TapProblem& pr) {
+    return pr.ntaps > 0 ? static_cast<long long>(pr.ntaps) * P.kchunks + 4 : 1;
+}
 __device__ __forceinline__ long long tiles_before(const TapGemmParams& P, long long cost_per_nblk, long long x) {
     long long nb_full = x / cost_per_nblk;
     if (nb_full >= P.n_blocks) return static_cast<long long>(P.n_blocks) * P.m_tiles;
     long long rem = x - nb_full * cost_per_nblk, count = nb_full * P.m_tiles;
     for (int p = 0; p < P.nprob; ++p) {
         const TapProblem& pr = P.prob[p];
-        const long long c = pr.ntaps > 0 ? pr.ntaps : 1;
+        const long long c = tile_cost(P, pr);
         const long long tiles = static_cast<long long>(pr.tiles_h) * pr.tiles_w * P.tiles_n;
         if (rem >= tiles * c) { count += tiles; rem -= tiles * c; }
         else { count += (rem + c - 1) / c; break; }
@@ -105,9 +134,16 @@ __device__ __forceinline__ long long tiles_before(const TapGemmParams& P, long l
     return count;
 }
 __device__ __forceinline__ void tile_range(const TapGemmParams& P, int& begin, int& end) {
+    if (P.interleave) {      // every group of 2 * nprob tiles costs the same: split the groups evenly
+        const int per = 2 * P.nprob;
+        const long long groups = static_cast<long long>(P.n_blocks) * (P.m_tiles / per);
+        begin = static_cast<int>(groups * blockIdx.x / gridDim.x) * per;
+        end = static_cast<int>(groups * (blockIdx.x + 1) / gridDim.x) * per;
+        return;
+    }
     long long cost = 0;
     for (int p = 0; p < P.nprob; ++p)
-        cost += static_cast<long long>(P.prob[p].tiles_h) * P.prob[p].tiles_w * P.tiles_n * (P.prob[p].ntaps > 0 ? P.prob[p].ntaps : 1);
+        cost += static_cast<long long>(P.prob[p].tiles_h) * P.prob[p].tiles_w * P.tiles_n * tile_cost(P, P.prob[p]);
     const long long total = cost * P.n_blocks;
     begin = static_cast<int>(tiles_before(P, cost, total * blockIdx.x / gridDim.x));
     end = static_cast<int>(tiles_before(P, cost, total * (blockIdx.x + 1) / gridDim.x));
@@ -116,6 +152,9 @@ __device__ __forceinline__ void tile_range(const TapGemmParams& P, int& begin, i
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void st_global_if(unsigned* p, unsigned v, bool ok) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.b32 [%0], %1;\n\t}" ::"l"(p), "r"(v), "r"(static_cast<int>(ok)));
 }
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 __device__ __forceinline__ float bf16lo_f(uint32_t u) { return __uint_as_float(u << 16); }
@@ -211,7 +250,7 @@ __device__ __forceinline__ void stage_bf16x32(uint8_t* stg, int lane, const floa
 // instead of 16-byte pieces per thread); `stg` = kStageTensors x 2 KB.
 template <int BN, int EPI, bool kTma, class LoadChunk>
 __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const TileCoord& tc, int q, int lane, int ch_begin, int ch_end,
-                                                   int part, bool fill_other, uint8_t* stg, LoadChunk&& load_chunk) {
+                                                   int part, bool fill_other, uint8_t* stg, const float* ctab, LoadChunk&& load_chunk) {
     const RowCtx rc = make_row(P, tc, q * 32 + lane);
     float nz = 0.f;
     if (EPI == kEpiFwd && rc.valid && P.noise) nz = __ldg(P.noise + rc.n * P.noise_stride_n + rc.px_in_img) * P.noise_scale;
@@ -221,18 +260,51 @@ __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const
 #pragma unroll
     for (int k = 0; k < 8; ++k) { best_s[k] = __int_as_float(0x7f800000); best_i[k] = -1; }
     const bool tk_valid = rc.valid && rc.pix < P.n_queries;
-    // tensor-store coordinates of the warp's 32 rows (a box of 32 / tw image rows, or whole small images)
-    int sc1 = 0, sc2 = 0, sc3 = 0;
+    const float clampv = P.act_clamp >= 0.f ? P.act_clamp : __int_as_float(0x7f800000);
+    // staged stores: the lane re-reads 16-byte piece (lane & 3) of rows 8j + (lane >> 2), j = 0..3, so that
+    // every store instruction writes whole 64-byte row segments (row-owner stores write 32 scattered pieces)
+    long long srow[4];
+    bool sok[4];
     if (kTma) {
-        const int box_px = P.th * P.tw, r0 = q * 32;
-        const int ni = r0 / box_px, rem = r0 - ni * box_px;
-        sc1 = tc.w0; sc2 = tc.h0 + rem / P.tw; sc3 = tc.n0 + ni;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const RowCtx r = make_row(P, tc, q * 32 + 8 * j + (lane >> 2));
+            srow[j] = r.pix * P.n_total + (lane & 3) * 8;
+            sok[j] = r.valid;
+        }
     }
+    auto flush_stage = [&](const uint8_t* tile, void* dst_base, int col0) {
+        __syncwarp();
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(dst_base) + col0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int rr = 8 * j + (lane >> 2);
+            const uint4 v = *reinterpret_cast<const uint4*>(tile + rr * 64 + ((((lane & 3) ^ (rr >> 1)) & 3) << 4));
+            if (sok[j]) {
+                if (P.dbg_skip_epi == 200) *reinterpret_cast<uint4*>(dst + srow[j]) = v;
+                else __stcs(reinterpret_cast<uint4*>(dst + srow[j]), v);      // streaming: the outputs must not displace the operands in L2
+            }
+        }
+        __syncwarp();
+    };
 
 #pragma unroll 1
     for (int ch = ch_begin; ch < ch_end; ++ch) {
         float acc[32];
         load_chunk(ch, acc);
+        if (P.dbg_skip_epi == 1) continue;
+        if (P.dbg_skip_epi >= 2 && P.dbg_skip_epi < 100) {            // timing experiment: ALU work only (about as many FMAs as the real epilogue)
+            float t = 0.f;
+#pragma unroll 1
+            for (int rep = 0; rep < P.dbg_skip_epi; ++rep) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = fmaf(acc[j], 1.0001f, 0.5f);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) t += acc[j];
+            if (t == 123.456f) P.raw_out[0] = t;
+            continue;
+        }
         const int col0 = tc.nblk * BN + ch * 32;
         const long long eoff = rc.pix * P.n_total + col0;             // element offset in [pixel][N] tensors
         const long long coff = static_cast<long long>(rc.n) * P.n_total + col0;   // offset in [batch][N] tensors
@@ -244,12 +316,8 @@ __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const
             }
         } else if constexpr (EPI == kEpiStoreBf16) {
             if (kTma) {
-                if (lane == 0) bulk_wait_read<0>();       // the previous store has read the staging tile
-                __syncwarp();
                 stage_bf16x32(stg, lane, acc);
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) { tma_store_4d(&P.o_map[tc.prob], stg, col0, sc1, sc2, sc3); bulk_commit(); }
+                flush_stage(stg, P.x_hi, col0);
             } else if (rc.valid) {
                 store_bf16x32(P.x_hi, P.split ? P.x_lo : nullptr, eoff, acc);
             }
@@ -275,19 +343,64 @@ __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const
                 }
             }
         } else if constexpr (EPI == kEpiFwd) {
-            float xs[32];
-            if (rc.valid) {
+            if (kTma) {
+                // staged path (one sample per tile): coefficients come from the warp group's shared-memory table
+                const float4* t_dm = reinterpret_cast<const float4*>(ctab + ch * 32);
+                const float4* t_bs = reinterpret_cast<const float4*>(ctab + 5 * BN + ch * 32);
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 d4 = (P.dbg_skip_epi >= 100 && ((P.dbg_skip_epi - 100) & 2)) ? make_float4(1.f, 1.f, 1.f, 1.f) : t_dm[j4];
+                    const float4 b4 = (P.dbg_skip_epi >= 100 && ((P.dbg_skip_epi - 100) & 2)) ? make_float4(1.f, 1.f, 1.f, 1.f) : t_bs[j4];
+                    const float dd[4] = {d4.x, d4.y, d4.z, d4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float z = fmaf(acc[4 * j4 + k], dd[k], nz) + bb[k];
+                        z = fmaxf(z, z * P.act_slope) * P.act_gain;          // lrelu (slope < 1)
+                        acc[4 * j4 + k] = fminf(fmaxf(z, -clampv), clampv);
+                    }
+                }
+                const int dbg = P.dbg_skip_epi >= 100 ? P.dbg_skip_epi - 100 : 0;   // timing experiments (wrong results)
+                if (!(dbg & 1)) {
+                    stage_bf16x32(stg, lane, acc);
+                    flush_stage(stg, P.x_hi, col0);
+                }
+                if (P.rgbw && !(dbg & 4)) {
+                    const float4* t0 = reinterpret_cast<const float4*>(ctab + 2 * BN + ch * 32);
+                    const float4* t1 = reinterpret_cast<const float4*>(ctab + 3 * BN + ch * 32);
+                    const float4* t2 = reinterpret_cast<const float4*>(ctab + 4 * BN + ch * 32);
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 a4 = t0[j4], b4 = t1[j4], c4 = t2[j4];
+                        rgb0 = fmaf(acc[4 * j4], a4.x, fmaf(acc[4 * j4 + 1], a4.y, fmaf(acc[4 * j4 + 2], a4.z, fmaf(acc[4 * j4 + 3], a4.w, rgb0))));
+                        rgb1 = fmaf(acc[4 * j4], b4.x, fmaf(acc[4 * j4 + 1], b4.y, fmaf(acc[4 * j4 + 2], b4.z, fmaf(acc[4 * j4 + 3], b4.w, rgb1))));
+                        rgb2 = fmaf(acc[4 * j4], c4.x, fmaf(acc[4 * j4 + 1], c4.y, fmaf(acc[4 * j4 + 2], c4.z, fmaf(acc[4 * j4 + 3], c4.w, rgb2))));
+                    }
+                }
+                if (P.s_next) {
+                    const float4* t_sn = reinterpret_cast<const float4*>(ctab + BN + ch * 32);
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 s4 = t_sn[j4];
+                        acc[4 * j4] *= s4.x; acc[4 * j4 + 1] *= s4.y; acc[4 * j4 + 2] *= s4.z; acc[4 * j4 + 3] *= s4.w;
+                    }
+                    if (!(dbg & 1)) {
+                        stage_bf16x32(stg, lane, acc);
+                        flush_stage(stg, P.xs_hi, col0);
+                    } else if (acc[3] == 123.456f) {
+                        P.raw_out[0] = acc[5];
+                    }
+                }
+            } else if (rc.valid) {
                 float dm[32], bs[32];
                 load_f32x32(P.demod + coff, dm);
                 load_f32x32(P.bias + col0, bs);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     float z = fmaf(acc[j], dm[j], nz) + bs[j];
-                    z = (z > 0.f ? z : z * P.act_slope) * P.act_gain;
-                    if (P.act_clamp >= 0.f) z = fminf(fmaxf(z, -P.act_clamp), P.act_clamp);
-                    acc[j] = z;
+                    z = fmaxf(z, z * P.act_slope) * P.act_gain;
+                    acc[j] = fminf(fmaxf(z, -clampv), clampv);
                 }
-                if (!kTma) store_bf16x32(P.x_hi, P.split ? P.x_lo : nullptr, eoff, acc);
+                store_bf16x32(P.x_hi, P.split ? P.x_lo : nullptr, eoff, acc);
                 if (P.rgbw) {
                     const float4* rw = P.rgbw + coff;
 #pragma unroll
@@ -301,21 +414,8 @@ __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const
                 if (P.s_next) {
                     load_f32x32(P.s_next + coff, dm);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) xs[j] = acc[j] * dm[j];
-                    if (!kTma) store_bf16x32(P.xs_hi, P.split ? P.xs_lo : nullptr, eoff, xs);
-                }
-            }
-            if (kTma) {
-                if (lane == 0) bulk_wait_read<0>();
-                __syncwarp();
-                stage_bf16x32(stg, lane, acc);                 // masked rows stage garbage; the tensor store clips them
-                if (P.s_next) stage_bf16x32(stg + 2048, lane, xs);
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) {
-                    tma_store_4d(&P.o_map[0], stg, col0, sc1, sc2, sc3);
-                    if (P.s_next) tma_store_4d(&P.o_map[1], stg + 2048, col0, sc1, sc2, sc3);
-                    bulk_commit();
+                    for (int j = 0; j < 32; ++j) acc[j] *= dm[j];
+                    store_bf16x32(P.xs_hi, P.split ? P.xs_lo : nullptr, eoff, acc);
                 }
             }
         }
@@ -385,17 +485,58 @@ __device__ __forceinline__ void bwd_flush(const TapGemmParams& P, BwdState<NSTEP
     st.key = -1;
 }
 
-template <int BN, int NSTEP, bool kHaveAcc, class LoadChunk, class Release>
-__device__ __forceinline__ void bwd_warp_tile(const TapGemmParams& P, const TileCoord& tc, int q, int lane, int step0, int nsteps,
-                                              WarpSmem* ws, BwdState<NSTEP>& st, LoadChunk&& load_chunk, Release&& release_acc) {
+// One warp's share of one M tile in the backward epilogue.
+struct BwdTile {
+    TileCoord tc;
+    int step0, nsteps;      // 32-column steps [step0, step0 + nsteps) of the column block
+    int sub_tile;           // which M tile of its unit
+};
+struct BwdRowRegs {          // lane = row: what phase 0 loads for it
+    unsigned off;
+    float nz;
+    float4 g;
+};
+__device__ __forceinline__ BwdRowRegs bwd_row_load(const TapGemmParams& P, const BwdTile& t, int q, int lane) {
+    const RowCtx rc = make_row(P, t.tc, q * 32 + lane);
+    BwdRowRegs r;
+    r.off = rc.valid ? static_cast<unsigned>(rc.pix) * static_cast<unsigned>(P.n_total >> 1) : kRowMasked;
+    r.nz = (rc.valid && P.noise_prev && !P.bwd_last)
+               ? __ldg(P.noise_prev + rc.n * P.noise_prev_stride_n + rc.px_in_img) * P.noise_prev_scale : 0.f;
+    r.g = (rc.valid && P.g_rgb) ? __ldg(P.g_rgb + rc.pix) : make_float4(0.f, 0.f, 0.f, 0.f);
+    return r;
+}
+__device__ __forceinline__ void bwd_row_store(WarpSmem* ws, int buf, int lane, const BwdRowRegs& r) {
+    ws->off[buf][lane] = r.off;
+    ws->nz[buf][lane] = r.nz;
+    ws->grgb[buf][lane] = r.g;
+}
+// x_{l-1} of one 32-column step: 16 rows of this half-warp, one bf16 pair per lane
+template <int BN>
+__device__ __forceinline__ void bwd_prefetch_x(const TapGemmParams& P, const WarpSmem* ws, int buf, const BwdTile& t, int slot, int lane,
+                                               unsigned (&xu)[16]) {
+    const unsigned* xph = reinterpret_cast<const unsigned*>(P.xp_hi) + ((t.tc.nblk * BN + (t.step0 + slot) * 32) >> 1) + (lane & 15);
+    const unsigned* soff = ws->off[buf] + (lane >> 4) * 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const unsigned o = soff[i];
+        xu[i] = __ldg(xph + (o == kRowMasked ? 0u : o));
+        if (o == kRowMasked) xu[i] = 0u;
+    }
+}
+
+// `xa` holds x_{l-1} of the tile's first step on entry (prefetched while the previous tile was computed) and
+// that of `next`'s first step on exit; the row data of `next` goes to ws buffer buf ^ 1.
+template <int BN, int NSTEP, bool kSplit, class LoadChunk, class Release>
+__device__ __forceinline__ void bwd_warp_tile(const TapGemmParams& P, const BwdTile& cur, const BwdTile* next, int q, int lane, WarpSmem* ws,
+                                              int buf, BwdState<NSTEP>& st, unsigned (&xa)[16], LoadChunk&& load_chunk, Release&& release_acc) {
+    const TileCoord& tc = cur.tc;
+    const int step0 = cur.step0, nsteps = cur.nsteps;
     const int half = lane >> 4, cp = lane & 15;
-    // ---- phase 0 (lane = row): pixel index, noise and toRGB gradient of the warp's 32 rows
-    const RowCtx rc = make_row(P, tc, q * 32 + lane);
-    __syncwarp();                    // previous tile's readers are done with ws
-    ws->off[lane] = rc.valid ? static_cast<unsigned>(rc.pix) * static_cast<unsigned>(P.n_total >> 1) : kRowMasked;
-    ws->nz[lane] = (rc.valid && P.noise_prev && !P.bwd_last)
-                       ? __ldg(P.noise_prev + rc.n * P.noise_prev_stride_n + rc.px_in_img) * P.noise_prev_scale : 0.f;
-    ws->grgb[lane] = (rc.valid && P.g_rgb) ? __ldg(P.g_rgb + rc.pix) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // loads of the NEXT tile's row data are issued now and parked in registers until the last step
+    BwdRowRegs nrow;
+    if (next) nrow = bwd_row_load(P, *next, q, lane);
+    const bool row_valid = ws->off[buf][lane] != kRowMasked;
+    const bool any_invalid = __any_sync(0xffffffffu, !row_valid);
     // sample of this half-warp's 16 rows (a half never straddles two samples: box_px is 16, 64 or 128)
     const int box_px = P.th * P.tw;
     const int ni_h = (q * 32 + half * 16) / box_px;
@@ -407,32 +548,18 @@ __device__ __forceinline__ void bwd_warp_tile(const TapGemmParams& P, const Tile
         st.key = new_key;
     }
     if (n_ok) st.nsteps = nsteps;
-    __syncwarp();
 
     const float inv_gain = 1.f / P.act_gain, inv_gain_slope = 1.f / (P.act_gain * P.act_slope);
     const float clampv = P.act_clamp >= 0.f ? P.act_clamp : __int_as_float(0x7f800000);
-    const unsigned* xph = reinterpret_cast<const unsigned*>(P.xp_hi);
-    const unsigned* xpl = P.split ? reinterpret_cast<const unsigned*>(P.xp_lo) : nullptr;
-    unsigned* gyh = reinterpret_cast<unsigned*>(P.gy_hi);
-    unsigned* gyl = P.split ? reinterpret_cast<unsigned*>(P.gy_lo) : nullptr;
-    const int colw0 = (tc.nblk * BN + step0 * 32 + 2 * cp) >> 1;      // column pair index of step slot 0
-    const bool any_invalid = __any_sync(0xffffffffu, !rc.valid);
-    const unsigned* soff = ws->off + half * 16;
-
-    unsigned xa[16], xb[16];
-    auto prefetch = [&](int slot, unsigned (&xu)[16]) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const unsigned o = soff[i];
-            xu[i] = __ldg(xph + (o == kRowMasked ? 0u : o) + (colw0 + slot * 16));
-            if (o == kRowMasked) xu[i] = 0u;
-        }
-    };
-    prefetch(0, xa);
+    const bool last = P.bwd_last != 0;        // x_{l-1} is the constant input: only red_s is wanted (coefficients stay 0, no store)
+    const unsigned* soff = ws->off[buf] + half * 16;
+    const float* snz = ws->nz[buf] + half * 16;
+    const float4* sgr = ws->grgb[buf] + half * 16;
+    const float* strans = ws->trans + half * 16 * kTransStride + 2 * cp;
+    const int colp0 = ((tc.nblk * BN + step0 * 32) >> 1) + cp;      // column pair of step slot 0
 
     // One 32-column step, branch-free over its 16 rows (masked rows carry a == x == g_rgb == 0 and only
     // their store is predicated off), so the compiler interleaves the rows.
-    const bool last = P.bwd_last != 0;        // x_{l-1} is the constant input: only red_s is wanted (coefficients stay 0, no store)
     auto step_body = [&](auto rgb_tag, int c, float (&r)[10]) {
         constexpr bool kRgb = decltype(rgb_tag)::value;
         const int col = tc.nblk * BN + (step0 + c) * 32 + 2 * cp;
@@ -450,62 +577,61 @@ __device__ __forceinline__ void bwd_warp_tile(const TapGemmParams& P, const Tile
                 rw1.x *= P.act_gain; rw1.y *= P.act_gain; rw1.z *= P.act_gain;
             }
         }
+        unsigned* gy_step = reinterpret_cast<unsigned*>(P.gy_hi) + (colp0 + c * 16);
+        unsigned* gyl_step = kSplit ? reinterpret_cast<unsigned*>(P.gy_lo) + (colp0 + c * 16) : nullptr;
         unsigned xl[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) xl[i] = 0u;
-        if (xpl) {
+        if (kSplit) {
+            const unsigned* xpl = reinterpret_cast<const unsigned*>(P.xp_lo) + (colp0 + c * 16);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const unsigned o = soff[i];
-                xl[i] = __ldg(xpl + (o == kRowMasked ? 0u : o) + (colw0 + c * 16));
+                xl[i] = __ldg(xpl + (o == kRowMasked ? 0u : o));
                 if (o == kRowMasked) xl[i] = 0u;
             }
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-            const int row = half * 16 + i;
             const unsigned o = soff[i];
-            float2 a = make_float2(0.f, 0.f);
-            if (kHaveAcc) a = *reinterpret_cast<const float2*>(ws->trans + row * kTransStride + 2 * cp);
-            const float x0 = bf16lo_f(xa[i]) + bf16lo_f(xl[i]), x1 = bf16hi_f(xa[i]) + bf16hi_f(xl[i]);
+            const float2 a = *reinterpret_cast<const float2*>(strans + i * kTransStride);
+            float x0 = bf16lo_f(xa[i]), x1 = bf16hi_f(xa[i]);
+            if (kSplit) { x0 += bf16lo_f(xl[i]); x1 += bf16hi_f(xl[i]); }
             r[0] = fmaf(a.x, x0, r[0]);
             r[1] = fmaf(a.y, x1, r[1]);
-            {
-                float g0 = a.x * sc.x, g1 = a.y * sc.y;
-                if (kRgb) {
-                    const float4 g = ws->grgb[row];
-                    g0 = fmaf(g.x, rw0.x, fmaf(g.y, rw0.y, fmaf(g.z, rw0.z, g0)));
-                    g1 = fmaf(g.x, rw1.x, fmaf(g.y, rw1.y, fmaf(g.z, rw1.z, g1)));
-                    r[4] = fmaf(x0, g.x, r[4]); r[5] = fmaf(x1, g.x, r[5]);
-                    r[6] = fmaf(x0, g.y, r[6]); r[7] = fmaf(x1, g.y, r[7]);
-                    r[8] = fmaf(x0, g.z, r[8]); r[9] = fmaf(x1, g.z, r[9]);
-                }
-                const float nz = ws->nz[row];
-                // activation backward of layer l-1 decided by its saved output; y recovered from it
-                const bool p0 = x0 > 0.f, p1 = x1 > 0.f;
-                float gz0 = g0 * (p0 ? 1.f : P.act_slope);
-                float gz1 = g1 * (p1 ? 1.f : P.act_slope);
-                gz0 = fabsf(x0) < clampv ? gz0 : 0.f;
-                gz1 = fabsf(x1) < clampv ? gz1 : 0.f;
-                const float z0 = x0 * (p0 ? inv_gain : inv_gain_slope), z1 = x1 * (p1 ? inv_gain : inv_gain_slope);
-                r[2] = fmaf(gz0, z0 - nz - bs.x, r[2]);
-                r[3] = fmaf(gz1, z1 - nz - bs.y, r[3]);
-                const float y0 = gz0 * dm.x, y1 = gz1 * dm.y;
-                if (o != kRowMasked && !last) {
-                    gyh[o + (colw0 + c * 16)] = pack_bf16(y0, y1);
-                    if (gyl) gyl[o + (colw0 + c * 16)] = pack_bf16(y0 - bf16_round(y0), y1 - bf16_round(y1));
-                }
+            float g0 = a.x * sc.x, g1 = a.y * sc.y;
+            if (kRgb) {
+                const float4 g = sgr[i];
+                g0 = fmaf(g.x, rw0.x, fmaf(g.y, rw0.y, fmaf(g.z, rw0.z, g0)));
+                g1 = fmaf(g.x, rw1.x, fmaf(g.y, rw1.y, fmaf(g.z, rw1.z, g1)));
+                r[4] = fmaf(x0, g.x, r[4]); r[5] = fmaf(x1, g.x, r[5]);
+                r[6] = fmaf(x0, g.y, r[6]); r[7] = fmaf(x1, g.y, r[7]);
+                r[8] = fmaf(x0, g.z, r[8]); r[9] = fmaf(x1, g.z, r[9]);
             }
+            const float nz = snz[i];
+            // activation backward of layer l-1 decided by its saved output; y recovered from it
+            const bool p0 = x0 > 0.f, p1 = x1 > 0.f;
+            float gz0 = g0 * (p0 ? 1.f : P.act_slope);
+            float gz1 = g1 * (p1 ? 1.f : P.act_slope);
+            gz0 = fabsf(x0) < clampv ? gz0 : 0.f;
+            gz1 = fabsf(x1) < clampv ? gz1 : 0.f;
+            const float z0 = x0 * (p0 ? inv_gain : inv_gain_slope), z1 = x1 * (p1 ? inv_gain : inv_gain_slope);
+            r[2] = fmaf(gz0, z0 - (nz + bs.x), r[2]);
+            r[3] = fmaf(gz1, z1 - (nz + bs.y), r[3]);
+            const float y0 = gz0 * dm.x, y1 = gz1 * dm.y;
+            const bool st_ok = o != kRowMasked && !last;
+            st_global_if(gy_step + o, pack_bf16(y0, y1), st_ok);
+            if (kSplit) st_global_if(gyl_step + o, pack_bf16(y0 - bf16_round(y0), y1 - bf16_round(y1)), st_ok);
         }
     };
 
+    unsigned xb[16];
 #pragma unroll 1
     for (int c = 0; c < nsteps; ++c) {       // (a runtime loop: unrolled, the epilogue outgrows the instruction cache)
-        if (kHaveAcc) {
+        {
             float acc[32];
             load_chunk(step0 + c, acc);
             if (c == nsteps - 1) release_acc();
-            if (any_invalid && !rc.valid) {
+            if (P.dbg_skip_epi) continue;
+            if (any_invalid && !row_valid) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) acc[j] = 0.f;
             }
@@ -513,12 +639,14 @@ __device__ __forceinline__ void bwd_warp_tile(const TapGemmParams& P, const Tile
 #pragma unroll
             for (int j = 0; j < 8; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
         }
+        if (c == nsteps - 1 && next) bwd_row_store(ws, buf ^ 1, lane, nrow);
         __syncwarp();
-        if (c + 1 < nsteps) prefetch(c + 1, xb);
+        if (c + 1 < nsteps) bwd_prefetch_x<BN>(P, ws, buf, cur, c + 1, lane, xb);
+        else if (next) bwd_prefetch_x<BN>(P, ws, buf ^ 1, *next, 0, lane, xb);
         float r[10];
 #pragma unroll
         for (int k = 0; k < 10; ++k) r[k] = 0.f;
-        if (P.g_rgb && !P.bwd_last) step_body(std::true_type{}, c, r);
+        if (P.g_rgb && !last) step_body(std::true_type{}, c, r);
         else step_body(std::false_type{}, c, r);
 #pragma unroll
         for (int cc = 0; cc < NSTEP; ++cc)
@@ -530,6 +658,35 @@ __device__ __forceinline__ void bwd_warp_tile(const TapGemmParams& P, const Tile
 #pragma unroll
         for (int i = 0; i < 16; ++i) xa[i] = xb[i];
     }
+}
+
+// Driver of the backward epilogue for one warp: walks the CTA's units with one-tile lookahead.
+// get_tile(t, out_tile, out_advance) -> false at the end of the range.
+template <int BN, int NSTEP, bool kSplit, class TileAt, class LoadChunkFor, class ReleaseFor>
+__device__ __forceinline__ void bwd_warp_loop(const TapGemmParams& P, int q, int lane, WarpSmem* ws, int t_begin, int t_end, TileAt&& tile_at,
+                                              LoadChunkFor&& chunk_loader, ReleaseFor&& releaser) {
+    BwdState<NSTEP> st;
+    bwd_state_init(st);
+    BwdTile cur, nxt;
+    int adv = 0;
+    int t = t_begin;
+    if (t >= t_end) return;
+    tile_at(t, cur, adv);
+    int buf = 0;
+    bwd_row_store(ws, buf, lane, bwd_row_load(P, cur, q, lane));
+    __syncwarp();
+    unsigned xa[16];
+    bwd_prefetch_x<BN>(P, ws, buf, cur, 0, lane, xa);
+    int it = 0;
+    while (t < t_end) {
+        const int tn = t + adv;
+        int adv_n = 0;
+        const bool has_next = tn < t_end;
+        if (has_next) tile_at(tn, nxt, adv_n);
+        bwd_warp_tile<BN, NSTEP, kSplit>(P, cur, has_next ? &nxt : nullptr, q, lane, ws, buf, st, xa, chunk_loader(it, cur), releaser(it));
+        cur = nxt; adv = adv_n; t = tn; buf ^= 1; ++it;
+    }
+    bwd_flush<BN, NSTEP>(P, st, lane);
 }
 
 // Work split of the 8 epilogue warps over a unit: with two M tiles, warps 0-3 take tile 0 and warps 4-7
@@ -575,6 +732,11 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     const int lane = threadIdx.x & 31;
     int t_begin, t_end;
     tile_range(P, t_begin, t_end);
+    unsigned long long dbg_c0 = 0, dbg_t0 = 0;
+    if (P.dbg_clock && blockIdx.x == 0 && threadIdx.x == 64) {
+        dbg_c0 = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+    }
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&P.a_map[0]);
@@ -606,7 +768,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
             uint32_t aph = 0, bph = 0;
             for (int t = t_begin; t < t_end;) {
                 const Unit u = get_unit<C::kMtMax>(P, t, t_end);
-                t += u.mt;
+                t += u.adv;
+                if (u.mt == 0) continue;
                 const TapProblem& pr = P.prob[u.tc0.prob];
                 for (int g = 0; g < pr.ngroups; ++g) {
                     const TapGroup grp = P.groups[pr.grp_begin + g];
@@ -638,7 +801,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
             uint32_t acc_phase = 0;
             for (int t = t_begin; t < t_end;) {
                 const Unit u = get_unit<C::kMtMax>(P, t, t_end);
-                t += u.mt;
+                t += u.adv;
+                if (u.mt == 0) continue;
                 const TapProblem& pr = P.prob[u.tc0.prob];
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1, P.err_flag, 2);
                 tc_fence_after();
@@ -678,54 +842,112 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
         setmaxnreg_inc<kRegsEpilogue>();
         const int e = warp - 4;
         const int q = e & 3, sub = e >> 2;          // TMEM lane quarter (= warp % 4), warp group
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        BwdState<C::kBwdSteps> st;
-        if (EPI == kEpiBwd) bwd_state_init(st);
-        WarpSmem* ws = reinterpret_cast<WarpSmem*>(epi_smem) + e;
-        for (int t = t_begin; t < t_end;) {
-            const Unit u = get_unit<C::kMtMax>(P, t, t_end);
-            t += u.mt;
-            const EpiSplit<BN> sp = epi_split<BN>(u.mt, sub);
-            const TileCoord tc = u.tile(sp.st);
-            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                                    static_cast<uint32_t>((acc * C::kMtMax + sp.st) * BN);
-            bool waited = false;
-            auto load_chunk = [&](int ch, float (&v)[32]) {
-                if (!waited) {       // the row-info phase of the backward epilogue runs before this wait
-                    mbar_wait(&tfull_bar[acc], acc_phase, P.err_flag, 4);
-                    tc_fence_after();
-                    waited = true;
-                }
-                uint32_t r[32];
-                tmem_ld32(t_addr + ch * 32, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if constexpr (EPI == kEpiBwd) {
+            WarpSmem* ws = reinterpret_cast<WarpSmem*>(epi_smem) + e;
+            auto tile_at = [&](int t, BwdTile& bt, int& adv) {
+                const Unit u = get_unit<C::kMtMax>(P, t, t_end);     // (the backward GEMMs are single-problem: never empty)
+                const EpiSplit<BN> sp = epi_split<BN>(u.mt, sub);
+                bt.tc = u.tile(sp.st); bt.step0 = sp.ch_begin; bt.nsteps = sp.ch_end - sp.ch_begin; bt.sub_tile = sp.st;
+                adv = u.adv;
             };
-            auto release = [&]() {
+            auto chunk_loader = [&](int it, const BwdTile& bt) {
+                const int acc = it & 1;
+                const uint32_t ph = static_cast<uint32_t>(it >> 1) & 1u;
+                const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                        static_cast<uint32_t>((acc * C::kMtMax + bt.sub_tile) * BN);
+                uint64_t* bar = &tfull_bar[acc];
+                int* err = P.err_flag;
+                bool waited = false;
+                return [=](int ch, float (&v)[32]) mutable {
+                    if (!waited) {       // the row-data phase runs before this wait
+                        mbar_wait(bar, ph, err, 4);
+                        tc_fence_after();
+                        waited = true;
+                    }
+                    uint32_t r[32];
+                    tmem_ld32(t_addr + ch * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                };
+            };
+            auto releaser = [&](int it) {
+                uint64_t* bar = &tempty_bar[it & 1];
+                return [=]() {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar);
+                };
+            };
+            if (P.split) bwd_warp_loop<BN, C::kBwdSteps, true>(P, q, lane, ws, t_begin, t_end, tile_at, chunk_loader, releaser);
+            else bwd_warp_loop<BN, C::kBwdSteps, false>(P, q, lane, ws, t_begin, t_end, tile_at, chunk_loader, releaser);
+        } else {
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            int coef_key = -1;
+            for (int t = t_begin; t < t_end;) {
+                const Unit u = get_unit<C::kMtMax>(P, t, t_end);
+                t += u.adv;
+                if (u.mt == 0) continue;
+                const EpiSplit<BN> sp = epi_split<BN>(u.mt, sub);
+                const TileCoord tc = u.tile(sp.st);
+                const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                        static_cast<uint32_t>((acc * C::kMtMax + sp.st) * BN);
+                bool waited = false;
+                auto load_chunk = [&](int ch, float (&v)[32]) {
+                    if (!waited) {
+                        mbar_wait(&tfull_bar[acc], acc_phase, P.err_flag, 4);
+                        tc_fence_after();
+                        waited = true;
+                    }
+                    uint32_t r[32];
+                    tmem_ld32(t_addr + ch * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                };
+                uint8_t* stg = epi_smem + e * (2048 * C::kStageTensors);
+                if (C::kStageTensors > 0 && P.tma_store) {
+                    const float* ctab = nullptr;
+                    if constexpr (EPI == kEpiFwd) {
+                        // (re)fill the warp group's coefficient table when the (sample, column block) changes
+                        float* tab = reinterpret_cast<float*>(epi_smem + 8 * 2048 * C::kStageTensors) + sub * (6 * BN);
+                        const int key = tc.n0 * P.n_blocks + tc.nblk;
+                        if (key != coef_key) {
+                            asm volatile("bar.sync %0, 128;" ::"r"(1 + sub) : "memory");       // the group is done with the old table
+                            const long long cb = static_cast<long long>(tc.n0) * P.n_total + tc.nblk * BN;
+                            for (int i = q * 32 + lane; i < BN; i += 128) {
+                                tab[i] = __ldg(P.demod + cb + i);
+                                tab[BN + i] = P.s_next ? __ldg(P.s_next + cb + i) : 0.f;
+                                const float4 w4 = P.rgbw ? __ldg(P.rgbw + cb + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                tab[2 * BN + i] = w4.x; tab[3 * BN + i] = w4.y; tab[4 * BN + i] = w4.z;
+                                tab[5 * BN + i] = __ldg(P.bias + tc.nblk * BN + i);
+                            }
+                            asm volatile("bar.sync %0, 128;" ::"r"(1 + sub) : "memory");
+                            coef_key = key;
+                        }
+                        ctab = tab;
+                    }
+                    rowowner_warp_tile<BN, EPI, (C::kStageTensors > 0)>(P, tc, q, lane, sp.ch_begin, sp.ch_end, sp.whole ? 0 : sub, sp.whole, stg, ctab, load_chunk);
+                } else {
+                    rowowner_warp_tile<BN, EPI, false>(P, tc, q, lane, sp.ch_begin, sp.ch_end, sp.whole ? 0 : sub, sp.whole, nullptr, nullptr, load_chunk);
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-            };
-            if constexpr (EPI == kEpiBwd) {
-                bwd_warp_tile<BN, C::kBwdSteps, true>(P, tc, q, lane, sp.ch_begin, sp.ch_end - sp.ch_begin, ws, st, load_chunk, release);
-            } else {
-                uint8_t* stg = epi_smem + e * (2048 * C::kStageTensors);
-                if (C::kStageTensors > 0 && P.tma_store)
-                    rowowner_warp_tile<BN, EPI, (C::kStageTensors > 0)>(P, tc, q, lane, sp.ch_begin, sp.ch_end, sp.whole ? 0 : sub, sp.whole, stg, load_chunk);
-                else
-                    rowowner_warp_tile<BN, EPI, false>(P, tc, q, lane, sp.ch_begin, sp.ch_end, sp.whole ? 0 : sub, sp.whole, nullptr, load_chunk);
-                release();
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (EPI == kEpiBwd) bwd_flush<BN, C::kBwdSteps>(P, st, lane);
-        if (C::kStageTensors > 0 && lane == 0) bulk_wait_read<0>();      // staging tiles stay valid until the last store has read them
     }
 
     tc_fence_before();
     __syncthreads();
+    if (P.dbg_clock && blockIdx.x == 0 && threadIdx.x == 64) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        P.dbg_clock[0] = clock64() - dbg_c0;
+        P.dbg_clock[1] = t1 - dbg_t0;
+    }
     if (warp == 2) tmem_dealloc<C::kTmemCols>(tmem_base);
 }
 
@@ -742,48 +964,60 @@ __global__ void __launch_bounds__(kEpiThreads) tapgemm_simt_kernel(const __grid_
     const int q = e & 3, sub = e >> 2;
     int t_begin, t_end;
     tile_range(P, t_begin, t_end);
-    BwdState<C::kBwdSteps> st;
-    if (EPI == kEpiBwd) bwd_state_init(st);
     const int K = P.kchunks * kBlockK;
     const int box_px = P.th * P.tw;
-    for (int t = t_begin; t < t_end;) {
-        const Unit u = get_unit<C::kMtMax>(P, t, t_end);
-        t += u.mt;
-        const EpiSplit<BN> sp = epi_split<BN>(u.mt, sub);
-        const TileCoord tc = u.tile(sp.st);
+    // brute-force accumulator chunk of row (32q + lane) of tile tc
+    auto brute = [&](const TileCoord& tc, int ch, float (&v)[32]) {
         const TapProblem& pr = P.prob[tc.prob];
         const int row = q * 32 + lane;
         const int ni = row / box_px, rem = row - ni * box_px;
         const int n = tc.n0 + ni, h = tc.h0 + rem / P.tw, w = tc.w0 + rem % P.tw;
-        const bool in_box = ni < P.nb && n < P.batch;
-        auto load_chunk = [&](int ch, float (&v)[32]) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
-            if (!in_box) return;
-            const int rows_total = EPI == kEpiTopK ? P.n_codes : P.n_total;
-            const int jmax = rows_total - (tc.nblk * BN + ch * 32);
-            for (int ti = 0; ti < pr.ntaps; ++ti) {
-                const Tap tap = P.taps[pr.tap_begin + ti];
-                const int hh = h + tap.dy, ww = w + tap.dx;
-                if (hh < 0 || hh >= ops.a_hs[tap.src] || ww < 0 || ww >= ops.a_ws[tap.src]) continue;
-                const __nv_bfloat16* arow = reinterpret_cast<const __nv_bfloat16*>(ops.a_ptrs[tap.src]) +
-                                            n * ops.a_sn + hh * ops.a_sh + ww * ops.a_sw;
-                const __nv_bfloat16* wmat = reinterpret_cast<const __nv_bfloat16*>(ops.w) +
-                                            (static_cast<long long>(tap.widx) * rows_total + tc.nblk * BN + ch * 32) * K;
-                for (int k = 0; k < K; ++k) {
-                    const float a = __bfloat162float(arow[k]);
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        if (!(ni < P.nb && n < P.batch)) return;
+        const int rows_total = EPI == kEpiTopK ? P.n_codes : P.n_total;
+        const int jmax = rows_total - (tc.nblk * BN + ch * 32);
+        for (int ti = 0; ti < pr.ntaps; ++ti) {
+            const Tap tap = P.taps[pr.tap_begin + ti];
+            const int hh = h + tap.dy, ww = w + tap.dx;
+            if (hh < 0 || hh >= ops.a_hs[tap.src] || ww < 0 || ww >= ops.a_ws[tap.src]) continue;
+            const __nv_bfloat16* arow = reinterpret_cast<const __nv_bfloat16*>(ops.a_ptrs[tap.src]) +
+                                        n * ops.a_sn + hh * ops.a_sh + ww * ops.a_sw;
+            const __nv_bfloat16* wmat = reinterpret_cast<const __nv_bfloat16*>(ops.w) +
+                                        (static_cast<long long>(tap.widx) * rows_total + tc.nblk * BN + ch * 32) * K;
+            for (int k = 0; k < K; ++k) {
+                const float a = __bfloat162float(arow[k]);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < jmax) v[j] = fmaf(a, __bfloat162float(wmat[static_cast<long long>(j) * K + k]), v[j]);
-                }
+                for (int j = 0; j < 32; ++j)
+                    if (j < jmax) v[j] = fmaf(a, __bfloat162float(wmat[static_cast<long long>(j) * K + k]), v[j]);
             }
+        }
+    };
+    if constexpr (EPI == kEpiBwd) {
+        auto tile_at = [&](int t, BwdTile& bt, int& adv) {
+            const Unit u = get_unit<C::kMtMax>(P, t, t_end);
+            const EpiSplit<BN> sp = epi_split<BN>(u.mt, sub);
+            bt.tc = u.tile(sp.st); bt.step0 = sp.ch_begin; bt.nsteps = sp.ch_end - sp.ch_begin; bt.sub_tile = sp.st;
+            adv = u.adv;
         };
-        if constexpr (EPI == kEpiBwd)
-            bwd_warp_tile<BN, C::kBwdSteps, true>(P, tc, q, lane, sp.ch_begin, sp.ch_end - sp.ch_begin, &wsm[e], st, load_chunk, [] {});
-        else
-            rowowner_warp_tile<BN, EPI, false>(P, tc, q, lane, sp.ch_begin, sp.ch_end, sp.whole ? 0 : sub, sp.whole, nullptr, load_chunk);
+        auto chunk_loader = [&](int, const BwdTile& bt) {
+            const TileCoord tc = bt.tc;
+            return [&brute, tc](int ch, float (&v)[32]) { brute(tc, ch, v); };
+        };
+        auto releaser = [&](int) { return [] {}; };
+        if (P.split) bwd_warp_loop<BN, C::kBwdSteps, true>(P, q, lane, &wsm[e], t_begin, t_end, tile_at, chunk_loader, releaser);
+        else bwd_warp_loop<BN, C::kBwdSteps, false>(P, q, lane, &wsm[e], t_begin, t_end, tile_at, chunk_loader, releaser);
+    } else {
+        for (int t = t_begin; t < t_end;) {
+            const Unit u = get_unit<C::kMtMax>(P, t, t_end);
+            t += u.adv;
+            if (u.mt == 0) continue;
+            const EpiSplit<BN> sp = epi_split<BN>(u.mt, sub);
+            const TileCoord tc = u.tile(sp.st);
+            auto load_chunk = [&](int ch, float (&v)[32]) { brute(tc, ch, v); };
+            rowowner_warp_tile<BN, EPI, false>(P, tc, q, lane, sp.ch_begin, sp.ch_end, sp.whole ? 0 : sub, sp.whole, nullptr, nullptr, load_chunk);
+        }
     }
-    if (EPI == kEpiBwd) bwd_flush<BN, C::kBwdSteps>(P, st, lane);
 }
 
 // Seed of the backward chain: activation backward of the top layer from the toRGB gradient alone (the
@@ -998,6 +1232,7 @@ int launch_bn_epi(const TapGemmParams& p, int num_sms, cudaStream_t stream) {
     for (int i = 0; i < p.nprob; ++i)
         if (p.prob[i].ntaps <= 0 || p.prob[i].ngroups <= 0) return static_cast<int>(cudaErrorInvalidValue);   // accumulator would be undefined
     if (p.halo != 0 && (p.halo != 2 || p.tw != 8 || p.nb != 1 || p.th != 16)) return static_cast<int>(cudaErrorInvalidValue);
+    if (p.interleave && (p.epilogue == kEpiBwd || p.m_tiles % (2 * p.nprob))) return static_cast<int>(cudaErrorInvalidValue);
     if (p.nb * (p.th + p.halo) * p.tw * 128 > kASubBytes) return static_cast<int>(cudaErrorInvalidValue);
     if (total <= num_sms && !p.no_pair) {       // one tile per CTA: nothing to pair, so run the deeper unpaired A ring
         TapGemmParams q = p;

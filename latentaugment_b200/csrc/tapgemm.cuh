@@ -70,6 +70,10 @@ struct TapGemmParams {
     uint8_t gwidx[kMaxTaps];         // per grouped tap: weight matrix
     int halo;                        // extra rows of the A box (0 or 2); 2 needs tw == 8 and nb == 1
     int no_pair;                     // 1: never pair M tiles (tuning switch)
+    int interleave;                  // 1: all problems share one tile grid (tiles_h/w equal, vh/vw mask) and are walked
+                                     //    [column block][pair of spatial tiles][problem][tile of the pair], so that every
+                                     //    CTA gets the same mix of cheap and expensive problems
+    int dbg_skip_epi;                // 1: epilogues only drain the accumulators (timing experiments: wrong results)
     TapProblem prob[kMaxProblems];
     int nprob;
     int th, tw, nb;        // M-tile box: nb images x th rows x tw cols (nb*th*tw <= 128)
@@ -122,6 +126,7 @@ struct TapGemmParams {
     int* cand_idx;                     // [n_queries][n_blocks][2][topk]
 
     int* err_flag;
+    unsigned long long* dbg_clock;     // optional [2]: SM cycles and nanoseconds CTA 0 spent in the kernel (clock-under-load experiments)
 };
 
 // Groups the flat taps of every problem (call after taps / prob[].tap_begin / ntaps are set).  Returns 0 on success.
