@@ -60,23 +60,71 @@ __global__ void pairwise_kernel(const float* __restrict__ X, int n, const float*
     if (lane == 0) D[pair] = (static_cast<float>(yy) + static_cast<float>(xx)) - 2.f * static_cast<float>(yx);
 }
 
-// Exact re-rank: warp per query over its n_blocks*kCand candidates; keeps the k smallest
-// (distance, index) pairs, ties to the lowest index.
-__global__ void rerank_kernel(const float* __restrict__ X, const float* __restrict__ xx, const float* __restrict__ Y,
-                              const float* __restrict__ yy, int n, int K, const int* __restrict__ cand_idx, int ncand, int k,
-                              long long index_offset, float* out_dist, long long* out_idx) {
-    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// Exact re-rank, warp per query.  The tap-GEMM left n_blocks * 2 * kCand candidates with approximate
+// scores |y|^2 - 2<x,y> (split-bf16 operands, fp32 accumulate: relative error ~1e-5).  Stage 1: every
+// lane keeps the 8 best of its strided share by approximate score (the union holds the global 8 best);
+// the warp's 8th best plus a 2e-3 relative margin -- two orders of magnitude above the GEMM error --
+// bounds what can still be among the exact k best.  Stage 2: the surviving candidates are recomputed
+// exactly (fp64 dot, one rounding, the reference's association (YY + XX) - 2 YX) and the k smallest
+// (distance, index) pairs are kept, ties to the lowest index.
+__global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ X, const float* __restrict__ xx, const float* __restrict__ Y,
+                                                     const float* __restrict__ yy, int n, int K, const float* __restrict__ cand_score,
+                                                     const int* __restrict__ cand_idx, int ncand, int k, long long index_offset,
+                                                     float* out_dist, long long* out_idx) {
+    __shared__ int s_list[8][256];
+    const int wib = threadIdx.x >> 5;
+    const int i = blockIdx.x * (blockDim.x >> 5) + wib;
     const int lane = threadIdx.x & 31;
     if (i >= n) return;
+    const float INF = __int_as_float(0x7f800000);
+    float ls[8];
+    int li[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) { ls[t] = INF; li[t] = -1; }
+    const float* cs = cand_score + static_cast<long long>(i) * ncand;
+    const int* ci = cand_idx + static_cast<long long>(i) * ncand;
+    for (int c = lane; c < ncand; c += 32) {
+        float sc = cs[c];
+        int id = ci[c];
+        if (id < 0 || !(sc < ls[7])) continue;
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+            if (sc < ls[t]) { const float ts = ls[t]; const int ti = li[t]; ls[t] = sc; li[t] = id; sc = ts; id = ti; }
+    }
+    // the warp's 8th smallest approximate score: pop the minimum of the lane heads 8 times
+    int head = 0;
+    float thr = INF;
+    for (int r = 0; r < 8; ++r) {
+        float h = INF;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) if (t == head) h = ls[t];
+        float m = h;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        thr = m;
+        if (m == INF) break;
+        const unsigned who = __ballot_sync(0xffffffffu, h == m);
+        if (lane == __ffs(who) - 1) ++head;
+    }
+    const float xi = xx[i];
+    const float cut = thr == INF ? INF : thr + 2e-3f * (fabsf(thr) + xi + 1e-30f);
+    // compact the survivors into the warp's list
+    int cnt = 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const bool keep = li[t] >= 0 && ls[t] <= cut;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) s_list[wib][cnt + __popc(bal & ((1u << lane) - 1))] = li[t];
+        cnt += __popc(bal);
+    }
+    __syncwarp();
     float bd[8];
     int bi[8];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) { bd[t] = __int_as_float(0x7f800000); bi[t] = 0x7fffffff; }
+    for (int t = 0; t < 8; ++t) { bd[t] = INF; bi[t] = 0x7fffffff; }
     const float* x = X + static_cast<long long>(i) * K;
-    const float xi = xx[i];
-    for (int c = 0; c < ncand; ++c) {
-        const int j = cand_idx[static_cast<long long>(i) * ncand + c];
-        if (j < 0) continue;
+    for (int c = 0; c < cnt; ++c) {
+        const int j = s_list[wib][c];
         const float* y = Y + static_cast<long long>(j) * K;
         double dot = 0.0;
         for (int kk = lane; kk < K; kk += 32) dot += static_cast<double>(x[kk]) * y[kk];
@@ -244,7 +292,7 @@ int la_nearest_codes(const float* d_X, int n, const float* d_Y, const void* d_ba
         int r = launch_tapgemm(P, sms, s);
         if (r) return la_fail_msg(r, "launch_tapgemm failed");
     }
-    rerank_kernel<<<(n + 7) / 8, 256, 0, s>>>(d_X, xx, d_Y, d_bank_sqnorm, n, K, ci, L.ncand, k, index_offset, d_dist, d_idx);
+    rerank_kernel<<<(n + 7) / 8, 256, 0, s>>>(d_X, xx, d_Y, d_bank_sqnorm, n, K, cs, ci, L.ncand, k, index_offset, d_dist, d_idx);
     DCU(cudaGetLastError());
     return 0;
 }

@@ -149,14 +149,6 @@ int make_a_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, lon
     uint32_t box[4] = {64, static_cast<uint32_t>(tw), static_cast<uint32_t>(th), static_cast<uint32_t>(nb)};
     return encode_tmap_bf16(m, base, 4, dims, strides, box);
 }
-// Output map of the row-owner epilogues: box = 32 channels x the 32 tile rows one epilogue warp owns, SWIZZLE_64B.
-int make_o_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, long long sW, long long sH, long long sN, int tw, int th) {
-    uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(N)};
-    uint64_t strides[3] = {static_cast<uint64_t>(sW) * 2, static_cast<uint64_t>(sH) * 2, static_cast<uint64_t>(sN) * 2};
-    const int px = th * tw;
-    uint32_t box[4] = {32, static_cast<uint32_t>(tw), static_cast<uint32_t>(px >= 32 ? 32 / tw : th), static_cast<uint32_t>(px >= 32 ? 1 : 32 / px)};
-    return encode_tmap_bf16(m, base, 4, dims, strides, box, 64);
-}
 int make_b_map(CUtensorMap* m, const void* base, int K, int rows, int nmat, int bn) {
     uint64_t dims[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(rows), static_cast<uint64_t>(nmat)};
     uint64_t strides[2] = {static_cast<uint64_t>(K) * 2, static_cast<uint64_t>(K) * rows * 2};
@@ -429,23 +421,9 @@ int build_params(la_engine* e) {
             F.xs_hi = F.xs_lo = nullptr; F.s_next = nullptr; F.rgbw = nullptr;
         }
 
-        // tensor stores of the forward epilogue (bf16 mode; the folded x2 layers keep per-thread stores)
-        static const bool no_tma_store = getenv("LA_NO_TMA_STORE") != nullptr;
-        if (!split && !no_tma_store) {
-            if (c.split_up) {
-                for (int ph = 0; ph < 4; ++ph) {
-                    const int py = ph / 2, px = ph % 2;
-                    LA(make_o_map(&F.o_map[ph], e->t_hi + (static_cast<long long>(py) * TWp + px) * c.cout, c.cout, F.prob[ph].vw, F.prob[ph].vh, B,
-                                  2LL * c.cout, 2LL * TWp * c.cout, static_cast<long long>(TH) * TWp * c.cout, F.tw, F.th));
-                }
-                F.tma_store = 1;
-            } else if (c.up == 1 && F.nb == 1) {
-                const long long oW = c.cout, oH = static_cast<long long>(c.res) * c.cout, oN = oH * c.res;
-                LA(make_o_map(&F.o_map[0], c.x_hi, c.cout, c.res, c.res, B, oW, oH, oN, F.tw, F.th));
-                if (next) LA(make_o_map(&F.o_map[1], e->xs_hi[(l + 1) & 1], c.cout, c.res, c.res, B, oW, oH, oN, F.tw, F.th));
-                F.tma_store = 1;
-            }
-        }
+        // staged stores + coefficient tables in the row-owner epilogues (bf16 mode, one sample per tile)
+        static const bool no_staged = getenv("LA_NO_STAGED") != nullptr;
+        if (!split && !no_staged && F.nb == 1 && (c.split_up || c.up == 1)) F.staged = 1;
 
         // ---------------------------------------------------------------- data gradient
         TapGemmParams& G = c.bwd;
@@ -506,7 +484,7 @@ int build_params(la_engine* e) {
         G.prob[0].ntaps = nt;
         if (tapgemm_finalize(F) || tapgemm_finalize(G)) return fail(-2, "tap grouping failed");
         F.no_pair = G.no_pair = getenv("LA_NO_PAIR") != nullptr;
-        F.dbg_skip_epi = G.dbg_skip_epi = getenv("LA_DBG_SKIP_EPI") ? atoi(getenv("LA_DBG_SKIP_EPI")) : 0;
+        F.dbg_skip_epi = G.dbg_skip_epi = getenv("LA_DBG_SKIP_EPI") != nullptr;     // timing experiment: wrong results
         const int bnb = pick_bn(c.cin, G.m_tiles);
         LA(make_b_map(&G.b_map, c.wb, c.cout, c.cin, nmat * (split ? 2 : 1), bnb));
         G.kchunks = c.cout / 64; G.n_total = c.cin; G.n_blocks = c.cin / bnb;

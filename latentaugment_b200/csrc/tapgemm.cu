@@ -245,10 +245,11 @@ __device__ __forceinline__ void stage_bf16x32(uint8_t* stg, int lane, const floa
 // ---- row-owner epilogues: raw store, bf16 store, forward activation, top-k.
 // The lane owns row 32*q + lane and walks chunks [ch_begin, ch_end); `part` selects the per-column-block
 // slot (0 / 1) of the per-row outputs (toRGB partial, top-k candidates); with `fill_other` the other slot is
-// written as empty (the warp covered the whole column block).  With kTma the bf16 outputs go through the
-// warp's shared-memory staging tile and one tensor store per 32-channel chunk (full 64-byte row segments
-// instead of 16-byte pieces per thread); `stg` = kStageTensors x 2 KB.
-template <int BN, int EPI, bool kTma, class LoadChunk>
+// written as empty (the warp covered the whole column block).  With kStaged (one sample per tile) the bf16
+// outputs go through the warp's 2 KB shared-memory staging tile `stg` and are re-read so that every store
+// instruction writes whole 64-byte row segments instead of 32 scattered 16-byte pieces, and the forward
+// epilogue reads its per-column coefficients from the warp group's table `ctab` instead of global memory.
+template <int BN, int EPI, bool kStaged, class LoadChunk>
 __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const TileCoord& tc, int q, int lane, int ch_begin, int ch_end,
                                                    int part, bool fill_other, uint8_t* stg, const float* ctab, LoadChunk&& load_chunk) {
     const RowCtx rc = make_row(P, tc, q * 32 + lane);
@@ -265,7 +266,7 @@ __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const
     // every store instruction writes whole 64-byte row segments (row-owner stores write 32 scattered pieces)
     long long srow[4];
     bool sok[4];
-    if (kTma) {
+    if (kStaged) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const RowCtx r = make_row(P, tc, q * 32 + 8 * j + (lane >> 2));
@@ -280,10 +281,7 @@ __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const
         for (int j = 0; j < 4; ++j) {
             const int rr = 8 * j + (lane >> 2);
             const uint4 v = *reinterpret_cast<const uint4*>(tile + rr * 64 + ((((lane & 3) ^ (rr >> 1)) & 3) << 4));
-            if (sok[j]) {
-                if (P.dbg_skip_epi == 200) *reinterpret_cast<uint4*>(dst + srow[j]) = v;
-                else __stcs(reinterpret_cast<uint4*>(dst + srow[j]), v);      // streaming: the outputs must not displace the operands in L2
-            }
+            if (sok[j]) *reinterpret_cast<uint4*>(dst + srow[j]) = v;
         }
         __syncwarp();
     };
@@ -293,18 +291,6 @@ __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const
         float acc[32];
         load_chunk(ch, acc);
         if (P.dbg_skip_epi == 1) continue;
-        if (P.dbg_skip_epi >= 2 && P.dbg_skip_epi < 100) {            // timing experiment: ALU work only (about as many FMAs as the real epilogue)
-            float t = 0.f;
-#pragma unroll 1
-            for (int rep = 0; rep < P.dbg_skip_epi; ++rep) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) acc[j] = fmaf(acc[j], 1.0001f, 0.5f);
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) t += acc[j];
-            if (t == 123.456f) P.raw_out[0] = t;
-            continue;
-        }
         const int col0 = tc.nblk * BN + ch * 32;
         const long long eoff = rc.pix * P.n_total + col0;             // element offset in [pixel][N] tensors
         const long long coff = static_cast<long long>(rc.n) * P.n_total + col0;   // offset in [batch][N] tensors
@@ -315,7 +301,7 @@ __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const
                 for (int j = 0; j < 8; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
             }
         } else if constexpr (EPI == kEpiStoreBf16) {
-            if (kTma) {
+            if (kStaged) {
                 stage_bf16x32(stg, lane, acc);
                 flush_stage(stg, P.x_hi, col0);
             } else if (rc.valid) {
@@ -343,14 +329,13 @@ __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const
                 }
             }
         } else if constexpr (EPI == kEpiFwd) {
-            if (kTma) {
+            if (kStaged) {
                 // staged path (one sample per tile): coefficients come from the warp group's shared-memory table
                 const float4* t_dm = reinterpret_cast<const float4*>(ctab + ch * 32);
                 const float4* t_bs = reinterpret_cast<const float4*>(ctab + 5 * BN + ch * 32);
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 d4 = (P.dbg_skip_epi >= 100 && ((P.dbg_skip_epi - 100) & 2)) ? make_float4(1.f, 1.f, 1.f, 1.f) : t_dm[j4];
-                    const float4 b4 = (P.dbg_skip_epi >= 100 && ((P.dbg_skip_epi - 100) & 2)) ? make_float4(1.f, 1.f, 1.f, 1.f) : t_bs[j4];
+                    const float4 d4 = t_dm[j4], b4 = t_bs[j4];
                     const float dd[4] = {d4.x, d4.y, d4.z, d4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -359,12 +344,9 @@ __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const
                         acc[4 * j4 + k] = fminf(fmaxf(z, -clampv), clampv);
                     }
                 }
-                const int dbg = P.dbg_skip_epi >= 100 ? P.dbg_skip_epi - 100 : 0;   // timing experiments (wrong results)
-                if (!(dbg & 1)) {
-                    stage_bf16x32(stg, lane, acc);
-                    flush_stage(stg, P.x_hi, col0);
-                }
-                if (P.rgbw && !(dbg & 4)) {
+                stage_bf16x32(stg, lane, acc);
+                flush_stage(stg, P.x_hi, col0);
+                if (P.rgbw) {
                     const float4* t0 = reinterpret_cast<const float4*>(ctab + 2 * BN + ch * 32);
                     const float4* t1 = reinterpret_cast<const float4*>(ctab + 3 * BN + ch * 32);
                     const float4* t2 = reinterpret_cast<const float4*>(ctab + 4 * BN + ch * 32);
@@ -383,12 +365,8 @@ __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const
                         const float4 s4 = t_sn[j4];
                         acc[4 * j4] *= s4.x; acc[4 * j4 + 1] *= s4.y; acc[4 * j4 + 2] *= s4.z; acc[4 * j4 + 3] *= s4.w;
                     }
-                    if (!(dbg & 1)) {
-                        stage_bf16x32(stg, lane, acc);
-                        flush_stage(stg, P.xs_hi, col0);
-                    } else if (acc[3] == 123.456f) {
-                        P.raw_out[0] = acc[5];
-                    }
+                    stage_bf16x32(stg, lane, acc);
+                    flush_stage(stg, P.xs_hi, col0);
                 }
             } else if (rc.valid) {
                 float dm[32], bs[32];
@@ -907,7 +885,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                 };
                 uint8_t* stg = epi_smem + e * (2048 * C::kStageTensors);
-                if (C::kStageTensors > 0 && P.tma_store) {
+                if (C::kStageTensors > 0 && P.staged) {
                     const float* ctab = nullptr;
                     if constexpr (EPI == kEpiFwd) {
                         // (re)fill the warp group's coefficient table when the (sample, column block) changes

@@ -60,10 +60,9 @@ enum TapEpilogue : int {
 struct TapGemmParams {
     alignas(64) CUtensorMap a_map[kMaxAMaps];
     alignas(64) CUtensorMap b_map;
-    // Output tensor maps of the row-owner epilogues (bf16 mode): box = [32 channels, the 32 rows of one warp],
-    // SWIZZLE_64B.  kEpiFwd: o_map[0] = x, o_map[1] = x * s_next.  kEpiStoreBf16: o_map[problem].
-    alignas(64) CUtensorMap o_map[4];
-    int tma_store;                   // 1: stage through shared memory + tensor stores (o_map valid)
+    int staged;                      // 1 (bf16 mode, nb == 1): the row-owner epilogues stage their bf16 outputs through shared
+                                     //    memory (whole 64-byte row segments per store) and, in the forward epilogue, read the
+                                     //    per-column coefficients from a shared-memory table
     Tap taps[kMaxTaps];              // flat tap list (host bookkeeping + the SIMT twin)
     TapGroup groups[kMaxTaps];       // the same taps grouped for the tensor-core kernel (tapgemm_finalize)
     uint8_t gdyrel[kMaxTaps];        // per grouped tap: dy - dy0 of its group (0..halo)
@@ -73,7 +72,7 @@ struct TapGemmParams {
     int interleave;                  // 1: all problems share one tile grid (tiles_h/w equal, vh/vw mask) and are walked
                                      //    [column block][pair of spatial tiles][problem][tile of the pair], so that every
                                      //    CTA gets the same mix of cheap and expensive problems
-    int dbg_skip_epi;                // 1: epilogues only drain the accumulators (timing experiments: wrong results)
+    int dbg_skip_epi;                // 1: epilogues only drain the accumulators (timing experiment: wrong results)
     TapProblem prob[kMaxProblems];
     int nprob;
     int th, tw, nb;        // M-tile box: nb images x th rows x tw cols (nb*th*tw <= 128)
