@@ -105,6 +105,7 @@ __global__ void prep_const_kernel(const float* __restrict__ cst, int C, int hw, 
 // warp per affine row; the row stays in registers while the warp walks the batch.
 constexpr int kMaxRowRegs = 32;   // rows up to 1024 floats
 
+constexpr int kSampleUnroll = 4;
 __global__ void styles_kernel(LayerTable T, const float* __restrict__ ws, long long sn, long long sidx,
                               const float* __restrict__ a_cat, const float* __restrict__ b_cat, int w_dim, int batch,
                               float* s_cat) {
@@ -120,14 +121,23 @@ __global__ void styles_kernel(LayerTable T, const float* __restrict__ ws, long l
 #pragma unroll
     for (int r = 0; r < kMaxRowRegs; ++r) a[r] = (lane + 32 * r < w_dim) ? arow[lane + 32 * r] : 0.f;
     const float b = b_cat[soff + i];
-    for (int n = 0; n < batch; ++n) {
-        const float* wrow = ws + n * sn + widx * sidx;
-        float acc = 0.f;
+    for (int n0 = 0; n0 < batch; n0 += kSampleUnroll) {
+        float acc[kSampleUnroll];
 #pragma unroll
-        for (int r = 0; r < kMaxRowRegs; ++r)
-            if (lane + 32 * r < w_dim) acc = fmaf(a[r], wrow[lane + 32 * r], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) s_cat[static_cast<long long>(batch) * soff + static_cast<long long>(n) * cin + i] = acc + b;
+        for (int u = 0; u < kSampleUnroll; ++u) {
+            acc[u] = 0.f;
+            if (n0 + u < batch) {
+                const float* wrow = ws + (n0 + u) * sn + widx * sidx;
+#pragma unroll
+                for (int r = 0; r < kMaxRowRegs; ++r)
+                    if (lane + 32 * r < w_dim) acc[u] = fmaf(a[r], wrow[lane + 32 * r], acc[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kSampleUnroll; ++u) acc[u] = warp_sum(acc[u]);
+#pragma unroll
+        for (int u = 0; u < kSampleUnroll; ++u)
+            if (lane == 0 && n0 + u < batch) s_cat[static_cast<long long>(batch) * soff + static_cast<long long>(n0 + u) * cin + i] = acc[u] + b;
     }
 }
 
@@ -140,14 +150,24 @@ __global__ void demod_kernel(LayerTable T, int batch, const float* __restrict__ 
     const float* row = D.w2 + static_cast<long long>(o) * D.cin;
 #pragma unroll
     for (int r = 0; r < kMaxRowRegs; ++r) a[r] = (lane + 32 * r < D.cin) ? row[lane + 32 * r] : 0.f;
-    for (int n = 0; n < batch; ++n) {
-        const float* s = s_cat + static_cast<long long>(batch) * D.soff + static_cast<long long>(n) * D.cin;
-        float acc = 0.f;
+    for (int n0 = 0; n0 < batch; n0 += kSampleUnroll) {      // several samples in flight: the loop is latency-bound otherwise
+        float acc[kSampleUnroll];
 #pragma unroll
-        for (int r = 0; r < kMaxRowRegs; ++r)
-            if (lane + 32 * r < D.cin) { const float v = s[lane + 32 * r]; acc = fmaf(a[r], v * v, acc); }
-        acc = warp_sum(acc);
-        if (lane == 0) d_cat[static_cast<long long>(batch) * D.doff + static_cast<long long>(n) * D.cout + o] = rsqrtf(acc + 1e-8f);
+        for (int u = 0; u < kSampleUnroll; ++u) {
+            acc[u] = 0.f;
+            if (n0 + u < batch) {
+                const float* s = s_cat + static_cast<long long>(batch) * D.soff + static_cast<long long>(n0 + u) * D.cin;
+#pragma unroll
+                for (int r = 0; r < kMaxRowRegs; ++r)
+                    if (lane + 32 * r < D.cin) { const float v = s[lane + 32 * r]; acc[u] = fmaf(a[r], v * v, acc[u]); }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kSampleUnroll; ++u) acc[u] = warp_sum(acc[u]);
+#pragma unroll
+        for (int u = 0; u < kSampleUnroll; ++u)
+            if (lane == 0 && n0 + u < batch)
+                d_cat[static_cast<long long>(batch) * D.doff + static_cast<long long>(n0 + u) * D.cout + o] = rsqrtf(acc[u] + 1e-8f);
     }
 }
 
@@ -596,20 +616,29 @@ __global__ void style_grad_conv_kernel(LayerTable T, int batch, const float* __r
     const float* row = D.w2t + static_cast<long long>(i) * D.cout;
 #pragma unroll
     for (int r = 0; r < kMaxRowRegs; ++r) a[r] = (lane + 32 * r < D.cout) ? row[lane + 32 * r] : 0.f;
-    for (int n = 0; n < batch; ++n) {
-        const long long dbase = static_cast<long long>(batch) * D.doff + static_cast<long long>(n) * D.cout;
-        float acc = 0.f;
+    for (int n0 = 0; n0 < batch; n0 += kSampleUnroll) {
+        float acc[kSampleUnroll];
 #pragma unroll
-        for (int r = 0; r < kMaxRowRegs; ++r)
-            if (lane + 32 * r < D.cout) {
-                const float d = d_cat[dbase + lane + 32 * r];
-                acc = fmaf(a[r], red_d[dbase + lane + 32 * r] * d * d, acc);
+        for (int u = 0; u < kSampleUnroll; ++u) {
+            acc[u] = 0.f;
+            if (n0 + u < batch) {
+                const long long dbase = static_cast<long long>(batch) * D.doff + static_cast<long long>(n0 + u) * D.cout;
+#pragma unroll
+                for (int r = 0; r < kMaxRowRegs; ++r)
+                    if (lane + 32 * r < D.cout) {
+                        const float d = d_cat[dbase + lane + 32 * r];
+                        acc[u] = fmaf(a[r], red_d[dbase + lane + 32 * r] * d * d, acc[u]);
+                    }
             }
-        acc = warp_sum(acc);
-        if (lane == 0) {
-            const long long si = static_cast<long long>(batch) * D.soff + static_cast<long long>(n) * D.cin + i;
-            g_s[si] = red_s[si] - s_cat[si] * acc;
         }
+#pragma unroll
+        for (int u = 0; u < kSampleUnroll; ++u) acc[u] = warp_sum(acc[u]);
+#pragma unroll
+        for (int u = 0; u < kSampleUnroll; ++u)
+            if (lane == 0 && n0 + u < batch) {
+                const long long si = static_cast<long long>(batch) * D.soff + static_cast<long long>(n0 + u) * D.cin + i;
+                g_s[si] = red_s[si] - s_cat[si] * acc[u];
+            }
     }
 }
 
