@@ -79,15 +79,16 @@ class LatentAugOracle:
     """The N-step Adam loop on w (ULA:207-310) with the latent and pixel criteria.
 
     ``G`` exposes ``.synthesis(ws, noise_mode=...)``, ``.mapping``, ``num_ws``,
-    ``w_dim``.  LPIPS / discriminator terms need weights and classes that are not
-    available offline and must have zero weight here.
+    ``w_dim``; ``D`` (optional) is the realism-term discriminator (oracle/sg2_disc.py).  The LPIPS
+    term needs weights that are not available offline and must have zero weight.
     """
 
     def __init__(self, G, W=None, X=None, *, num_epochs=10, opt_lr=0.01, w_latent=1.0, w_pix=1.0,
                  w_lpips=0.0, w_disc=0.0, soft_aug=False, alpha=1.0, truncation_psi=1.0,
-                 n_modalities=None, res=None, crop_size=64, preprocess='center_random_crop', fused=True):
-        assert w_lpips == 0.0 and w_disc == 0.0, 'oracle covers the latent and pixel criteria only'
-        self.G, self.W, self.X = G, W, X
+                 n_modalities=None, res=None, crop_size=64, preprocess='center_random_crop', fused=True, D=None):
+        assert w_lpips == 0.0, 'oracle covers the latent, pixel and discriminator criteria'
+        assert w_disc == 0.0 or D is not None, 'w_disc > 0 needs a discriminator'
+        self.G, self.W, self.X, self.D, self.w_disc = G, W, X, D, w_disc
         self.num_ws, self.w_dim = G.num_ws, G.w_dim
         self.num_epochs, self.opt_lr = num_epochs, opt_lr
         self.w_latent, self.w_pix = w_latent, w_pix
@@ -119,8 +120,11 @@ class LatentAugOracle:
             if self.w_pix > 0:
                 l_pix = calc_loss_pix(center_crop(x, self.res), center_crop(self.X, self.res),
                                       self.w_pix, self.n_modalities)
-            loss = -l_lat - l_pix                                              # ULA:270
-            self.loss_log.append(tuple(float(torch.as_tensor(v).detach()) for v in (l_lat, l_pix, loss)))
+            l_disc = 0.0
+            if self.w_disc > 0:                                                # ULA:363-371
+                l_disc = torch.nn.functional.softplus(-self.D(x, c=None)).mean() * self.w_disc
+            loss = -l_lat - l_pix + l_disc                                     # ULA:270
+            self.loss_log.append(tuple(float(torch.as_tensor(v).detach()) for v in (l_lat, l_pix, loss, l_disc)))
             optim.zero_grad()
             loss.backward()
             optim.step()
