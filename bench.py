@@ -169,6 +169,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32_parity'])
+    ap.add_argument('--w-disc', type=float, default=0.0, help='weight of the discriminator realism term (0 = the headline workload)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile', action='store_true', help='short run for ncu: skips the e2e leg, the CPU baseline and the per-GEMM timing')
     ap.add_argument('--layers-out', default='', help='write the per-layer tap-GEMM timing table (JSON) here')
@@ -207,7 +208,7 @@ def main():
     os.dup2(2, 1)
     real_stdout = os.fdopen(json_fd, 'w')
     sys.stdout = sys.stderr
-    opt = AugOptions().parse(args={'p_thres': 0.0, 'w_lpips': 0.0, 'w_disc': 0.0, 'init_w': 'inv', 'n_imgs': 0}, argv=argv)
+    opt = AugOptions().parse(args={'p_thres': 0.0, 'w_lpips': 0.0, 'w_disc': args.w_disc, 'init_w': 'inv', 'n_imgs': 0}, argv=argv)
     aug = create_augment(opt)
     core = aug.latent_aug.module
     eng = core.engines[0]
@@ -313,7 +314,8 @@ def main():
                 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'bf16 operands, f32 accumulate' if args.precision == 'bf16' else 'split-bf16 (hi+lo) operands, f32 accumulate',
                 'data': 'synthetic',
-                'config': {'workload': workload_name(args.config, c), 'precision': args.precision,
+                'config': {'workload': workload_name(args.config, c) + (f', w_disc={args.w_disc:g} (StyleGAN2 discriminator term)' if args.w_disc > 0 else ''),
+                           'precision': args.precision,
                            'l2': 'working set >> L2: ~2 GB of activations written and re-read per Adam step',
                            'parallelism': f'batch-sharded x{world}, no data-path collective'},
                 'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cb}

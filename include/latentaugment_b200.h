@@ -17,6 +17,8 @@
  *                            (ops: torch_utils/ops/{conv2d_resample,upfirdn2d,bias_act,fma}.py)
  *   la_augment            <- LatentAug.forward: the N-step Adam loop, criteria, gate, final synthesis
  *                                                                                util_latent_aug.py:207-310
+ *   la_set_discriminator  <- self.D (the unpickled StyleGAN2 discriminator, parameter contract legacy.py:220-289) and the
+ *                            realism term calc_loss_disc: softplus(-D(x, c=None)).mean() * w_disc   util_latent_aug.py:363-371
  *   la_pairwise_sqdist    <- l2_loss_vectorized(X, Y, compute_mean=False)         util_latent_aug.py:315-361
  *   la_nearest_codes      <- (north_star extension) argmin / top-k of that matrix
  */
@@ -87,15 +89,54 @@ typedef struct la_generator_desc {
 typedef struct la_augment_options {
     int num_steps;                 /* opt_num_epochs */
     float lr;                      /* opt_lr */
-    float w_latent, w_pix;         /* criteria weights; perceptual / discriminator terms must be 0 here */
+    float w_latent, w_pix;         /* criteria weights (the perceptual term is not part of this boundary) */
     int soft_aug;                  /* 0: hard_aug, 1: smooth_aug */
     float alpha;
     int final_noise_mode;          /* la_noise_mode of the last synthesis (reference default: random) */
     int n_modalities;              /* number of leading image channels the pixel criterion covers */
+    float w_disc;                  /* weight of the discriminator realism term; > 0 needs la_set_discriminator */
 } la_augment_options;
+
+/* One residual block of the StyleGAN2 'resnet' discriminator at resolution res (names per legacy.py:267-287). */
+typedef struct la_disc_block_params {
+    const float* d_fromrgb_weight; /* [ch, img_channels, 1, 1]  (top block only, else null) */
+    const float* d_fromrgb_bias;   /* [ch] */
+    const float* d_conv0_weight;   /* [ch, ch, 3, 3] */
+    const float* d_conv0_bias;     /* [ch] */
+    const float* d_conv1_weight;   /* [ch_next, ch, 3, 3]   (down 2) */
+    const float* d_conv1_bias;     /* [ch_next] */
+    const float* d_skip_weight;    /* [ch_next, ch, 1, 1]   (down 2, no bias) */
+} la_disc_block_params;
+
+/* StyleGAN2 discriminator description (c_dim = 0, architecture 'resnet', mbstd_num_channels = 1). */
+typedef struct la_disc_desc {
+    int img_resolution, img_channels;
+    int num_blocks;                /* log2(res) - 2 residual blocks: res, res/2, ..., 8 */
+    int channels[LA_MAX_BLOCKS];   /* feature maps at res, res/2, ..., 8, 4  (num_blocks + 1 entries, multiples of 64) */
+    float conv_clamp;              /* < 0: no clamp */
+    int mbstd_group_size;          /* 4 upstream */
+    const float* d_resample_filter;/* [4, 4] (setup_filter([1,3,3,1])) */
+    la_disc_block_params block[LA_MAX_BLOCKS];
+    const float* d_b4_conv_weight; /* [ch4, ch4 + 1, 3, 3] */
+    const float* d_b4_conv_bias;   /* [ch4] */
+    const float* d_b4_fc_weight;   /* [ch4, ch4 * 16] */
+    const float* d_b4_fc_bias;     /* [ch4] */
+    const float* d_b4_out_weight;  /* [1, ch4] */
+    const float* d_b4_out_bias;    /* [1] */
+} la_disc_desc;
 
 const char* la_last_error(void);
 int la_version(void);
+
+/* Discriminator of the realism term.  It runs in bf16 operands / fp32 accumulate in both precisions of the engine.
+ * The workspace is caller-owned like the engine's.  la_disc_logits / la_disc_loss_grad are the stand-alone forms
+ * of what la_augment does every step when w_disc > 0 (tests, criteria plugin). */
+int la_disc_workspace_bytes(const la_disc_desc* d, int batch, size_t* bytes);
+int la_set_discriminator(la_engine* e, const la_disc_desc* d, void* d_workspace, size_t workspace_bytes, la_stream stream);
+/* d_img [batch, img_channels, res, res] fp32 -> d_logits [batch] */
+int la_disc_logits(la_engine* e, const float* d_img, float* d_logits, la_stream stream);
+/* loss = w_disc * mean softplus(-D(img)) -> d_loss [1];  d loss / d img -> d_grad [batch, img_channels, res, res] */
+int la_disc_loss_grad(la_engine* e, const float* d_img, float w_disc, float* d_loss, float* d_grad, la_stream stream);
 
 /* Bytes of device workspace an engine of this shape needs. */
 int la_engine_workspace_bytes(const la_generator_desc* g, int batch, int precision, size_t* bytes);

@@ -38,7 +38,21 @@ class GeneratorDesc(C.Structure):
 
 class AugmentOptions(C.Structure):
     _fields_ = [('num_steps', C.c_int), ('lr', C.c_float), ('w_latent', C.c_float), ('w_pix', C.c_float),
-                ('soft_aug', C.c_int), ('alpha', C.c_float), ('final_noise_mode', C.c_int), ('n_modalities', C.c_int)]
+                ('soft_aug', C.c_int), ('alpha', C.c_float), ('final_noise_mode', C.c_int), ('n_modalities', C.c_int),
+                ('w_disc', C.c_float)]
+
+
+class DiscBlockParams(C.Structure):
+    _fields_ = [('d_fromrgb_weight', fptr), ('d_fromrgb_bias', fptr), ('d_conv0_weight', fptr), ('d_conv0_bias', fptr),
+                ('d_conv1_weight', fptr), ('d_conv1_bias', fptr), ('d_skip_weight', fptr)]
+
+
+class DiscDesc(C.Structure):
+    _fields_ = [('img_resolution', C.c_int), ('img_channels', C.c_int), ('num_blocks', C.c_int),
+                ('channels', C.c_int * LA_MAX_BLOCKS), ('conv_clamp', C.c_float), ('mbstd_group_size', C.c_int),
+                ('d_resample_filter', fptr), ('block', DiscBlockParams * LA_MAX_BLOCKS),
+                ('d_b4_conv_weight', fptr), ('d_b4_conv_bias', fptr), ('d_b4_fc_weight', fptr), ('d_b4_fc_bias', fptr),
+                ('d_b4_out_weight', fptr), ('d_b4_out_bias', fptr)]
 
 
 # name -> (restype, argtypes); every symbol include/latentaugment_b200.h declares
@@ -55,6 +69,10 @@ SIGNATURES = {
     'la_synthesis': (C.c_int, [C.c_void_p, fptr, C.c_longlong, C.c_longlong, C.c_int, fptr, fptr, C.c_void_p]),
     'la_noise_floats': (C.c_size_t, [C.c_void_p]),
     'la_augment': (C.c_int, [C.c_void_p, fptr, C.POINTER(AugmentOptions), fptr, fptr, fptr, fptr, C.c_void_p]),
+    'la_disc_workspace_bytes': (C.c_int, [C.POINTER(DiscDesc), C.c_int, C.POINTER(C.c_size_t)]),
+    'la_set_discriminator': (C.c_int, [C.c_void_p, C.POINTER(DiscDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
+    'la_disc_logits': (C.c_int, [C.c_void_p, fptr, fptr, C.c_void_p]),
+    'la_disc_loss_grad': (C.c_int, [C.c_void_p, fptr, C.c_float, fptr, fptr, C.c_void_p]),
     'la_pairwise_sqdist': (C.c_int, [fptr, C.c_int, fptr, C.c_int, C.c_int, fptr, C.c_void_p]),
     'la_bank_prepare': (C.c_int, [fptr, C.c_int, C.c_int, C.c_void_p, fptr, C.c_void_p]),
     'la_nearest_codes': (C.c_int, [fptr, C.c_int, fptr, C.c_void_p, fptr, C.c_int, C.c_int, C.c_int, C.c_longlong,

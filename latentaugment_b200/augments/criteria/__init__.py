@@ -6,16 +6,16 @@ under ``augments/criteria/<name>/``.  Here each term is a plugin class with the 
 handled by the loop exactly as ``loss = -latent - pix - lpips + disc`` (:270).
 
 Inside the captured CUDA loop the latent and pixel terms run fused (bank-moment form,
-csrc/kernels.cu); the plugin objects configure the engine and evaluate the same quantity
+csrc/kernels.cu) and so does the discriminator term (csrc/disc.cu); the plugin objects configure the engine and evaluate the same quantity
 stand-alone through the pairwise-distance kernel (the reference's ``l2_loss_vectorized``).
 """
+from .disc import DiscriminatorCriterion
 from .latent import LatentCriterion
 from .pix import PixelCriterion
 
-REGISTRY = {'latent': LatentCriterion, 'pix': PixelCriterion}
-# terms whose networks / weights cannot exist offline (SURVEY.md §8c, §8f rank 1-2)
-UNAVAILABLE = {'lpips': 'perceptual term needs the NVIDIA vgg16.pt / LPIPS weights (SURVEY.md §8f rank 2)',
-               'disc': 'discriminator term needs the StyleGAN2 Discriminator (SURVEY.md §8f rank 1)'}
+REGISTRY = {'latent': LatentCriterion, 'pix': PixelCriterion, 'disc': DiscriminatorCriterion}
+# terms whose networks / weights cannot exist offline (SURVEY.md §8c, §8f rank 2)
+UNAVAILABLE = {'lpips': 'perceptual term needs the NVIDIA vgg16.pt / LPIPS weights (SURVEY.md §8f rank 2)'}
 
 
 def find_criterion_using_name(name):

@@ -84,7 +84,7 @@ class LatentAug:
         self.crop_size, self.preprocess = opt.crop_size_aug, opt.preprocess_aug
         self.verbose_flag = bool(getattr(opt, 'verbose_log', False))
         self.precision = getattr(opt, 'precision', 'fp32_parity')
-        self.criteria = create_criteria(opt)           # raises NotImplementedError for lpips / disc weights > 0
+        self.criteria = create_criteria(opt)           # raises NotImplementedError for a positive lpips weight
         self.stats_loss, self.stats_time = {}, {}
         self.module = self
 
@@ -143,6 +143,20 @@ class LatentAug:
             self.X = image_bank.float()
             for e in self.engines:
                 self.criteria['pix'].attach(e, self.X)
+        # ---- discriminator of the realism term (reference: self.D from the same pickle, :117)
+        if self.w_disc > 0:
+            disc_state = None
+            if getattr(opt, 'discriminator_state', ''):
+                disc_state = torch.load(opt.discriminator_state, map_location='cpu', weights_only=True)
+            elif getattr(opt, 'synthetic', False):
+                disc_state = synthetic.random_discriminator_state(
+                    img_resolution=self.res, img_channels=self.img_channels, channel_base=opt.synthetic_channel_base,
+                    channel_max=opt.synthetic_channel_max, seed=5)
+            if disc_state is None:
+                raise FileNotFoundError('w_disc > 0 needs a discriminator: --discriminator_state <state_dict.pt> '
+                                        '(reference names, legacy.py:267-287) or --synthetic')
+            for e in self.engines:
+                self.criteria['disc'].attach(e, disc_state, conv_clamp=conv_clamp)
         # ---- inverted codes (reference: LatentCodeDataset zip, :140-143; latent_aug.py:310-324)
         if inverted_codes is None and getattr(opt, 'inverted_codes', ''):
             blob = torch.load(opt.inverted_codes, map_location='cpu', weights_only=False)
@@ -169,6 +183,10 @@ class LatentAug:
 
     def calc_loss_pix(self, x, x_bank):
         return self.criteria['pix'](x, x_bank)
+
+    def calc_loss_disc(self, x):
+        """:363-371 (x is one engine's batch shard)."""
+        return self.criteria['disc'](x)
 
     def _shards(self, t):
         n = self.batch_size // self.world_size
@@ -197,7 +215,7 @@ class LatentAug:
         imgs, ws_out, self.last_losses = [], [], []
         for e, wsh in zip(self.engines, self._shards(w)):
             out = e.augment(wsh, num_steps=self.num_epochs, lr=self.opt_lr, w_latent=self.w_latent, w_pix=self.w_pix,
-                            soft_aug=self.soft_aug, alpha=self.alpha, final_noise_mode='random',
+                            w_disc=self.w_disc, soft_aug=self.soft_aug, alpha=self.alpha, final_noise_mode='random',
                             return_losses=self.verbose_flag)
             imgs.append(out[0])
             ws_out.append(out[1])
@@ -208,7 +226,7 @@ class LatentAug:
         if self.verbose_flag:
             for rank, ll in enumerate(self.last_losses):
                 for t, row in enumerate(ll.cpu().tolist()):
-                    print(f'[rank {rank}] epoch {t}: loss_latent {row[0]:.6f} loss_pix {row[1]:.6f} loss {row[2]:.6f}')
+                    print(f'[rank {rank}] epoch {t}: loss_latent {row[0]:.6f} loss_pix {row[1]:.6f} loss_disc {row[3]:.6f} loss {row[2]:.6f}')
         return img, self.broadcasting(w_aug.unsqueeze(1))
 
     __call__ = forward

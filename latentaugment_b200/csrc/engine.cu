@@ -13,6 +13,8 @@
 #include "../../include/latentaugment_b200.h"
 #include "kernels.cuh"
 #include "tapgemm.cuh"
+#include "plan.cuh"
+#include "disc.cuh"
 
 using namespace la;
 
@@ -105,7 +107,9 @@ struct la_engine {
     cudaGraphExec_t step_graph = nullptr; bool warmed = false; bool graph_disabled = false;
     int use_simt = 0;
     long long launches = 0, launches_captured = 0, graph_kernels = 0;   // kernel launches (graph replays count their kernels)
-    float cur_w_pix = -1.f;
+    float cur_w_pix = -1.f, cur_w_disc = -1.f;
+    la_disc* disc = nullptr;          // realism-term discriminator (optional)
+    float* disc_loss = nullptr;
 };
 
 namespace {
@@ -115,85 +119,6 @@ namespace {
 int upconv_split_min_res() {
     const char* v = getenv("LA_UPCONV_SPLIT_MIN_RES");
     return v ? atoi(v) : 8;
-}
-
-// M tile of a grid of resolution g: 16 rows x 8 pixels with a 2-row halo (the three vertical taps share
-// one TMA box) from 16^2 up; whole small images below that.
-void tile_geometry(int g, int& th, int& tw, int& nb, int& halo) {
-    if (g >= 16) { th = 16; tw = 8; nb = 1; halo = 2; }
-    else if (g == 8) { th = 8; tw = 8; nb = 2; halo = 0; }
-    else { th = g; tw = g; nb = 128 / (g * g); halo = 0; }
-}
-long long grid_m_tiles(int g, int batch) {
-    int th, tw, nb, halo;
-    tile_geometry(g, th, tw, nb, halo);
-    return static_cast<long long>((batch + nb - 1) / nb) * ((g + th - 1) / th) * ((g + tw - 1) / tw);
-}
-// Column block: 256 where the channel count allows (N = 256 MMAs run at the full tensor rate, N = 128 ones at
-// about 80 % of it), 128 with two M tiles sharing each weight tile otherwise, 64 when the layer has 64 channels
-// or the grid is too small to occupy the SMs with wider blocks.
-int pick_bn(int n, long long m_tiles = 1 << 30) {
-    if (n % 64) return 0;
-    if (n == 64) return 64;
-    if (n % 128) return 0;
-    static const int force = getenv("LA_BN") ? atoi(getenv("LA_BN")) : 0;      // tuning switch
-    if (force && n % force == 0) return force;
-    if (m_tiles * (n / 128) <= 74) return 64;
-    return n % 256 == 0 ? 256 : 128;
-}
-
-int make_a_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, long long sW, long long sH, long long sN, int tw, int th,
-               int nb) {
-    uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(N)};
-    uint64_t strides[3] = {static_cast<uint64_t>(sW) * 2, static_cast<uint64_t>(sH) * 2, static_cast<uint64_t>(sN) * 2};
-    uint32_t box[4] = {64, static_cast<uint32_t>(tw), static_cast<uint32_t>(th), static_cast<uint32_t>(nb)};
-    return encode_tmap_bf16(m, base, 4, dims, strides, box);
-}
-int make_b_map(CUtensorMap* m, const void* base, int K, int rows, int nmat, int bn) {
-    uint64_t dims[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(rows), static_cast<uint64_t>(nmat)};
-    uint64_t strides[2] = {static_cast<uint64_t>(K) * 2, static_cast<uint64_t>(K) * rows * 2};
-    uint32_t box[3] = {64, static_cast<uint32_t>(bn), 1};
-    return encode_tmap_bf16(m, base, 3, dims, strides, box);
-}
-
-void set_ops_dims(TapSimtOperands& o, int w, int h) {
-    for (int i = 0; i < kMaxAMaps; ++i) { o.a_ws[i] = w; o.a_hs[i] = h; }
-}
-
-void add_tap(TapGemmParams& P, int& nt, int dy, int dx, int widx, int src_hi, int src_lo, int nmat, int split) {
-    P.taps[nt++] = Tap{static_cast<int8_t>(dy), static_cast<int8_t>(dx), static_cast<uint8_t>(widx), static_cast<uint8_t>(src_hi)};
-    if (split) {
-        P.taps[nt++] = Tap{static_cast<int8_t>(dy), static_cast<int8_t>(dx), static_cast<uint8_t>(widx), static_cast<uint8_t>(src_lo)};
-        P.taps[nt++] = Tap{static_cast<int8_t>(dy), static_cast<int8_t>(dx), static_cast<uint8_t>(nmat + widx), static_cast<uint8_t>(src_hi)};
-    }
-}
-
-// Tile box from the grid resolution g; problem i covers a gh[i] x gw[i] grid (all = g unless given).
-void set_grid(TapGemmParams& P, int g, int batch, int nprob, const int* gh = nullptr, const int* gw = nullptr) {
-    tile_geometry(g, P.th, P.tw, P.nb, P.halo);
-    P.tiles_n = (batch + P.nb - 1) / P.nb;
-    P.batch = batch;
-    P.nprob = nprob;
-    P.m_tiles = 0;
-    for (int i = 0; i < nprob; ++i) {
-        TapProblem& pr = P.prob[i];
-        pr.vh = gh ? gh[i] : g;
-        pr.vw = gw ? gw[i] : g;
-        pr.tiles_h = (pr.vh + P.th - 1) / P.th;
-        pr.tiles_w = (pr.vw + P.tw - 1) / P.tw;
-        pr.tile_begin = P.m_tiles;
-        P.m_tiles += P.tiles_n * pr.tiles_h * pr.tiles_w;
-    }
-}
-
-// Interleaved walk of a multi-problem launch: one common tile grid (the largest), problems masked by vh / vw.
-void set_interleaved(TapGemmParams& P) {
-    int th = 0, tw = 0;
-    for (int i = 0; i < P.nprob; ++i) { th = P.prob[i].tiles_h > th ? P.prob[i].tiles_h : th; tw = P.prob[i].tiles_w > tw ? P.prob[i].tiles_w : tw; }
-    for (int i = 0; i < P.nprob; ++i) { P.prob[i].tiles_h = th; P.prob[i].tiles_w = tw; P.prob[i].tile_begin = 0; }
-    const int spatial = P.tiles_n * th * tw;
-    P.m_tiles = 2 * P.nprob * ((spatial + 1) / 2);
-    P.interleave = 1;
 }
 
 // Plans layers and carves the workspace.  With ws == nullptr only sizes are computed.
@@ -306,6 +231,7 @@ int plan(la_engine* e, char* ws, size_t* bytes_out) {
     e->consts = bp.take<AdamConsts>(1);
     e->step = bp.take<int>(1);
     e->err_flag = bp.take<int>(1);
+    e->disc_loss = bp.take<float>(1);
     e->dbg_clock = bp.take<unsigned long long>(2);
     const size_t wn = static_cast<size_t>(B) * g.w_dim;
     e->w_opt = bp.take<float>(wn); e->m = bp.take<float>(wn); e->v = bp.take<float>(wn);
@@ -632,15 +558,23 @@ int run_forward(la_engine* e, const float* ws, long long sn, long long si, int n
     return 0;
 }
 
-int run_backward(la_engine* e, const la_augment_options& /*opt*/, cudaStream_t s) {
+int run_backward(la_engine* e, const la_augment_options& opt, cudaStream_t s) {
     const la_generator_desc& g = e->g;
     const int B = e->batch;
     const int L = static_cast<int>(e->conv.size());
     Rgb& top = e->rgb.back();
     int nparts = 0;
-    LA(pix_loss(top.img, e->bank_mean, e->bank_m2, B, g.img_resolution, g.img_channels, e->crop_off, e->crop_size, e->cur_w_pix,
-                top.g_img, e->loss_parts, &nparts, s));
+    if (opt.w_pix > 0.f) {
+        LA(pix_loss(top.img, e->bank_mean, e->bank_m2, B, g.img_resolution, g.img_channels, e->crop_off, e->crop_size, e->cur_w_pix,
+                    top.g_img, e->loss_parts, &nparts, s));
+    } else {
+        CU(cudaMemsetAsync(top.g_img, 0, sizeof(float4) * static_cast<size_t>(B) * g.img_resolution * g.img_resolution, s));
+    }
     e->n_loss_parts = nparts;
+    if (opt.w_disc > 0.f) {          // realism term (util_latent_aug.py:363-371): + w_disc * mean softplus(-D(x))
+        if (disc_forward(e->disc, top.img, s, &e->launches) || disc_backward(e->disc, opt.w_disc, top.g_img, 1, e->disc_loss, s, &e->launches))
+            return fail(-6, "discriminator: %s", disc_last_error());
+    }
     for (int b = g.num_blocks - 1; b >= 0; --b) {
         Rgb& r = e->rgb[b];
         LA(rgb_backward(r.g_img, r.parts, r.nparts, r.p.d_bias, g.img_channels, g.conv_clamp, B, r.res, r.g_rgb,
@@ -661,14 +595,15 @@ int run_backward(la_engine* e, const la_augment_options& /*opt*/, cudaStream_t s
 int run_step(la_engine* e, const la_augment_options& opt, cudaStream_t s) {
     const la_generator_desc& g = e->g;
     const int B = e->batch;
-    const bool synth = opt.w_pix > 0.f;
+    const bool synth = opt.w_pix > 0.f || opt.w_disc > 0.f;
     if (synth) {
         CU(cudaMemsetAsync(e->red_all, 0, e->red_bytes, s));
         LA(run_forward(e, e->w_opt, g.w_dim, 0, LA_NOISE_CONST, nullptr, nullptr, s));
         LA(run_backward(e, opt, s));
     }
     LA(adam_step(e->partial, e->nchunks, synth ? 1 : 0, e->w_sum, e->lat_m2, e->consts, e->step, e->w_opt, e->m, e->v, B, g.w_dim,
-                 e->loss_parts, synth ? e->n_loss_parts : 0, e->bank_m2, opt.n_modalities, e->crop_size, e->loss_log, LA_MAX_STEPS, s));
+                 e->loss_parts, synth ? e->n_loss_parts : 0, e->bank_m2, opt.n_modalities, e->crop_size, e->loss_log, LA_MAX_STEPS,
+                 opt.w_disc > 0.f ? e->disc_loss : nullptr, s));
     e->launches += 3;
     return 0;
 }
@@ -740,6 +675,7 @@ LA_API int la_engine_create(const la_generator_desc* g, int batch, int precision
 
 LA_API void la_engine_destroy(la_engine* e) {
     if (!e) return;
+    if (e->disc) disc_destroy(e->disc);
     if (e->step_graph) cudaGraphExecDestroy(e->step_graph);
     if (e->ev_in) cudaEventDestroy(e->ev_in);
     if (e->ev_out) cudaEventDestroy(e->ev_out);
@@ -818,6 +754,7 @@ LA_API int la_augment(la_engine* e, const float* d_w0, const la_augment_options*
     if (opt->w_latent > 0.f && !e->has_lat_bank) return fail(-2, "w_latent > 0 needs la_set_latent_bank");
     if (opt->final_noise_mode == LA_NOISE_RANDOM && !d_final_noise) return fail(-2, "final_noise_mode random needs d_final_noise");
     if (opt->n_modalities != e->g.img_channels) return fail(-2, "n_modalities must equal img_channels");
+    if (opt->w_disc > 0.f && !e->disc) return fail(-2, "w_disc > 0 needs la_set_discriminator");
     const la_generator_desc& g = e->g;
     const int B = e->batch;
     const size_t wbytes = sizeof(float) * B * g.w_dim;
@@ -832,13 +769,14 @@ LA_API int la_augment(la_engine* e, const float* d_w0, const la_augment_options*
     CU(cudaMemsetAsync(e->v, 0, wbytes, w));
     CU(cudaMemsetAsync(e->step, 0, sizeof(int), w));
     CU(cudaMemsetAsync(e->loss_log, 0, sizeof(float) * 4 * LA_MAX_STEPS, w));
-    if (e->cur_w_pix != opt->w_pix && e->step_graph) {       // w_pix is baked into the pixel-criterion launch
+    if ((e->cur_w_pix != opt->w_pix || e->cur_w_disc != opt->w_disc) && e->step_graph) {   // baked into the criterion launches
         cudaGraphExecDestroy(e->step_graph);
         e->step_graph = nullptr;
     }
     e->cur_w_pix = opt->w_pix;
+    e->cur_w_disc = opt->w_disc;
     for (int it = 0; it < opt->num_steps; ++it) {
-        const bool synth = opt->w_pix > 0.f;
+        const bool synth = opt->w_pix > 0.f || opt->w_disc > 0.f;
         if (!synth || e->graph_disabled || !e->warmed) {
             LA(run_step(e, *opt, w));
             e->warmed = true;
@@ -867,6 +805,50 @@ LA_API int la_augment(la_engine* e, const float* d_w0, const la_augment_options*
     CU(cudaMemcpyAsync(d_w_aug, e->w_aug, wbytes, cudaMemcpyDeviceToDevice, w));
     if (d_loss_log && opt->num_steps > 0)
         CU(cudaMemcpyAsync(d_loss_log, e->loss_log, sizeof(float) * 4 * opt->num_steps, cudaMemcpyDeviceToDevice, w));
+    LA(bridge_out(e, s));
+    return 0;
+}
+
+LA_API int la_disc_workspace_bytes(const la_disc_desc* d, int batch, size_t* bytes) {
+    if (!d || !bytes || batch < 1) return fail(-2, "bad arguments");
+    if (disc_workspace_bytes(*d, batch, bytes)) return fail(-2, "%s", disc_last_error());
+    return 0;
+}
+
+LA_API int la_set_discriminator(la_engine* e, const la_disc_desc* d, void* d_workspace, size_t workspace_bytes, la_stream stream) {
+    if (!e || !d || !d_workspace) return fail(-2, "bad arguments");
+    if (d->img_resolution != e->g.img_resolution || d->img_channels != e->g.img_channels)
+        return fail(-2, "discriminator shape %dx%d (%d ch) does not match the generator", d->img_resolution, d->img_resolution, d->img_channels);
+    if (e->disc) { disc_destroy(e->disc); e->disc = nullptr; }
+    if (e->step_graph) { cudaGraphExecDestroy(e->step_graph); e->step_graph = nullptr; }
+    if (disc_create(*d, e->batch, e->num_sms, d_workspace, workspace_bytes, static_cast<cudaStream_t>(stream), &e->disc))
+        return fail(-6, "discriminator: %s", disc_last_error());
+    return 0;
+}
+
+LA_API int la_disc_logits(la_engine* e, const float* d_img, float* d_logits, la_stream stream) {
+    if (!e || !e->disc || !d_img || !d_logits) return fail(-2, "bad arguments (la_set_discriminator first)");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    Rgb& top = e->rgb.back();
+    LA(bridge_in(e, s));
+    LA(nchw_to_f4(d_img, e->batch, e->g.img_channels, e->g.img_resolution, top.img, e->work));
+    if (disc_forward(e->disc, top.img, e->work, &e->launches)) return fail(-6, "discriminator: %s", disc_last_error());
+    CU(cudaMemcpyAsync(d_logits, disc_logits(e->disc), sizeof(float) * e->batch, cudaMemcpyDeviceToDevice, e->work));
+    LA(bridge_out(e, s));
+    return 0;
+}
+
+LA_API int la_disc_loss_grad(la_engine* e, const float* d_img, float w_disc, float* d_loss, float* d_grad, la_stream stream) {
+    if (!e || !e->disc || !d_img || !d_loss || !d_grad) return fail(-2, "bad arguments (la_set_discriminator first)");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    Rgb& top = e->rgb.back();
+    LA(bridge_in(e, s));
+    LA(nchw_to_f4(d_img, e->batch, e->g.img_channels, e->g.img_resolution, top.img, e->work));
+    if (disc_forward(e->disc, top.img, e->work, &e->launches) ||
+        disc_backward(e->disc, w_disc, top.g_img, 0, e->disc_loss, e->work, &e->launches))
+        return fail(-6, "discriminator: %s", disc_last_error());
+    LA(f4_to_nchw(top.g_img, e->batch, e->g.img_channels, e->g.img_resolution, d_grad, e->work));
+    CU(cudaMemcpyAsync(d_loss, e->disc_loss, sizeof(float), cudaMemcpyDeviceToDevice, e->work));
     LA(bridge_out(e, s));
     return 0;
 }

@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(256, SEP ? 3 : 2) upfir_slide_kernel(const __g
 
     float2 dm = make_float2(0.f, 0.f), bs = dm, sn = dm;
     const float* nrow = nullptr;
-    if (FWD) {
+    if (FWD && !P.act_saved) {
         const int c = 2 * cp;
         dm = __ldg(reinterpret_cast<const float2*>(P.demod + static_cast<long long>(n) * P.C + c));
         bs = __ldg(reinterpret_cast<const float2*>(P.bias + c));
@@ -316,7 +316,15 @@ __global__ void __launch_bounds__(256, SEP ? 3 : 2) upfir_slide_kernel(const __g
                     }
             }
             const long long o = obase + static_cast<long long>(x) * hc;
-            if (FWD) {
+            if (FWD && P.act_saved) {
+                const unsigned sv = __ldg(reinterpret_cast<const unsigned*>(P.act_saved) + o);
+                const float s0 = __uint_as_float(sv << 16), s1 = __uint_as_float(sv & 0xffff0000u);
+                const float cl = P.act_clamp >= 0.f ? P.act_clamp : __int_as_float(0x7f800000);
+                float g0 = a0 * P.act_gain * (s0 > 0.f ? 1.f : P.act_slope), g1 = a1 * P.act_gain * (s1 > 0.f ? 1.f : P.act_slope);
+                g0 = fabsf(s0) < cl ? g0 : 0.f;
+                g1 = fabsf(s1) < cl ? g1 : 0.f;
+                st_bf16x2(oh, ol, o, g0, g1);
+            } else if (FWD) {
                 float z0 = fmaf(a0, dm.x, nzv[u]) + bs.x, z1 = fmaf(a1, dm.y, nzv[u]) + bs.y;
                 z0 = (z0 > 0.f ? z0 : z0 * P.act_slope) * P.act_gain;
                 z1 = (z1 > 0.f ? z1 : z1 * P.act_slope) * P.act_gain;
@@ -383,7 +391,7 @@ __global__ void __launch_bounds__(160) upfir_tma_kernel(const __grid_constant__ 
     for (int k = 0; k < 4; ++k) { wy[k] = FWD ? P.fy[k] : P.fy[3 - k]; wx[k] = FWD ? P.fx[k] : P.fx[3 - k]; }
     float2 dm = make_float2(0.f, 0.f), bs = dm, sn = dm;
     const int c = c0 + 2 * lane;
-    if (FWD) {
+    if (FWD && !P.act_saved) {
         dm = __ldg(reinterpret_cast<const float2*>(P.demod + static_cast<long long>(n) * P.C + c));
         bs = __ldg(reinterpret_cast<const float2*>(P.bias + c));
         if (P.s_next) sn = __ldg(reinterpret_cast<const float2*>(P.s_next + static_cast<long long>(n) * P.C + c));
@@ -412,7 +420,17 @@ __global__ void __launch_bounds__(160) upfir_tma_kernel(const __grid_constant__ 
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[j0 % kFirRing]);       // the oldest row of the window is done
         float nzv[8];
-        if (FWD && P.noise) {
+        unsigned svv[8];
+        if (FWD && P.act_saved) {
+            const unsigned* sp = reinterpret_cast<const unsigned*>(P.act_saved) +
+                                 ((static_cast<long long>(n) * P.OH + r) * P.OW) * (P.C >> 1) + (c0 >> 1) + lane;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int x = x0 + px0 + i;
+                svv[i] = x < P.OW ? __ldg(sp + static_cast<long long>(x) * (P.C >> 1)) : 0u;
+            }
+        }
+        if (FWD && P.noise && !P.act_saved) {
             const float4* np = reinterpret_cast<const float4*>(P.noise + n * P.noise_stride_n + static_cast<long long>(r) * P.OW + x0 + px0);
             const bool in = x0 + px0 + 8 <= P.OW;
             const float4 a = in ? __ldg(np) : make_float4(0.f, 0.f, 0.f, 0.f), b = in ? __ldg(np + 1) : a;
@@ -431,7 +449,13 @@ __global__ void __launch_bounds__(160) upfir_tma_kernel(const __grid_constant__ 
             float a0 = 0.f, a1 = 0.f;
 #pragma unroll
             for (int k = 0; k < 4; ++k) { a0 = fmaf(wx[k], cs[i + k].x, a0); a1 = fmaf(wx[k], cs[i + k].y, a1); }
-            if (FWD) {
+            if (FWD && P.act_saved) {
+                const float s0 = __uint_as_float(svv[i] << 16), s1 = __uint_as_float(svv[i] & 0xffff0000u);
+                float g0 = a0 * P.act_gain * (s0 > 0.f ? 1.f : P.act_slope), g1 = a1 * P.act_gain * (s1 > 0.f ? 1.f : P.act_slope);
+                g0 = fabsf(s0) < clampv ? g0 : 0.f;
+                g1 = fabsf(s1) < clampv ? g1 : 0.f;
+                reinterpret_cast<unsigned*>(sx)[i * 32 + lane] = pack2(g0, g1);
+            } else if (FWD) {
                 float z0 = fmaf(a0, dm.x, nzv[i]) + bs.x, z1 = fmaf(a1, dm.y, nzv[i]) + bs.y;
                 z0 = (z0 > 0.f ? z0 : z0 * P.act_slope) * P.act_gain;
                 z1 = (z1 > 0.f ? z1 : z1 * P.act_slope) * P.act_gain;
@@ -448,7 +472,7 @@ __global__ void __launch_bounds__(160) upfir_tma_kernel(const __grid_constant__ 
         if (lane == 0) {
             if (FWD) {
                 tma_store_4d(&P.fwd_out_x, sx, c0, x0 + px0, r, n);
-                if (P.s_next) tma_store_4d(&P.fwd_out_xs, sx + 1024, c0, x0 + px0, r, n);
+                if (P.s_next && !P.act_saved) tma_store_4d(&P.fwd_out_xs, sx + 1024, c0, x0 + px0, r, n);
             } else {
                 tma_store_4d(&P.bwd_out, sx, c0, x0 + px0, r, n);
             }
@@ -690,7 +714,7 @@ __global__ void gw_partial_kernel(const float* __restrict__ g_s, const float* __
 __global__ void loss_value_kernel(const float* __restrict__ w, const float* __restrict__ w_sum_bank, const float* __restrict__ lat_m2, const AdamConsts* C,
                                   const int* step_counter, int batch, int w_dim, const float* __restrict__ pix_parts,
                                   int n_pix_parts, const float* __restrict__ bank_m2, int img_c, int crop_size, float* loss_log,
-                                  int max_steps) {
+                                  int max_steps, const float* __restrict__ disc_loss) {
     double sq = 0.0, dot = 0.0, px = 0.0;
     for (int e = threadIdx.x; e < batch * w_dim; e += blockDim.x) {
         const double v = w[e];
@@ -718,8 +742,9 @@ __global__ void loss_value_kernel(const float* __restrict__ w, const float* __re
             }
             loss_log[4 * t + 0] = static_cast<float>(l_lat);
             loss_log[4 * t + 1] = static_cast<float>(l_pix);
-            loss_log[4 * t + 2] = static_cast<float>(-l_lat - l_pix);
-            loss_log[4 * t + 3] = 0.f;
+            const double l_disc = disc_loss ? disc_loss[0] : 0.0;
+            loss_log[4 * t + 2] = static_cast<float>(-l_lat - l_pix + l_disc);      // util_latent_aug.py:270
+            loss_log[4 * t + 3] = static_cast<float>(l_disc);
         }
     }
 }
@@ -1015,9 +1040,9 @@ int gw_partial(const float* g_s, const float* a_cat, const int* chunk_soff, cons
 }
 int adam_step(const float* partial, int nchunks, int use_partial, const float* w_sum_bank, const float* lat_m2, const AdamConsts* consts, int* step_counter,
               float* w, float* m, float* v, int batch, int w_dim, const float* pix_parts, int n_pix_parts, const float* bank_m2,
-              int img_c, int crop_size, float* loss_log, int max_steps, cudaStream_t s) {
+              int img_c, int crop_size, float* loss_log, int max_steps, const float* disc_loss, cudaStream_t s) {
     loss_value_kernel<<<1, 512, 0, s>>>(w, w_sum_bank, lat_m2, consts, step_counter, batch, w_dim, pix_parts, n_pix_parts, bank_m2, img_c,
-                                        crop_size, loss_log, max_steps);
+                                        crop_size, loss_log, max_steps, disc_loss);
     adam_kernel<<<cdiv(batch * w_dim, 256), 256, 0, s>>>(partial, nchunks, use_partial, w_sum_bank, consts, step_counter, w, m, v, batch, w_dim);
     step_inc_kernel<<<1, 1, 0, s>>>(step_counter);
     return last_err();

@@ -52,6 +52,9 @@ struct UpFirParams {
     const float* s_next;
     void* x_hi; void* x_lo; void* xs_hi; void* xs_lo;
     float act_gain, act_clamp, act_slope;
+    // forward, activation-backward variant (discriminator: gradient through blur + lrelu): when act_saved is set the
+    // epilogue is  y = FIR(T) * act_gain * (saved > 0 ? 1 : act_slope) * (|saved| < act_clamp)  -> x_hi
+    const void* act_saved;                   // bf16 [B, OH, OW, C] saved activation output, or null
     // backward: g_y [B, OH, OW, C] -> g_T
     const void* gy_hi; const void* gy_lo;
     void* gt_hi; void* gt_lo;
@@ -88,7 +91,7 @@ struct AdamConsts {      // device-resident so one captured graph serves every o
 };
 int adam_step(const float* partial, int nchunks, int use_partial, const float* w_sum_bank, const float* lat_m2, const AdamConsts* consts, int* step_counter,
               float* w, float* m, float* v, int batch, int w_dim, const float* pix_parts, int n_pix_parts, const float* bank_m2,
-              int img_c, int crop_size, float* loss_log, int max_steps, cudaStream_t s);
+              int img_c, int crop_size, float* loss_log, int max_steps, const float* disc_loss /*or null*/, cudaStream_t s);
 int finalize_w(const float* w_opt, const float* w0, float alpha, int soft, int batch, int w_dim, float* w_aug, cudaStream_t s);
 
 // ---- banks

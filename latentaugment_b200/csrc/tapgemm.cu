@@ -189,6 +189,18 @@ __device__ __forceinline__ void store_bf16x32(void* hi, void* lo, long long off,
     }
 }
 
+__device__ __forceinline__ void load_bf16x32(const void* p, long long off, float (&v)[32]) {
+    const uint4* s = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p) + off);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint4 a = __ldg(s + j);
+        v[8 * j + 0] = bf16lo_f(a.x); v[8 * j + 1] = bf16hi_f(a.x);
+        v[8 * j + 2] = bf16lo_f(a.y); v[8 * j + 3] = bf16hi_f(a.y);
+        v[8 * j + 4] = bf16lo_f(a.z); v[8 * j + 5] = bf16hi_f(a.z);
+        v[8 * j + 6] = bf16lo_f(a.w); v[8 * j + 7] = bf16hi_f(a.w);
+    }
+}
+
 __device__ __forceinline__ void load_f32x32(const float* p, float (&v)[32]) {
     const float4* s = reinterpret_cast<const float4*>(p);
 #pragma unroll
@@ -306,6 +318,25 @@ __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const
                 flush_stage(stg, P.x_hi, col0);
             } else if (rc.valid) {
                 store_bf16x32(P.x_hi, P.split ? P.x_lo : nullptr, eoff, acc);
+            }
+        } else if constexpr (EPI == kEpiLinear) {
+            if (rc.valid) {
+                float t[32];
+                if (P.lin_add) {
+                    load_bf16x32(P.lin_add, eoff, t);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[j] += t[j];
+                }
+                if (P.lin_out) store_bf16x32(P.lin_out, nullptr, eoff, acc);
+                if (P.lin_gz) {
+                    load_bf16x32(P.lin_saved, eoff, t);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float g = acc[j] * P.act_gain * (t[j] > 0.f ? 1.f : P.act_slope);
+                        acc[j] = fabsf(t[j]) < clampv ? g : 0.f;
+                    }
+                    store_bf16x32(P.lin_gz, nullptr, eoff, acc);
+                }
             }
         } else if constexpr (EPI == kEpiTopK) {
             if (tk_valid) {
@@ -1230,6 +1261,7 @@ int launch_bn(const TapGemmParams& p, int num_sms, cudaStream_t stream) {
         case kEpiBwd: return launch_bn_epi<BN, kEpiBwd>(p, num_sms, stream);
         case kEpiTopK: return launch_bn_epi<BN, kEpiTopK>(p, num_sms, stream);
         case kEpiStoreBf16: return launch_bn_epi<BN, kEpiStoreBf16>(p, num_sms, stream);
+        case kEpiLinear: return launch_bn_epi<BN, kEpiLinear>(p, num_sms, stream);
         default: return static_cast<int>(cudaErrorInvalidValue);
     }
 }
@@ -1251,6 +1283,7 @@ int launch_simt_bn(const TapGemmParams& p, const TapSimtOperands& ops, cudaStrea
         case kEpiBwd: return launch_simt_bn_epi<BN, kEpiBwd>(p, ops, stream);
         case kEpiTopK: return launch_simt_bn_epi<BN, kEpiTopK>(p, ops, stream);
         case kEpiStoreBf16: return launch_simt_bn_epi<BN, kEpiStoreBf16>(p, ops, stream);
+        case kEpiLinear: return launch_simt_bn_epi<BN, kEpiLinear>(p, ops, stream);
         default: return static_cast<int>(cudaErrorInvalidValue);
     }
 }

@@ -55,6 +55,8 @@ enum TapEpilogue : int {
     kEpiBwd = 2,       // style-gradient reductions + activation backward of the producer layer -> g_y
     kEpiTopK = 3,      // rows = queries, columns = bank codes: per-tile k smallest |y|^2 - 2<x,y> per row
     kEpiStoreBf16 = 4, // store accumulators as bf16 (hi [+ lo]) into x_hi / x_lo [pixel][n_total]
+    kEpiLinear = 5,    // plain (unmodulated) layers of the discriminator: r = acc (+ lin_add) -> lin_out;
+                       // r * act'(lin_saved) -> lin_gz   (bf16 [pixel][n_total] tensors, each optional)
 };
 
 struct TapGemmParams {
@@ -117,6 +119,12 @@ struct TapGemmParams {
     float* red_d;                      // [batch, N]      += sum_px g_z * (z - noise - bias)
     float* red_rgb;                    // [3][batch, N]   += sum_px x_{l-1} * g_rgb[c]
     int bwd_last;                      // 1: x_{l-1} is the constant input: only red_s is produced
+
+    // ---- kEpiLinear
+    const void* lin_add;               // bf16 addend (residual branch / second gradient path) or null
+    void* lin_out;                     // bf16 r or null
+    const void* lin_saved;             // bf16 saved activation output deciding the activation gradient, or null
+    void* lin_gz;                      // bf16 r * act_gain * (saved > 0 ? 1 : act_slope) * (|saved| < act_clamp), or null
 
     // ---- kEpiTopK: acc[query, code] = <x, y>
     const float* code_sqnorm;          // [n_codes] |y_j|^2

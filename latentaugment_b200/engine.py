@@ -133,6 +133,72 @@ class SynthesisEngine:
             _lib.check(self.lib.la_set_image_bank(self.handle, _ptr(X), X.shape[0], _stream_ptr(self.device)))
         torch.cuda.current_stream(self.device).synchronize()
 
+    # ---- discriminator of the realism term (reference self.D, util_latent_aug.py:117,363-371)
+    def set_discriminator(self, state, channels=None, conv_clamp=256.0, mbstd_group_size=4):
+        """``state``: mapping with the reference parameter names of the StyleGAN2 'resnet' discriminator
+        (``b{res}.{fromrgb,conv0,conv1,skip}.{weight,bias}``, ``b4.{conv,fc,out}.{weight,bias}``,
+        ``b{res}.conv1.resample_filter``; models/stylegan3/legacy.py:267-287)."""
+        state = generator_state(state)
+        res = self.img_resolution
+        blocks = []
+        r = res
+        while r > 4:
+            blocks.append(r)
+            r //= 2
+        keep = self._disc_keep = []
+
+        def dev(name):
+            t = state[name].detach().to(self.device, torch.float32).contiguous()
+            keep.append(t)
+            return t
+        d = _lib.DiscDesc()
+        d.img_resolution, d.img_channels, d.num_blocks = res, self.img_channels, len(blocks)
+        d.conv_clamp = -1.0 if conv_clamp is None else float(conv_clamp)
+        d.mbstd_group_size = int(mbstd_group_size)
+        for i, r in enumerate(blocks):
+            d.channels[i] = state[f'b{r}.conv0.weight'].shape[0]
+            b = d.block[i]
+            if i == 0:
+                b.d_fromrgb_weight = _ptr(dev(f'b{r}.fromrgb.weight'))
+                b.d_fromrgb_bias = _ptr(dev(f'b{r}.fromrgb.bias'))
+            b.d_conv0_weight, b.d_conv0_bias = _ptr(dev(f'b{r}.conv0.weight')), _ptr(dev(f'b{r}.conv0.bias'))
+            b.d_conv1_weight, b.d_conv1_bias = _ptr(dev(f'b{r}.conv1.weight')), _ptr(dev(f'b{r}.conv1.bias'))
+            b.d_skip_weight = _ptr(dev(f'b{r}.skip.weight'))
+        d.channels[len(blocks)] = state['b4.fc.weight'].shape[0]
+        fname = f'b{blocks[0]}.conv1.resample_filter'
+        filt = state[fname] if fname in state else torch.outer(torch.tensor([1., 3., 3., 1.]), torch.tensor([1., 3., 3., 1.])) / 64
+        keep.append(filt.detach().to(self.device, torch.float32).contiguous())
+        d.d_resample_filter = _ptr(keep[-1])
+        d.d_b4_conv_weight, d.d_b4_conv_bias = _ptr(dev('b4.conv.weight')), _ptr(dev('b4.conv.bias'))
+        d.d_b4_fc_weight, d.d_b4_fc_bias = _ptr(dev('b4.fc.weight')), _ptr(dev('b4.fc.bias'))
+        d.d_b4_out_weight, d.d_b4_out_bias = _ptr(dev('b4.out.weight')), _ptr(dev('b4.out.bias'))
+        nbytes = C.c_size_t(0)
+        _lib.check(self.lib.la_disc_workspace_bytes(C.byref(d), self.batch, C.byref(nbytes)))
+        self.disc_workspace = torch.empty(nbytes.value + 1024, dtype=torch.uint8, device=self.device)
+        base = (self.disc_workspace.data_ptr() + 1023) // 1024 * 1024
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.la_set_discriminator(self.handle, C.byref(d), C.c_void_p(base), nbytes.value, _stream_ptr(self.device)))
+        torch.cuda.current_stream(self.device).synchronize()
+        self.has_disc = True
+
+    def disc_logits(self, img):
+        """reference ``self.D(x, c=None)``: img [batch, C, res, res] -> logits [batch, 1]."""
+        img = img.detach().to(self.device, torch.float32).contiguous()
+        assert img.shape == (self.batch, self.img_channels, self.img_resolution, self.img_resolution), img.shape
+        out = torch.empty([self.batch], device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.la_disc_logits(self.handle, _ptr(img), _ptr(out), _stream_ptr(self.device)))
+        return out.unsqueeze(1)
+
+    def disc_loss_grad(self, img, w_disc=1.0):
+        """(w_disc * softplus(-D(img)).mean(), its gradient wrt img) -- reference calc_loss_disc + autograd."""
+        img = img.detach().to(self.device, torch.float32).contiguous()
+        loss = torch.empty([1], device=self.device)
+        grad = torch.empty_like(img)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.la_disc_loss_grad(self.handle, _ptr(img), float(w_disc), _ptr(loss), _ptr(grad), _stream_ptr(self.device)))
+        return loss[0], grad
+
     # ---- network
     def mapping(self, z, truncation_psi=1.0):
         """[n, z_dim] -> [n, num_ws, w_dim] (broadcast rows), reference G.mapping(z, None, truncation_psi)."""
@@ -168,7 +234,7 @@ class SynthesisEngine:
                                              _lib.NOISE[noise_mode], _ptr(nz), _ptr(img), _stream_ptr(self.device)))
         return img
 
-    def augment(self, w0, *, num_steps=10, lr=0.01, w_latent=1.0, w_pix=1.0, soft_aug=False, alpha=1.0,
+    def augment(self, w0, *, num_steps=10, lr=0.01, w_latent=1.0, w_pix=1.0, w_disc=0.0, soft_aug=False, alpha=1.0,
                 final_noise_mode='random', final_noise=None, return_losses=False):
         """The hot path (reference LatentAug.forward).  w0 [batch, w_dim] or [batch, 1, w_dim]."""
         w0 = w0.detach().to(self.device, torch.float32).reshape(self.batch, self.w_dim).contiguous()
@@ -177,7 +243,7 @@ class SynthesisEngine:
         w_aug = torch.empty([self.batch, self.w_dim], device=self.device)
         losses = torch.zeros([max(num_steps, 1), 4], device=self.device) if return_losses else None
         opt = _lib.AugmentOptions(num_steps, lr, w_latent, w_pix, int(bool(soft_aug)), alpha, _lib.NOISE[final_noise_mode],
-                                  self.img_channels)
+                                  self.img_channels, w_disc)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.la_augment(self.handle, _ptr(w0), C.byref(opt), _ptr(nz), _ptr(img), _ptr(w_aug), _ptr(losses),
                                            _stream_ptr(self.device)))

@@ -65,3 +65,37 @@ def infer_generator_kwargs(state):
     aw = state['synthesis.b4.conv1.affine.weight']
     z_dim = state['mapping.fc0.weight'].shape[1] if 'mapping.fc0.weight' in state else aw.shape[1]
     return dict(img_resolution=res, img_channels=tw.shape[0], w_dim=aw.shape[1], z_dim=z_dim)
+
+
+def random_discriminator_state(img_resolution=256, img_channels=3, channel_base=32768, channel_max=512, seed=5, device='cpu'):
+    """Random-init StyleGAN2 'resnet' discriminator parameters (names per models/stylegan3/legacy.py:267-287)."""
+    g = torch.Generator(device='cpu').manual_seed(seed)
+
+    def randn(*shape):
+        return torch.randn(shape, generator=g).to(device)
+    log2 = int(math.log2(img_resolution))
+    res_list = [2 ** i for i in range(log2, 2, -1)]
+    ch = {r: min(channel_base // r, channel_max) for r in res_list + [4]}
+    f1 = torch.tensor([1., 3., 3., 1.])
+    fir = (torch.outer(f1, f1) / 64.0).to(device)
+    sd = {}
+    for r in res_list:
+        p = f'b{r}.'
+        c, cn = ch[r], ch[r // 2]
+        if r == img_resolution:
+            sd[p + 'fromrgb.weight'] = randn(c, img_channels, 1, 1)
+            sd[p + 'fromrgb.bias'] = torch.zeros(c, device=device)
+        sd[p + 'conv0.weight'] = randn(c, c, 3, 3)
+        sd[p + 'conv0.bias'] = torch.zeros(c, device=device)
+        sd[p + 'conv1.weight'] = randn(cn, c, 3, 3)
+        sd[p + 'conv1.bias'] = torch.zeros(cn, device=device)
+        sd[p + 'conv1.resample_filter'] = fir
+        sd[p + 'skip.weight'] = randn(cn, c, 1, 1)
+    c4 = ch[4]
+    sd['b4.conv.weight'] = randn(c4, c4 + 1, 3, 3)
+    sd['b4.conv.bias'] = torch.zeros(c4, device=device)
+    sd['b4.fc.weight'] = randn(c4, c4 * 16)
+    sd['b4.fc.bias'] = torch.zeros(c4, device=device)
+    sd['b4.out.weight'] = randn(1, c4)
+    sd['b4.out.bias'] = torch.zeros(1, device=device)
+    return sd

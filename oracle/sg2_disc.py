@@ -22,8 +22,26 @@ from . import ops
 from .sg2 import FC
 
 
+class _RoundBf16(torch.autograd.Function):
+    """Straight-through bf16 rounding of a layer output (and of the gradient flowing back through it)."""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
 class Conv2dLayer(torch.nn.Module):
-    """Equalised-lr conv + optional FIR down-sampling + bias + activation (names: weight, bias)."""
+    """Equalised-lr conv + optional FIR down-sampling + bias + activation (names: weight, bias).
+
+    ``emulate_bf16`` (class attribute, tests only): round the scaled weights and the layer output to bf16 --
+    the arithmetic of the CUDA discriminator -- so that its gradient can be checked at a tolerance below the
+    5 % that bf16 rounding alone moves the input gradient of a random-init D (sign flips of near-zero
+    pre-activations)."""
+    emulate_bf16 = False
 
     def __init__(self, cin, cout, k, bias=True, act='linear', down=1, conv_clamp=None, fir=(1, 3, 3, 1)):
         super().__init__()
@@ -36,10 +54,13 @@ class Conv2dLayer(torch.nn.Module):
 
     def forward(self, x, gain=1.0):
         w = self.weight * self.w_gain
+        if Conv2dLayer.emulate_bf16:
+            w = w.bfloat16().float()
         x = ops.conv2d_resample(x, w, f=self.resample_filter, down=self.down, padding=self.padding, flip_weight=True)
         act_gain = ops._ACTS[self.act][2] * gain
         clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
-        return ops.bias_act(x, self.bias, act=self.act, gain=act_gain, clamp=clamp)
+        x = ops.bias_act(x, self.bias, act=self.act, gain=act_gain, clamp=clamp)
+        return _RoundBf16.apply(x) if Conv2dLayer.emulate_bf16 else x
 
 
 class DiscBlock(torch.nn.Module):
