@@ -127,25 +127,32 @@ __global__ void f4_to_nchw_kernel(const float4* __restrict__ src, int C, int hw,
 }
 
 // ------------------------------------------------------------------------- fromrgb (1x1 conv from the image)
-// x[p][c] = act(sum_k img[p].k * w[c][k] * wg + b[c]);  thread per (pixel, channel pair)
+// x[p][c] = act(sum_k img[p].k * w[c][k] * wg + b[c]).  A thread owns one channel pair (weights in registers) and
+// walks a run of pixels; a warp writes 128 contiguous bytes per pixel.
+constexpr int kRgbPixels = 128;
 __global__ void fromrgb_fwd_kernel(const float4* __restrict__ img, const float* __restrict__ w, const float* __restrict__ b, long long npix,
                                    int C, int imgc, float wg, float gain, float slope, float clamp, unsigned* x) {
     const int hc = C >> 1;
-    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-    if (idx >= npix * hc) return;
-    const int cp = static_cast<int>(idx % hc);
-    const long long p = idx / hc;
-    const float4 v = __ldg(img + p);
-    float z[2];
+    const int cpb = hc < 256 ? hc : 256, lanes = 256 / cpb;
+    const int cp = blockIdx.y * cpb + threadIdx.x % cpb, lane = threadIdx.x / cpb;
+    float wr[2][3], br[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
         const int c = 2 * cp + u;
-        float a = v.x * w[c * imgc];
-        if (imgc > 1) a = fmaf(v.y, w[c * imgc + 1], a);
-        if (imgc > 2) a = fmaf(v.z, w[c * imgc + 2], a);
-        z[u] = act_fwd(a * wg + b[c], gain, slope, clamp);
+        wr[u][0] = w[c * imgc] * wg;
+        wr[u][1] = imgc > 1 ? w[c * imgc + 1] * wg : 0.f;
+        wr[u][2] = imgc > 2 ? w[c * imgc + 2] * wg : 0.f;
+        br[u] = b[c];
     }
-    x[idx] = pack2(z[0], z[1]);
+    const long long p0 = static_cast<long long>(blockIdx.x) * kRgbPixels;
+    for (int i = lane; i < kRgbPixels; i += lanes) {
+        const long long p = p0 + i;
+        if (p >= npix) break;
+        const float4 v = __ldg(img + p);
+        const float z0 = act_fwd(fmaf(v.x, wr[0][0], fmaf(v.y, wr[0][1], v.z * wr[0][2])) + br[0], gain, slope, clamp);
+        const float z1 = act_fwd(fmaf(v.x, wr[1][0], fmaf(v.y, wr[1][1], v.z * wr[1][2])) + br[1], gain, slope, clamp);
+        x[p * hc + cp] = pack2(z0, z1);
+    }
 }
 // g_img[p].k (+)= sum_c gz[p][c] * w[c][k] * wg;  warp per pixel
 __global__ void fromrgb_bwd_kernel(const unsigned* __restrict__ gz, const float* __restrict__ w, long long npix, int C, int imgc, float wg,
@@ -177,56 +184,25 @@ __global__ void fromrgb_bwd_kernel(const unsigned* __restrict__ gz, const float*
 struct Fir16 { float k[16]; };
 __global__ void firdown_fwd_kernel(const unsigned* __restrict__ x, int B, int R, int C, Fir16 f, unsigned* ys) {
     const int hc = C >> 1, Ro = R >> 1;
-    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-    if (idx >= static_cast<long long>(B) * Ro * Ro * hc) return;
-    const int cp = static_cast<int>(idx % hc);
-    long long p = idx / hc;
-    const int n = static_cast<int>(p % Ro); p /= Ro;
-    const int m = static_cast<int>(p % Ro);
-    const int b = static_cast<int>(p / Ro);
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;       // (n, channel pair) of output row m = blockIdx.y, sample blockIdx.z
+    if (e >= Ro * hc) return;
+    const int cp = e % hc, n = e / hc, m = blockIdx.y, b = blockIdx.z;
     float a0 = 0.f, a1 = 0.f;
 #pragma unroll
     for (int jy = 0; jy < 4; ++jy) {
         const int y = 2 * m + jy - 1;
         if (y < 0 || y >= R) continue;
+        const unsigned* row = x + (static_cast<long long>(b) * R + y) * R * hc + cp;
 #pragma unroll
         for (int jx = 0; jx < 4; ++jx) {
             const int xx = 2 * n + jx - 1;
             if (xx < 0 || xx >= R) continue;
-            const unsigned u = __ldg(x + ((static_cast<long long>(b) * R + y) * R + xx) * hc + cp);
+            const unsigned u = __ldg(row + xx * hc);
             a0 = fmaf(f.k[jy * 4 + jx], lo_f(u), a0);
             a1 = fmaf(f.k[jy * 4 + jx], hi_f(u), a1);
         }
     }
-    ys[idx] = pack2(a0, a1);
-}
-// adjoint: g_up[v] = sum over (m, j) with 2m + j - 1 = v of fk[j] * g_ys[m]
-__global__ void firdown_bwd_kernel(const unsigned* __restrict__ gys, int B, int R, int C, Fir16 f, unsigned* gup) {
-    const int hc = C >> 1, Ro = R >> 1;
-    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-    if (idx >= static_cast<long long>(B) * R * R * hc) return;
-    const int cp = static_cast<int>(idx % hc);
-    long long p = idx / hc;
-    const int vx = static_cast<int>(p % R); p /= R;
-    const int vy = static_cast<int>(p % R);
-    const int b = static_cast<int>(p / R);
-    float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-    for (int ty = 0; ty < 2; ++ty) {
-        const int jy = ((vy + 1) & 1) + 2 * ty;
-        const int m = (vy + 1 - jy) / 2;
-        if (vy + 1 - jy < 0 || m >= Ro) continue;
-#pragma unroll
-        for (int tx = 0; tx < 2; ++tx) {
-            const int jx = ((vx + 1) & 1) + 2 * tx;
-            const int n = (vx + 1 - jx) / 2;
-            if (vx + 1 - jx < 0 || n >= Ro) continue;
-            const unsigned u = __ldg(gys + ((static_cast<long long>(b) * Ro + m) * Ro + n) * hc + cp);
-            a0 = fmaf(f.k[jy * 4 + jx], lo_f(u), a0);
-            a1 = fmaf(f.k[jy * 4 + jx], hi_f(u), a1);
-        }
-    }
-    gup[idx] = pack2(a0, a1);
+    ys[((static_cast<long long>(b) * Ro + m) * Ro) * hc + e] = pack2(a0, a1);
 }
 
 // ------------------------------------------------------------------------- minibatch standard deviation (4x4 epilogue)
@@ -381,7 +357,7 @@ struct la_disc {
     std::vector<Block> blk;
     float fir[16];                            // flipped, normalised 4x4 filter (true convolution)
     // shared scratch (sized for the top block)
-    bf16 *yb, *ys, *g_ys, *g_up, *g_yb, *g_z0, *gz_rgb;
+    bf16 *yb, *ys, *g_ys, *g_yb, *g_z0, *gz_rgb;
     float* ones;                              // demod = 1 for the plain layers
     // epilogue
     int C4, Cp;
@@ -443,7 +419,7 @@ int plan_disc(la_disc* D, char* ws, size_t* bytes_out) {
     }
     D->yb = bp.take<bf16>(max_t); D->g_yb = bp.take<bf16>(max_t);
     D->ys = bp.take<bf16>(max_half); D->g_ys = bp.take<bf16>(max_half);
-    D->g_up = bp.take<bf16>(max_full); D->g_z0 = bp.take<bf16>(max_full); D->gz_rgb = bp.take<bf16>(max_full);
+    D->g_z0 = bp.take<bf16>(max_full); D->gz_rgb = bp.take<bf16>(max_full);
     const int C4 = d.channels[d.num_blocks], Cp = C4 + 64;
     D->C4 = C4; D->Cp = Cp;
     cmax = 16 * C4 > cmax ? 16 * C4 : cmax;
@@ -623,7 +599,8 @@ int build_disc(la_disc* D) {
             DLA(make_b_map(&P.b_map, k.w0b, C, C, 9, bn));
             P.kchunks = C / 64; P.n_total = C; P.n_blocks = C / bn;
             P.epilogue = kEpiLinear; P.OH = P.OW = R; P.osy = P.osx = 1;
-            P.lin_add = D->g_up;
+            P.lin_add_down = D->g_ys;          // FIRdown^T(g_ys) is evaluated inside the epilogue
+            for (int i = 0; i < 16; ++i) P.lin_fir[i] = D->fir[i];
             P.act_slope = 0.2f;
             if (b == 0) {                     // the producer is fromrgb (lrelu*sqrt2, clamp)
                 P.lin_out = nullptr; P.lin_saved = k.x_in; P.lin_gz = D->gz_rgb;
@@ -802,7 +779,8 @@ int disc_forward(la_disc* D, const float4* img, cudaStream_t s, long long* launc
     {
         Block& k = D->blk[0];
         const long long npix = static_cast<long long>(B) * k.R * k.R;
-        fromrgb_fwd_kernel<<<cdiv(npix * (k.C / 2), 256), 256, 0, s>>>(img, k.p.d_fromrgb_weight, k.p.d_fromrgb_bias, npix, k.C, d.img_channels,
+        const int hc = k.C / 2, cpb = hc < 256 ? hc : 256;
+        fromrgb_fwd_kernel<<<dim3(cdiv(npix, kRgbPixels), hc / cpb), 256, 0, s>>>(img, k.p.d_fromrgb_weight, k.p.d_fromrgb_bias, npix, k.C, d.img_channels,
                                                                      1.f / sqrtf(static_cast<float>(d.img_channels)), kSqrt2, 0.2f, d.conv_clamp,
                                                                      reinterpret_cast<unsigned*>(k.x_in));
         DCU(cudaGetLastError());
@@ -812,8 +790,7 @@ int disc_forward(la_disc* D, const float4* img, cudaStream_t s, long long* launc
         DLA(gemm(D, k.F0, s, launches));
         DLA(upfir_backward(k.blur, s));                               // blur: x0 -> yb
         DLA(gemm(D, k.F1, s, launches));
-        const long long nout = static_cast<long long>(B) * (k.R / 2) * (k.R / 2) * (k.C / 2);
-        firdown_fwd_kernel<<<cdiv(nout, 256), 256, 0, s>>>(reinterpret_cast<const unsigned*>(k.x_in), B, k.R, k.C, f, reinterpret_cast<unsigned*>(D->ys));
+        firdown_fwd_kernel<<<dim3(cdiv((k.R / 2) * (k.C / 2), 256), k.R / 2, B), 256, 0, s>>>(reinterpret_cast<const unsigned*>(k.x_in), B, k.R, k.C, f, reinterpret_cast<unsigned*>(D->ys));
         DCU(cudaGetLastError());
         DLA(gemm(D, k.FS, s, launches));
         if (launches) *launches += 2;
@@ -856,13 +833,10 @@ int disc_backward(la_disc* D, float w_disc, float4* g_img, int accumulate, float
     for (int b = d.num_blocks - 1; b >= 0; --b) {
         Block& k = D->blk[b];
         DLA(gemm(D, k.BS, s, launches));                              // g_ys = Ws^T g_y
-        const long long nfull = static_cast<long long>(B) * k.R * k.R * (k.C / 2);
-        firdown_bwd_kernel<<<cdiv(nfull, 256), 256, 0, s>>>(reinterpret_cast<const unsigned*>(D->g_ys), B, k.R, k.C, f, reinterpret_cast<unsigned*>(D->g_up));
-        DCU(cudaGetLastError());
         DLA(gemm(D, k.B1, s, launches));                              // g_yb = conv1^T g_z1
         DLA(upfir_forward(k.blur, s));                                // g_z0 = blur^T(g_yb) * act0'(x0)
         DLA(gemm(D, k.B0, s, launches));                              // conv0^T + g_up -> block input gradient
-        if (launches) *launches += 2;
+        if (launches) *launches += 1;
     }
     Block& top = D->blk[0];
     const long long npix = static_cast<long long>(B) * top.R * top.R;

@@ -327,6 +327,24 @@ __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const
 #pragma unroll
                     for (int j = 0; j < 32; ++j) acc[j] += t[j];
                 }
+                if (P.lin_add_down) {       // gradient of the skip branch: 2 x 2 coarse pixels reach this fine pixel
+                    const int vy = static_cast<int>(rc.px_in_img / P.OW), vx = static_cast<int>(rc.px_in_img - static_cast<long long>(vy) * P.OW);
+                    const int Ho = P.OH >> 1, Wo = P.OW >> 1;
+#pragma unroll
+                    for (int ty = 0; ty < 2; ++ty) {
+                        const int jy = ((vy + 1) & 1) + 2 * ty, my = vy + 1 - jy;
+                        if (my < 0 || (my >> 1) >= Ho) continue;
+#pragma unroll
+                        for (int tx = 0; tx < 2; ++tx) {
+                            const int jx = ((vx + 1) & 1) + 2 * tx, mx = vx + 1 - jx;
+                            if (mx < 0 || (mx >> 1) >= Wo) continue;
+                            const float wgt = P.lin_fir[jy * 4 + jx];
+                            load_bf16x32(P.lin_add_down, ((static_cast<long long>(rc.n) * Ho + (my >> 1)) * Wo + (mx >> 1)) * P.n_total + col0, t);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) acc[j] = fmaf(wgt, t[j], acc[j]);
+                        }
+                    }
+                }
                 if (P.lin_out) store_bf16x32(P.lin_out, nullptr, eoff, acc);
                 if (P.lin_gz) {
                     load_bf16x32(P.lin_saved, eoff, t);

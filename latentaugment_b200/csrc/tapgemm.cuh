@@ -122,6 +122,9 @@ struct TapGemmParams {
 
     // ---- kEpiLinear
     const void* lin_add;               // bf16 addend (residual branch / second gradient path) or null
+    const void* lin_add_down;          // bf16 [batch, OH/2, OW/2, N] or null: adds the ADJOINT of the decimating 4x4 FIR
+                                       // (upfirdn2d down=2, pad 1) of this tensor: sum_{2m+j-1=v} lin_fir[j] * t[m]
+    float lin_fir[16];                 // flipped 4x4 filter of lin_add_down
     void* lin_out;                     // bf16 r or null
     const void* lin_saved;             // bf16 saved activation output deciding the activation gradient, or null
     void* lin_gz;                      // bf16 r * act_gain * (saved > 0 ? 1 : act_slope) * (|saved| < act_clamp), or null
