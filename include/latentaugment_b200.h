@@ -128,10 +128,10 @@ typedef struct la_disc_desc {
 const char* la_last_error(void);
 int la_version(void);
 
-/* Discriminator of the realism term.  It runs in bf16 operands / fp32 accumulate in both precisions of the engine.
+/* Discriminator of the realism term; it runs in the engine's precision (`precision` below must equal the engine's).
  * The workspace is caller-owned like the engine's.  la_disc_logits / la_disc_loss_grad are the stand-alone forms
  * of what la_augment does every step when w_disc > 0 (tests, criteria plugin). */
-int la_disc_workspace_bytes(const la_disc_desc* d, int batch, size_t* bytes);
+int la_disc_workspace_bytes(const la_disc_desc* d, int batch, int precision, size_t* bytes);
 int la_set_discriminator(la_engine* e, const la_disc_desc* d, void* d_workspace, size_t workspace_bytes, la_stream stream);
 /* d_img [batch, img_channels, res, res] fp32 -> d_logits [batch] */
 int la_disc_logits(la_engine* e, const float* d_img, float* d_logits, la_stream stream);

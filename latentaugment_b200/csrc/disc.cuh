@@ -10,8 +10,9 @@ struct la_disc;
 
 namespace la {
 
-int disc_workspace_bytes(const la_disc_desc& d, int batch, size_t* bytes);
-int disc_create(const la_disc_desc& d, int batch, int num_sms, void* ws, size_t bytes, cudaStream_t s, la_disc** out);
+int disc_workspace_bytes(const la_disc_desc& d, int batch, int split, size_t* bytes);
+// split = 1: split-bf16 (hi/lo) operands like the engine's fp32_parity precision
+int disc_create(const la_disc_desc& d, int batch, int split, int num_sms, void* ws, size_t bytes, cudaStream_t s, la_disc** out);
 void disc_destroy(la_disc* D);
 
 // img: float4 per pixel [B, R, R] (channel k in .x / .y / .z).  Leaves the logits in disc_logits().

@@ -809,9 +809,9 @@ LA_API int la_augment(la_engine* e, const float* d_w0, const la_augment_options*
     return 0;
 }
 
-LA_API int la_disc_workspace_bytes(const la_disc_desc* d, int batch, size_t* bytes) {
+LA_API int la_disc_workspace_bytes(const la_disc_desc* d, int batch, int precision, size_t* bytes) {
     if (!d || !bytes || batch < 1) return fail(-2, "bad arguments");
-    if (disc_workspace_bytes(*d, batch, bytes)) return fail(-2, "%s", disc_last_error());
+    if (disc_workspace_bytes(*d, batch, precision == LA_PRECISION_FP32_PARITY, bytes)) return fail(-2, "%s", disc_last_error());
     return 0;
 }
 
@@ -821,7 +821,7 @@ LA_API int la_set_discriminator(la_engine* e, const la_disc_desc* d, void* d_wor
         return fail(-2, "discriminator shape %dx%d (%d ch) does not match the generator", d->img_resolution, d->img_resolution, d->img_channels);
     if (e->disc) { disc_destroy(e->disc); e->disc = nullptr; }
     if (e->step_graph) { cudaGraphExecDestroy(e->step_graph); e->step_graph = nullptr; }
-    if (disc_create(*d, e->batch, e->num_sms, d_workspace, workspace_bytes, static_cast<cudaStream_t>(stream), &e->disc))
+    if (disc_create(*d, e->batch, e->split, e->num_sms, d_workspace, workspace_bytes, static_cast<cudaStream_t>(stream), &e->disc))
         return fail(-6, "discriminator: %s", disc_last_error());
     return 0;
 }

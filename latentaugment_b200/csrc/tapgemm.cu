@@ -326,6 +326,11 @@ __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const
                     load_bf16x32(P.lin_add, eoff, t);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) acc[j] += t[j];
+                    if (P.split) {
+                        load_bf16x32(P.lin_add_lo, eoff, t);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[j] += t[j];
+                    }
                 }
                 if (P.lin_add_down) {       // gradient of the skip branch: 2 x 2 coarse pixels reach this fine pixel
                     const int vy = static_cast<int>(rc.px_in_img / P.OW), vx = static_cast<int>(rc.px_in_img - static_cast<long long>(vy) * P.OW);
@@ -339,13 +344,19 @@ __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const
                             const int jx = ((vx + 1) & 1) + 2 * tx, mx = vx + 1 - jx;
                             if (mx < 0 || (mx >> 1) >= Wo) continue;
                             const float wgt = P.lin_fir[jy * 4 + jx];
-                            load_bf16x32(P.lin_add_down, ((static_cast<long long>(rc.n) * Ho + (my >> 1)) * Wo + (mx >> 1)) * P.n_total + col0, t);
+                            const long long doff = ((static_cast<long long>(rc.n) * Ho + (my >> 1)) * Wo + (mx >> 1)) * P.n_total + col0;
+                            load_bf16x32(P.lin_add_down, doff, t);
 #pragma unroll
                             for (int j = 0; j < 32; ++j) acc[j] = fmaf(wgt, t[j], acc[j]);
+                            if (P.split) {
+                                load_bf16x32(P.lin_add_down_lo, doff, t);
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) acc[j] = fmaf(wgt, t[j], acc[j]);
+                            }
                         }
                     }
                 }
-                if (P.lin_out) store_bf16x32(P.lin_out, nullptr, eoff, acc);
+                if (P.lin_out) store_bf16x32(P.lin_out, P.split ? P.lin_out_lo : nullptr, eoff, acc);
                 if (P.lin_gz) {
                     load_bf16x32(P.lin_saved, eoff, t);
 #pragma unroll
@@ -353,7 +364,7 @@ __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const
                         const float g = acc[j] * P.act_gain * (t[j] > 0.f ? 1.f : P.act_slope);
                         acc[j] = fabsf(t[j]) < clampv ? g : 0.f;
                     }
-                    store_bf16x32(P.lin_gz, nullptr, eoff, acc);
+                    store_bf16x32(P.lin_gz, P.split ? P.lin_gz_lo : nullptr, eoff, acc);
                 }
             }
         } else if constexpr (EPI == kEpiTopK) {

@@ -128,6 +128,7 @@ struct TapGemmParams {
     void* lin_out;                     // bf16 r or null
     const void* lin_saved;             // bf16 saved activation output deciding the activation gradient, or null
     void* lin_gz;                      // bf16 r * act_gain * (saved > 0 ? 1 : act_slope) * (|saved| < act_clamp), or null
+    const void* lin_add_lo; const void* lin_add_down_lo; void* lin_out_lo; void* lin_gz_lo;   // residual planes when split
 
     // ---- kEpiTopK: acc[query, code] = <x, y>
     const float* code_sqnorm;          // [n_codes] |y_j|^2

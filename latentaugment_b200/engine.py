@@ -173,7 +173,7 @@ class SynthesisEngine:
         d.d_b4_fc_weight, d.d_b4_fc_bias = _ptr(dev('b4.fc.weight')), _ptr(dev('b4.fc.bias'))
         d.d_b4_out_weight, d.d_b4_out_bias = _ptr(dev('b4.out.weight')), _ptr(dev('b4.out.bias'))
         nbytes = C.c_size_t(0)
-        _lib.check(self.lib.la_disc_workspace_bytes(C.byref(d), self.batch, C.byref(nbytes)))
+        _lib.check(self.lib.la_disc_workspace_bytes(C.byref(d), self.batch, _lib.PRECISION[self.precision], C.byref(nbytes)))
         self.disc_workspace = torch.empty(nbytes.value + 1024, dtype=torch.uint8, device=self.device)
         base = (self.disc_workspace.data_ptr() + 1023) // 1024 * 1024
         with torch.cuda.device(self.device):
