@@ -115,7 +115,7 @@ def test_augment_loop_matches_oracle(cfg, steps, precision):
     assert ew < TOL[precision] and ei < TOL[precision]
 
 
-@pytest.mark.parametrize('name', ['loop_tiny.pt', 'loop_tiny_soft.pt', 'loop_tiny128.pt', 'loop_small.pt'])
+@pytest.mark.parametrize('name', ['loop_tiny.pt', 'loop_tiny_soft.pt', 'loop_tiny128.pt', 'loop_small.pt', 'loop_c1.pt'])
 def test_augment_loop_matches_reference_golden(golden, name):
     """Against outputs of the REFERENCE's own LatentAug.forward (tests/golden, oracle/make_golden.py)."""
     g = golden(name)
@@ -274,3 +274,49 @@ def test_both_upconv_formulations(monkeypatch, split_min_res, precision):
         b = eng.synthesis(ws, noise_mode='const').cpu()
         eng.debug_set_simt(0)
         assert rel_l2(a, b) < (2e-5 if precision == 'fp32_parity' else 5e-3)   # bf16: roundings of intermediates differ
+
+
+@pytest.mark.parametrize('batch', [1, 3, 5])
+@pytest.mark.parametrize('precision', ['fp32_parity', 'bf16'])
+def test_ragged_batches(batch, precision):
+    """Batch sizes that leave partial M tiles at every resolution (8 / 2 / 1 samples per tile) and odd tile pairs."""
+    from oracle import latent_aug as ola
+    from oracle import synthetic
+    wl = synthetic.make_workload('tiny', noise_strength=0.1, batch=batch)
+    G = wl['G']
+    eng = _engine(wl, precision, batch=batch)
+    eng.set_latent_bank(wl['W'])
+    eng.set_image_bank(wl['X'])
+    orc = ola.LatentAugOracle(G, wl['W'], wl['X'], num_epochs=2, fused=True)
+    random.seed(0)
+    _, w_ref = orc.forward(wl['w0'].clone())
+    with torch.no_grad():
+        img_ref = G.synthesis(w_ref, noise_mode='const')
+    img, w_aug = eng.augment(wl['w0'], num_steps=2, final_noise_mode='const')
+    eng.debug_check()
+    ew, ei = rel_l2(w_aug.cpu(), w_ref[:, 0]), rel_l2(img.cpu(), img_ref)
+    print(f'\n[ragged batch={batch} {precision}] rel_w={ew:.3e} rel_img={ei:.3e}')
+    assert ew < TOL[precision] and ei < TOL[precision]
+
+
+def test_single_channel_wide_generator():
+    """1-channel images and 256-wide layers at 64^2 (BN = 256 path, TMA FIR passes, bulk seed kernel) against the oracle."""
+    from oracle import latent_aug as ola
+    from oracle import synthetic
+    cfg = dict(img_resolution=64, img_channels=1, channel_base=16384, channel_max=256, batch=4, steps=2, bank=32, img_bank=4)
+    wl = synthetic.make_workload(cfg, noise_strength=0.1)
+    G = wl['G']
+    for precision in ('fp32_parity', 'bf16'):
+        eng = _engine(wl, precision)
+        eng.set_latent_bank(wl['W'])
+        eng.set_image_bank(wl['X'])
+        orc = ola.LatentAugOracle(G, wl['W'], wl['X'], num_epochs=2, fused=True)
+        random.seed(0)
+        _, w_ref = orc.forward(wl['w0'].clone())
+        with torch.no_grad():
+            img_ref = G.synthesis(w_ref, noise_mode='const')
+        img, w_aug = eng.augment(wl['w0'], num_steps=2, final_noise_mode='const')
+        eng.debug_check()
+        ew, ei = rel_l2(w_aug.cpu(), w_ref[:, 0]), rel_l2(img.cpu(), img_ref)
+        print(f'\n[1-ch wide {precision}] rel_w={ew:.3e} rel_img={ei:.3e}')
+        assert ew < TOL[precision] and ei < TOL[precision]
