@@ -138,6 +138,19 @@ int la_disc_logits(la_engine* e, const float* d_img, float* d_logits, la_stream 
 /* loss = w_disc * mean softplus(-D(img)) -> d_loss [1];  d loss / d img -> d_grad [batch, img_channels, res, res] */
 int la_disc_loss_grad(la_engine* e, const float* d_img, float w_disc, float* d_loss, float* d_grad, la_stream stream);
 
+/* filtered_lrelu (reference torch_utils/ops/filtered_lrelu.py:56-153; the StyleGAN3 synthesis-layer op):
+ * y = decimate_down( FIR_fd( clamp( lrelu( FIR_fu( pad( zero_insert_up( x + b ) ) ) * up^2 ) * gain ) ) ).
+ * d_x [N, C, H, W] fp32 -> d_y [N, C, out_h, out_w] with mid = H*up + py0 + py1 - (fu_taps - 1),
+ * out_h = ceil((mid - (fd_taps - 1)) / down).  h_fu / h_fd are HOST arrays of separable taps (null = identity).
+ * d_mask_out (int8 [N*C, mid_h, mid_w], or null) receives the activation-derivative class per intermediate pixel
+ * (0 clamped, 1 positive, 2 negative); with d_mask_in the activation is replaced by gain * that derivative -- the
+ * backward pass is this same call with the filters' roles swapped (latentaugment_b200/ops_sg3.py).  mask_o / mask_h /
+ * mask_w place the mask tensor inside the intermediate (0 sizes = it covers the intermediate exactly). */
+int la_filtered_lrelu(const float* d_x, int N, int C, int H, int W, const float* h_fu, int fu_taps, const float* h_fd, int fd_taps,
+                      const float* d_b, int up, int down, int px0, int px1, int py0, int py1, float gain, float slope, float clamp,
+                      int flip_filter, const signed char* d_mask_in, signed char* d_mask_out, int mask_oy, int mask_ox, int mask_h,
+                      int mask_w, float* d_y, la_stream stream);
+
 /* Bytes of device workspace an engine of this shape needs. */
 int la_engine_workspace_bytes(const la_generator_desc* g, int batch, int precision, size_t* bytes);
 
