@@ -117,6 +117,14 @@ __global__ void prep_fc_weights_kernel(const float* __restrict__ w, int C, float
     st_sp(wf, split ? wf + total : nullptr, idx, v);
     st_sp(wb, split ? wb + total : nullptr, (static_cast<long long>(hw) * C + c) * C + o, v);
 }
+__global__ void prep_rgb_w4_kernel(const float* __restrict__ w, int C, int imgc, float wg, float* w4) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    w4[4 * c + 0] = w[c * imgc] * wg;
+    w4[4 * c + 1] = imgc > 1 ? w[c * imgc + 1] * wg : 0.f;
+    w4[4 * c + 2] = imgc > 2 ? w[c * imgc + 2] * wg : 0.f;
+    w4[4 * c + 3] = 0.f;
+}
 __global__ void fill_kernel(float* p, float v, long long n) {
     const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (i < n) p[i] = v;
@@ -171,31 +179,6 @@ __global__ void fromrgb_fwd_kernel(const float4* __restrict__ img, const float* 
         st_sp2(x, x_lo, p * hc + cp, z0, z1);
     }
 }
-// g_img[p].k (+)= sum_c gz[p][c] * w[c][k] * wg;  warp per pixel
-__global__ void fromrgb_bwd_kernel(const unsigned* __restrict__ gz, const unsigned* __restrict__ gz_lo, const float* __restrict__ w, long long npix,
-                                   int C, int imgc, float wg, int accumulate, float4* g_img) {
-    const long long p = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (p >= npix) return;
-    const int hc = C >> 1;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    for (int cp = lane; cp < hc; cp += 32) {
-        const unsigned u = __ldg(gz + p * hc + cp);
-        float g0 = lo_f(u), g1 = hi_f(u);
-        if (gz_lo) { const unsigned l = __ldg(gz_lo + p * hc + cp); g0 += lo_f(l); g1 += hi_f(l); }
-        const int c = 2 * cp;
-        s0 = fmaf(g0, w[c * imgc], fmaf(g1, w[(c + 1) * imgc], s0));
-        if (imgc > 1) s1 = fmaf(g0, w[c * imgc + 1], fmaf(g1, w[(c + 1) * imgc + 1], s1));
-        if (imgc > 2) s2 = fmaf(g0, w[c * imgc + 2], fmaf(g1, w[(c + 1) * imgc + 2], s2));
-    }
-    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
-    if (lane == 0) {
-        float4 o = accumulate ? g_img[p] : make_float4(0.f, 0.f, 0.f, 0.f);
-        o.x += s0 * wg; o.y += s1 * wg; o.z += s2 * wg;
-        g_img[p] = o;
-    }
-}
-
 // ------------------------------------------------------------------------- decimating FIR of the skip branch
 // upfirdn2d(x, f, down=2, padding=1) (conv2d_resample.py:94-97):  ys[m, n] = sum_j fk[jy][jx] * x[2m + jy - 1, 2n + jx - 1]
 // (fk = flipped filter: true convolution, upfirdn2d.py:196-199).  Thread per (output pixel, channel pair).
@@ -384,8 +367,9 @@ struct la_disc {
     std::vector<Block> blk;
     float fir[16];                            // flipped, normalised 4x4 filter (true convolution)
     // shared scratch (sized for the top block)
-    Pl yb, ys, g_ys, g_yb, g_z0, gz_rgb;
+    Pl yb, ys, g_ys, g_yb, g_z0;
     float* ones;                              // demod = 1 for the plain layers
+    float* rgb_w4;                            // [C_top][4]: fromrgb weights * weight gain, for the fused fromrgb backward
     // epilogue
     int C4, Cp;
     Pl x4p, x5, x6, gz6, gz5, gx4p;
@@ -462,11 +446,12 @@ int plan_disc(la_disc* D, char* ws, size_t* bytes_out) {
     }
     D->yb = take_pl(max_t); D->g_yb = take_pl(max_t);
     D->ys = take_pl(max_half); D->g_ys = take_pl(max_half);
-    D->g_z0 = take_pl(max_full); D->gz_rgb = take_pl(max_full);
+    D->g_z0 = take_pl(max_full);
     const int C4 = d.channels[d.num_blocks], Cp = C4 + 64;
     D->C4 = C4; D->Cp = Cp;
     cmax = 16 * C4 > cmax ? 16 * C4 : cmax;
     D->ones = bp.take<float>(static_cast<size_t>(B) * cmax);
+    D->rgb_w4 = bp.take<float>(4 * static_cast<size_t>(d.channels[0]));
     D->x4p = take_pl(static_cast<size_t>(B) * 16 * Cp); D->gx4p = take_pl(static_cast<size_t>(B) * 16 * Cp);
     D->x5 = take_pl(static_cast<size_t>(B) * 16 * C4); D->gz5 = take_pl(static_cast<size_t>(B) * 16 * C4);
     D->x6 = take_pl(static_cast<size_t>(B) * C4); D->gz6 = take_pl(static_cast<size_t>(B) * C4);
@@ -644,8 +629,8 @@ int build_disc(la_disc* D) {
             lin_epi(P, D, C, bn, R, R);
             P.lin_add_down = D->g_ys.hi; P.lin_add_down_lo = D->g_ys.lo;      // FIRdown^T(g_ys) is evaluated inside the epilogue
             for (int i = 0; i < 16; ++i) P.lin_fir[i] = D->fir[i];
-            if (b == 0) {                     // the producer is fromrgb (lrelu*sqrt2, clamp)
-                P.lin_saved = k.x_in.hi; P.lin_gz = D->gz_rgb.hi; P.lin_gz_lo = D->gz_rgb.lo;
+            if (b == 0) {                     // the producer is fromrgb (lrelu*sqrt2, clamp): its backward is fused (atomics into g_img)
+                P.lin_saved = k.x_in.hi; P.lin_rgb_w = D->rgb_w4;       // lin_rgb_g is set per call
                 P.act_gain = kSqrt2; P.act_clamp = clamp;
             } else {                          // the producer is conv1 of the block above (gain sqrt2*sqrt(.5), clamp*sqrt(.5))
                 Block& up = D->blk[b - 1];
@@ -740,6 +725,9 @@ int prepare_disc(la_disc* D, cudaStream_t s) {
     if (!D->blk[0].p.d_fromrgb_weight || !D->blk[0].p.d_fromrgb_bias) return dfail(-2, "discriminator: missing fromrgb parameters");
     if (!d.d_b4_conv_weight || !d.d_b4_conv_bias || !d.d_b4_fc_weight || !d.d_b4_fc_bias || !d.d_b4_out_weight || !d.d_b4_out_bias)
         return dfail(-2, "discriminator: missing epilogue parameters");
+    prep_rgb_w4_kernel<<<cdiv(D->blk[0].C, 128), 128, 0, s>>>(D->blk[0].p.d_fromrgb_weight, D->blk[0].C, d.img_channels,
+                                                             1.f / sqrtf(static_cast<float>(d.img_channels)), D->rgb_w4);
+    DCU(cudaGetLastError());
     const int C4 = D->C4, Cp = D->Cp;
     DLA(prep(d.d_b4_conv_weight, C4, C4 + 1, 9, 1.f / sqrtf(9.f * (C4 + 1)), Cp, D->wef, D->web));
     prep_fc_weights_kernel<<<cdiv(16LL * C4 * C4, 256), 256, 0, s>>>(d.d_b4_fc_weight, C4, 1.f / sqrtf(16.f * C4), split, D->wff, D->wfb);
@@ -877,15 +865,16 @@ int disc_backward(la_disc* D, float w_disc, float4* g_img, int accumulate, float
         DLA(gemm(D, k.BS, s, launches));                              // g_ys = Ws^T g_y
         DLA(gemm(D, k.B1, s, launches));                              // g_yb = conv1^T g_z1
         DLA(upfir_forward(k.blur, s));                                // g_z0 = blur^T(g_yb) * act0'(x0)
-        DLA(gemm(D, k.B0, s, launches));                              // conv0^T + FIRdown^T(g_ys) -> block input gradient
+        if (b == 0) {                                                 // + fused fromrgb backward: atomics into g_img
+            if (!accumulate) DCU(cudaMemsetAsync(g_img, 0, sizeof(float4) * static_cast<size_t>(B) * k.R * k.R, s));
+            TapGemmParams P = k.B0;
+            P.lin_rgb_g = g_img;
+            DLA(gemm(D, P, s, launches));
+        } else {
+            DLA(gemm(D, k.B0, s, launches));                          // conv0^T + FIRdown^T(g_ys) -> block input gradient
+        }
         if (launches) *launches += 1;
     }
-    Block& top = D->blk[0];
-    const long long npix = static_cast<long long>(B) * top.R * top.R;
-    fromrgb_bwd_kernel<<<cdiv(npix, 8), 256, 0, s>>>(CU32(D->gz_rgb.hi), CU32(D->gz_rgb.lo), top.p.d_fromrgb_weight, npix, top.C, d.img_channels,
-                                                     1.f / sqrtf(static_cast<float>(d.img_channels)), accumulate, g_img);
-    DCU(cudaGetLastError());
-    if (launches) ++*launches;
     return 0;
 }
 

@@ -357,14 +357,24 @@ __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const
                     }
                 }
                 if (P.lin_out) store_bf16x32(P.lin_out, P.split ? P.lin_out_lo : nullptr, eoff, acc);
-                if (P.lin_gz) {
+                if (P.lin_gz || P.lin_rgb_w) {
                     load_bf16x32(P.lin_saved, eoff, t);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float g = acc[j] * P.act_gain * (t[j] > 0.f ? 1.f : P.act_slope);
                         acc[j] = fabsf(t[j]) < clampv ? g : 0.f;
                     }
-                    store_bf16x32(P.lin_gz, P.split ? P.lin_gz_lo : nullptr, eoff, acc);
+                    if (P.lin_gz) store_bf16x32(P.lin_gz, P.split ? P.lin_gz_lo : nullptr, eoff, acc);
+                    if (P.lin_rgb_w) {
+                        const float4* w4 = reinterpret_cast<const float4*>(P.lin_rgb_w) + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float4 w = __ldg(w4 + j);
+                            rgb0 = fmaf(acc[j], w.x, rgb0);
+                            rgb1 = fmaf(acc[j], w.y, rgb1);
+                            rgb2 = fmaf(acc[j], w.z, rgb2);
+                        }
+                    }
                 }
             }
         } else if constexpr (EPI == kEpiTopK) {
@@ -467,6 +477,10 @@ __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const
                 P.cand_score[base + k] = best_s[k]; P.cand_idx[base + k] = best_i[k];
                 if (fill_other) { P.cand_score[other + k] = __int_as_float(0x7f800000); P.cand_idx[other + k] = -1; }
             }
+    }
+    if (EPI == kEpiLinear && P.lin_rgb_w && rc.valid) {
+        float* g = reinterpret_cast<float*>(P.lin_rgb_g + rc.pix);
+        atomicAdd(g, rgb0); atomicAdd(g + 1, rgb1); atomicAdd(g + 2, rgb2);
     }
     if (EPI == kEpiFwd && P.rgbw && rc.valid) {   // one partial per (column block, slot): summed in fixed order later
         const long long plane = static_cast<long long>(P.batch) * P.OH * P.OW;

@@ -129,6 +129,8 @@ struct TapGemmParams {
     const void* lin_saved;             // bf16 saved activation output deciding the activation gradient, or null
     void* lin_gz;                      // bf16 r * act_gain * (saved > 0 ? 1 : act_slope) * (|saved| < act_clamp), or null
     const void* lin_add_lo; const void* lin_add_down_lo; void* lin_out_lo; void* lin_gz_lo;   // residual planes when split
+    const float* lin_rgb_w;            // [N][4] or null: fused 1x1 "fromrgb" backward -- the activation-gradient row (the lin_gz
+    float4* lin_rgb_g;                 // value) is contracted with these weights and atomically added to lin_rgb_g[pixel].xyz
 
     // ---- kEpiTopK: acc[query, code] = <x, y>
     const float* code_sqnorm;          // [n_codes] |y_j|^2
