@@ -257,6 +257,7 @@ def main():
                               'gpu_launches': int(launches), 'note': 'profile mode (no e2e / roofline / cpu_baseline legs)'}),
                   file=real_stdout, flush=True)
         return
+    time.sleep(3.0)      # both legs start from a comparable power / thermal state (the kernels are power-capped)
     for i in range(3):
         aug.set_input(batch_data(i)); aug.forward(); aug.get_output()
     barrier()
