@@ -497,7 +497,7 @@ int build_disc(la_disc* D) {
             set_grid(P, R, B, 1);
             DLA(dense_maps(D, P, 0, 1, k.x_in, C, R, R, P.tw, P.th + P.halo, P.nb));
             const int bn = choose_bn(C, P.m_tiles);
-            DLA(make_b_map(&P.b_map, k.w0f, C, C, 9 * wm, bn));
+            DLA(make_b_map(P, k.w0f, C, C, 9 * wm, bn));
             P.kchunks = C / 64;
             fwd_epi(P, D, k.p.d_conv0_bias, k.x0, kSqrt2, clamp, C, bn, R);
             P.err_flag = D->err_flag;
@@ -559,7 +559,7 @@ int build_disc(la_disc* D) {
                 }
             P.prob[0].tap_begin = 0; P.prob[0].ntaps = nt;
             const int bn = choose_bn(Cn, P.m_tiles);
-            DLA(make_b_map(&P.b_map, k.w1f, C, Cn, 9 * wm, bn));
+            DLA(make_b_map(P, k.w1f, C, Cn, 9 * wm, bn));
             P.kchunks = C / 64;
             fwd_epi(P, D, k.p.d_conv1_bias, k.y1, kSqrt2 * kSqrtHalf, clamp >= 0.f ? clamp * kSqrtHalf : clamp, Cn, bn, Ro);
             P.err_flag = D->err_flag;
@@ -572,7 +572,7 @@ int build_disc(la_disc* D) {
             set_grid(P, Ro, B, 1);
             DLA(dense_maps(D, P, 0, 1, D->ys, C, Ro, Ro, P.tw, P.th + P.halo, P.nb));
             const int bn = choose_bn(Cn, P.m_tiles);
-            DLA(make_b_map(&P.b_map, k.wsf, C, Cn, wm, bn));
+            DLA(make_b_map(P, k.wsf, C, Cn, wm, bn));
             P.kchunks = C / 64;
             lin_epi(P, D, Cn, bn, Ro, Ro);
             P.lin_add = k.y1.hi; P.lin_add_lo = k.y1.lo; P.lin_out = k.y.hi; P.lin_out_lo = k.y.lo;
@@ -586,7 +586,7 @@ int build_disc(la_disc* D) {
             set_grid(P, Ro, B, 1);
             DLA(dense_maps(D, P, 0, 1, k.g_y, Cn, Ro, Ro, P.tw, P.th + P.halo, P.nb));
             const int bn = choose_bn(C, P.m_tiles);
-            DLA(make_b_map(&P.b_map, k.wsb, Cn, C, wm, bn));
+            DLA(make_b_map(P, k.wsb, Cn, C, wm, bn));
             P.kchunks = Cn / 64;
             lin_epi(P, D, C, bn, Ro, Ro);
             P.lin_out = D->g_ys.hi; P.lin_out_lo = D->g_ys.lo;
@@ -609,7 +609,7 @@ int build_disc(la_disc* D) {
                 P.prob[ph].oy0 = ph / 2; P.prob[ph].ox0 = ph % 2;
             }
             const int bn = choose_bn(C, P.m_tiles);
-            DLA(make_b_map(&P.b_map, k.w1b, Cn, C, 9 * wm, bn));
+            DLA(make_b_map(P, k.w1b, Cn, C, 9 * wm, bn));
             P.kchunks = Cn / 64; P.n_total = C; P.n_blocks = C / bn;
             P.epilogue = kEpiStoreBf16; P.OH = TH; P.OW = TWp; P.osy = P.osx = 2; P.split = split;
             P.x_hi = D->g_yb.hi; P.x_lo = D->g_yb.lo;
@@ -624,7 +624,7 @@ int build_disc(la_disc* D) {
             set_grid(P, R, B, 1);
             DLA(dense_maps(D, P, 0, 1, D->g_z0, C, R, R, P.tw, P.th + P.halo, P.nb));
             const int bn = choose_bn(C, P.m_tiles);
-            DLA(make_b_map(&P.b_map, k.w0b, C, C, 9 * wm, bn));
+            DLA(make_b_map(P, k.w0b, C, C, 9 * wm, bn));
             P.kchunks = C / 64;
             lin_epi(P, D, C, bn, R, R);
             P.lin_add_down = D->g_ys.hi; P.lin_add_down_lo = D->g_ys.lo;      // FIRdown^T(g_ys) is evaluated inside the epilogue
@@ -649,7 +649,7 @@ int build_disc(la_disc* D) {
         set_grid(P, 4, B, 1);
         DLA(dense_maps(D, P, 0, 1, D->x4p, Cp, 4, 4, P.tw, P.th + P.halo, P.nb));
         const int bn = choose_bn(C4, P.m_tiles);
-        DLA(make_b_map(&P.b_map, D->wef, Cp, C4, 9 * wm, bn));
+        DLA(make_b_map(P, D->wef, Cp, C4, 9 * wm, bn));
         P.kchunks = Cp / 64;
         fwd_epi(P, D, d.d_b4_conv_bias, D->x5, kSqrt2, d.conv_clamp, C4, bn, 4);
         P.err_flag = D->err_flag;
@@ -670,7 +670,7 @@ int build_disc(la_disc* D) {
         for (int hw = 0; hw < 16; ++hw) add_tap(P, nt, hw / 4, hw % 4, hw, 0, 1, 16, split);
         P.prob[0].tap_begin = 0; P.prob[0].ntaps = nt;
         const int bn = 64;
-        DLA(make_b_map(&P.b_map, D->wff, C4, C4, 16 * wm, bn));
+        DLA(make_b_map(P, D->wff, C4, C4, 16 * wm, bn));
         P.kchunks = C4 / 64;
         fwd_epi(P, D, d.d_b4_fc_bias, D->x6, kSqrt2, -1.f, C4, bn, 1);
         P.staged = 0;
@@ -683,7 +683,7 @@ int build_disc(la_disc* D) {
         sample_rows(P);
         DLA(dense_maps(D, P, 0, 1, D->gz6, C4, 1, 1, 1, 1, 128));
         const int bn = 64;
-        DLA(make_b_map(&P.b_map, D->wfb, C4, 16 * C4, wm, bn));
+        DLA(make_b_map(P, D->wfb, C4, 16 * C4, wm, bn));
         P.kchunks = C4 / 64;
         lin_epi(P, D, 16 * C4, bn, 1, 1);
         P.lin_saved = D->x5.hi; P.lin_gz = D->gz5.hi; P.lin_gz_lo = D->gz5.lo;
@@ -697,7 +697,7 @@ int build_disc(la_disc* D) {
         set_grid(P, 4, B, 1);
         DLA(dense_maps(D, P, 0, 1, D->gz5, C4, 4, 4, P.tw, P.th + P.halo, P.nb));
         const int bn = 64;
-        DLA(make_b_map(&P.b_map, D->web, C4, Cp, 9 * wm, bn));
+        DLA(make_b_map(P, D->web, C4, Cp, 9 * wm, bn));
         P.kchunks = C4 / 64;
         lin_epi(P, D, Cp, bn, 4, 4);
         P.lin_out = D->gx4p.hi; P.lin_out_lo = D->gx4p.lo;

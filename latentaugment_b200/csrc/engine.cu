@@ -232,7 +232,7 @@ int plan(la_engine* e, char* ws, size_t* bytes_out) {
     e->step = bp.take<int>(1);
     e->err_flag = bp.take<int>(1);
     e->disc_loss = bp.take<float>(1);
-    e->dbg_clock = bp.take<unsigned long long>(2);
+    e->dbg_clock = bp.take<unsigned long long>(64);
     const size_t wn = static_cast<size_t>(B) * g.w_dim;
     e->w_opt = bp.take<float>(wn); e->m = bp.take<float>(wn); e->v = bp.take<float>(wn);
     e->w0 = bp.take<float>(wn); e->w_aug = bp.take<float>(wn);
@@ -276,7 +276,7 @@ int build_params(la_engine* e) {
         set_ops_dims(c.fwd_ops, c.res_in, c.res_in);
         c.fwd_ops.w = c.wf;
         const int bn = pick_bn(c.cout, F.m_tiles);
-        LA(make_b_map(&F.b_map, c.wf, c.cin, c.cout, nmat * (split ? 2 : 1), bn));
+        LA(make_b_map(F, c.wf, c.cin, c.cout, nmat * (split ? 2 : 1), bn));
         int nt = 0;
         for (int ph = 0; ph < F.nprob; ++ph) {
             F.prob[ph].tap_begin = nt;
@@ -412,7 +412,7 @@ int build_params(la_engine* e) {
         F.no_pair = G.no_pair = getenv("LA_NO_PAIR") != nullptr;
         F.dbg_skip_epi = G.dbg_skip_epi = getenv("LA_DBG_SKIP_EPI") != nullptr;     // timing experiment: wrong results
         const int bnb = pick_bn(c.cin, G.m_tiles);
-        LA(make_b_map(&G.b_map, c.wb, c.cout, c.cin, nmat * (split ? 2 : 1), bnb));
+        LA(make_b_map(G, c.wb, c.cout, c.cin, nmat * (split ? 2 : 1), bnb));
         G.kchunks = c.cout / 64; G.n_total = c.cin; G.n_blocks = c.cin / bnb;
         G.epilogue = kEpiBwd;
         G.OH = G.OW = c.res_in; G.osy = G.osx = 1; G.split = split;
@@ -886,9 +886,17 @@ LA_API int la_debug_time_gemms(la_engine* e, int reps, float* h_ms, int* n_layer
         cudaEventElapsedTime(&ms, a, b);
         h_ms[idx] = ms / reps;
         if (dbg_clk && !simt) {
-            unsigned long long hc[2] = {0, 1};
+            unsigned long long hc[64] = {0, 1, 0, 0, 0, 0, 0, 0};
             cudaMemcpy(hc, e->dbg_clock, sizeof hc, cudaMemcpyDeviceToHost);
-            fprintf(stderr, "[clk] gemm %2d: %.3f ms, CTA0 %.0f MHz over %.3f ms\n", idx, h_ms[idx], 1e3 * hc[0] / hc[1], hc[1] * 1e-6);
+            fprintf(stderr, "[clk] gemm %2d: %.3f ms, CTA0 %.0f MHz over %.3f ms | us since CTA start: roles %.1f, first operands %.1f, unit 0 issued %.1f, all %llu units issued %.1f, exit %.1f\n",
+                    idx, h_ms[idx], 1e3 * hc[0] / hc[1], hc[1] * 1e-6, (hc[2] - hc[7]) * 1e-3, (hc[3] - hc[7]) * 1e-3,
+                    (hc[4] - hc[7]) * 1e-3, hc[6], (hc[5] - hc[7]) * 1e-3, hc[1] * 1e-3);
+            fprintf(stderr, "[clk]    MMA thread waited (us): accumulator free %.1f, A landed %.1f, B landed %.1f\n", hc[60] * 1e-3, hc[61] * 1e-3, hc[62] * 1e-3);
+            if (getenv("LA_DBG_STEPS")) {
+                fprintf(stderr, "[clk]    A-group issue -> landed (us since CTA start):");
+                for (int k = 0; k < 28; ++k) fprintf(stderr, " %.2f>%.2f", (hc[8 + 2 * k] - hc[7]) * 1e-3, (hc[9 + 2 * k] - hc[7]) * 1e-3);
+                fprintf(stderr, "\n");
+            }
         }
         return 0;
     };

@@ -30,7 +30,7 @@ struct WarpSmem {                     // (row data is double-buffered: the next 
     unsigned off[2][32];              // per row: pixel index * N/2 (offset of the row in bf16x2 units), kRowMasked = masked
 };
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool kPair = false>
 struct Cfg {
     static constexpr int kMtMax = BN == 256 ? 1 : 2;             // M tiles per unit (they share every weight tile)
     static constexpr int kASlotBytes = kMtMax * kASubBytes;
@@ -45,7 +45,10 @@ struct Cfg {
     static constexpr int kCoefBytes = EPI == kEpiFwd ? 2 * 6 * BN * 4 : 0;
     static constexpr int kEpiSmemBytes = EPI == kEpiBwd ? 8 * static_cast<int>(sizeof(WarpSmem)) : 8 * 2048 * kStageTensors + kCoefBytes;
     static constexpr int kABytes = kAStages * kASlotBytes;       // unpaired launches cut this region into kASubBytes slots
-    static constexpr int kSmemBytes = kABytes + kBStages * kBBytes + kEpiSmemBytes + 320 /*barriers*/ + 1024 /*align slack*/;
+    // CTA pairs: each CTA holds half a weight tile per stage, so the same bytes give a ring twice as deep
+    static constexpr int kBSlotBytes = kPair ? kBBytes / 2 : kBBytes;
+    static constexpr int kBRing = kPair ? 2 * kBStages : kBStages;
+    static constexpr int kSmemBytes = kABytes + kBStages * kBBytes + kEpiSmemBytes + 512 /*barriers*/ + 1024 /*align slack*/;
     static constexpr int kBwdSteps = BN == 64 ? 2 : 4;           // 32-column steps one warp walks per tile (all of BN, or half of it)
 };
 
@@ -113,6 +116,15 @@ __device__ __forceinline__ Unit get_unit(const TapGemmParams& P, int t, int t_en
     return u;
 }
 
+// CTA-pair launches (cta_group::2): the two M tiles of a unit go to the two CTAs of the cluster.  A CTA without a
+// tile of its own (odd tile at a range or problem boundary) loads tile 0 again and runs its epilogue with every
+// row masked, so both CTAs walk the same barrier sequence.
+__device__ __forceinline__ TileCoord pair_tile(const Unit& u, uint32_t rank) {
+    TileCoord tc = (rank == 1u && u.mt == 2) ? u.tc1 : u.tc0;
+    if (static_cast<int>(rank) >= u.mt) tc.empty = true;
+    return tc;
+}
+
 // Contiguous, COST-balanced tile range of this CTA.  The phases of the transposed convolution have 4 / 2 / 2 / 1
 // taps; a tile costs (taps x K chunks) MMA steps plus a fixed epilogue share worth about four steps (measured:
 // with taps alone the CTAs that own the one-tap phase finish 35 % after the others).  Tiles are ordered
@@ -133,20 +145,23 @@ __device__ __forceinline__ long long tiles_before(const TapGemmParams& P, long l
     }
     return count;
 }
-__device__ __forceinline__ void tile_range(const TapGemmParams& P, int& begin, int& end) {
+__device__ __forceinline__ void tile_range(const TapGemmParams& P, int& begin, int& end, int worker, int nworkers) {
     if (P.interleave) {      // every group of 2 * nprob tiles costs the same: split the groups evenly
         const int per = 2 * P.nprob;
         const long long groups = static_cast<long long>(P.n_blocks) * (P.m_tiles / per);
-        begin = static_cast<int>(groups * blockIdx.x / gridDim.x) * per;
-        end = static_cast<int>(groups * (blockIdx.x + 1) / gridDim.x) * per;
+        begin = static_cast<int>(groups * worker / nworkers) * per;
+        end = static_cast<int>(groups * (worker + 1) / nworkers) * per;
         return;
     }
     long long cost = 0;
     for (int p = 0; p < P.nprob; ++p)
         cost += static_cast<long long>(P.prob[p].tiles_h) * P.prob[p].tiles_w * P.tiles_n * tile_cost(P, P.prob[p]);
     const long long total = cost * P.n_blocks;
-    begin = static_cast<int>(tiles_before(P, cost, total * blockIdx.x / gridDim.x));
-    end = static_cast<int>(tiles_before(P, cost, total * (blockIdx.x + 1) / gridDim.x));
+    begin = static_cast<int>(tiles_before(P, cost, total * worker / nworkers));
+    end = static_cast<int>(tiles_before(P, cost, total * (worker + 1) / nworkers));
+}
+__device__ __forceinline__ void tile_range(const TapGemmParams& P, int& begin, int& end) {
+    tile_range(P, begin, end, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x));
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -231,7 +246,7 @@ __device__ __forceinline__ RowCtx make_row(const TapGemmParams& P, const TileCoo
     const int wi = rem - hi * P.tw;
     const int n = tc.n0 + ni, h = tc.h0 + hi, w = tc.w0 + wi;
     const TapProblem& pr = P.prob[tc.prob];
-    r.valid = (ni < P.nb) && (n < P.batch) && (h < pr.vh) && (w < pr.vw);
+    r.valid = !tc.empty && (ni < P.nb) && (n < P.batch) && (h < pr.vh) && (w < pr.vw);
     r.n = n;
     const int oh = h * P.osy + pr.oy0, ow = w * P.osx + pr.ox0;
     r.px_in_img = static_cast<long long>(oh) * P.OW + ow;
@@ -759,31 +774,42 @@ __device__ __forceinline__ EpiSplit<BN> epi_split(int mt, int sub) {
 }
 
 // ------------------------------------------------------------------------------------
-template <int BN, int EPI>
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+template <int BN, int EPI, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams P) {
-    using C = Cfg<BN, EPI>;
+    using C = Cfg<BN, EPI, kPair>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
     uint8_t* a_smem = smem;
     uint8_t* b_smem = smem + C::kAStages * C::kASlotBytes;
-    uint8_t* epi_smem = b_smem + C::kBStages * C::kBBytes;
+    uint8_t* epi_smem = b_smem + C::kBRing * C::kBSlotBytes;
     constexpr int kMaxAStages = 8;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(epi_smem + C::kEpiSmemBytes);
     uint64_t* a_empty = a_full + kMaxAStages;
     uint64_t* b_full = a_empty + kMaxAStages;
-    uint64_t* b_empty = b_full + C::kBStages;
-    uint64_t* tfull_bar = b_empty + C::kBStages;
+    uint64_t* b_empty = b_full + C::kBRing;
+    uint64_t* tfull_bar = b_empty + C::kBRing;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    static_assert((2 * kMaxAStages + 2 * C::kBStages + 4) * 8 + 4 <= 320, "barrier area");
+    static_assert((2 * kMaxAStages + 2 * C::kBRing + 4) * 8 + 4 <= 512, "barrier area");
     // A ring: slots of one M tile when the launch never pairs tiles (twice as many stages in flight)
-    const int a_slot_bytes = (C::kMtMax == 2 && !P.no_pair) ? 2 * kASubBytes : kASubBytes;
+    constexpr bool pair = kPair;                                    // CTA pair: M = 256 MMAs issued by cluster rank 0
+    uint32_t rank = 0u;
+    if constexpr (kPair) rank = cluster_ctarank();
+    const int a_slot_bytes = (C::kMtMax == 2 && !P.no_pair && !pair) ? 2 * kASubBytes : kASubBytes;
     const int a_stages = min(kMaxAStages, C::kABytes / a_slot_bytes);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     int t_begin, t_end;
-    tile_range(P, t_begin, t_end);
+    if (pair) tile_range(P, t_begin, t_end, static_cast<int>(blockIdx.x >> 1), static_cast<int>(gridDim.x >> 1));
+    else tile_range(P, t_begin, t_end);
+    auto unit_at = [&](int t) { return pair ? get_unit<2>(P, t, t_end) : get_unit<C::kMtMax>(P, t, t_end); };
     unsigned long long dbg_c0 = 0, dbg_t0 = 0;
     if (P.dbg_clock && blockIdx.x == 0 && threadIdx.x == 64) {
         dbg_c0 = clock64();
@@ -796,16 +822,20 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kMaxAStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-        for (int s = 0; s < C::kBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < C::kBRing; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], kEpiThreads / 32);
+            mbar_init(&tempty_bar[a], (pair ? 2 : 1) * (kEpiThreads / 32));      // (pair: the peer's warps arrive on the leader's)
         }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc<C::kTmemCols>(tmem_slot);
+    if (warp == 2) {
+        if constexpr (kPair) tmem_alloc_pair<C::kTmemCols>(tmem_slot);
+        else tmem_alloc<C::kTmemCols>(tmem_slot);
+    }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) cluster_sync_all();       // the peer's barriers must be initialised before anything arrives on them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -814,79 +844,199 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
 
     if (warp < 4) {
         setmaxnreg_dec<kRegsProducer>();
-        if (warp == 0 && lane == 0) {
-            // ---------------------------------------------------------------- TMA producer
-            int as = 0, bs = 0;
-            uint32_t aph = 0, bph = 0;
+        if (warp == 0) {
+            // ---------------------------------------------------------------- TMA producer of the A ring (whole warp, one elected lane issues)
+            // (the two rings have separate producer threads: at 128^2 and 256^2 the activations come from DRAM with
+            // 2-3 us of latency while the weights sit in L2 -- one thread issuing both in order stalls the A stream on
+            // the shallow B ring and leaves most of the A ring empty)
+            int as = 0;
+            uint32_t aph = 0;
+            const bool dbg = P.dbg_clock && blockIdx.x == 0 && lane == 0;
+            int dbg_step = 0;
             for (int t = t_begin; t < t_end;) {
-                const Unit u = get_unit<C::kMtMax>(P, t, t_end);
+                const Unit u = unit_at(t);
                 t += u.adv;
                 if (u.mt == 0) continue;
-                const TapProblem& pr = P.prob[u.tc0.prob];
+                const TileCoord tc0 = kPair ? pair_tile(u, rank) : u.tc0;      // (pair: this CTA's own M tile)
+                const TapProblem& pr = P.prob[tc0.prob];
                 for (int g = 0; g < pr.ngroups; ++g) {
                     const TapGroup grp = P.groups[pr.grp_begin + g];
                     const CUtensorMap* amap = &P.a_map[grp.src];
                     for (int kc = 0; kc < P.kchunks; ++kc) {
                         mbar_wait(&a_empty[as], aph ^ 1, P.err_flag, 1);
+                        if (dbg && dbg_step < 28) P.dbg_clock[8 + 2 * dbg_step++] = global_timer_ns();
                         uint8_t* sa = a_smem + as * a_slot_bytes;
-                        mbar_expect_tx(&a_full[as], a_tx_bytes * u.mt);
-                        tma_load_4d(sa, amap, &a_full[as], kc * kBlockK, u.tc0.w0 + grp.dx, u.tc0.h0 + grp.dy0, u.tc0.n0);
-                        if (u.mt == 2)
-                            tma_load_4d(sa + kASubBytes, amap, &a_full[as], kc * kBlockK, u.tc1.w0 + grp.dx, u.tc1.h0 + grp.dy0, u.tc1.n0);
+                        if (elect_one()) {
+                            if constexpr (kPair) {
+                                // all bytes of the pair are counted on the LEADER's barrier; it alone posts the expected total
+                                if (rank == 0) mbar_expect_tx(&a_full[as], 2 * a_tx_bytes);
+                                tma_load_4d_pair(sa, amap, mapa_shared(smem_u32(&a_full[as]), 0), kc * kBlockK, tc0.w0 + grp.dx, tc0.h0 + grp.dy0, tc0.n0);
+                            } else {
+                                mbar_expect_tx(&a_full[as], a_tx_bytes * u.mt);
+                                tma_load_4d(sa, amap, &a_full[as], kc * kBlockK, u.tc0.w0 + grp.dx, u.tc0.h0 + grp.dy0, u.tc0.n0);
+                                if (u.mt == 2)
+                                    tma_load_4d(sa + kASubBytes, amap, &a_full[as], kc * kBlockK, u.tc1.w0 + grp.dx, u.tc1.h0 + grp.dy0, u.tc1.n0);
+                            }
+                        }
+                        __syncwarp();
                         if (++as == a_stages) { as = 0; aph ^= 1; }
+                    }
+                }
+            }
+        } else if (warp == 3) {
+            // ---------------------------------------------------------------- TMA producer of the B ring (whole warp, one elected lane issues)
+            int bs = 0;
+            uint32_t bph = 0;
+            const int b_row0 = kPair ? static_cast<int>(rank) * (BN / 2) : 0;      // (pair: this CTA's half of the column block)
+            for (int t = t_begin; t < t_end;) {
+                const Unit u = unit_at(t);
+                t += u.adv;
+                if (u.mt == 0) continue;
+                const TapProblem& pr = P.prob[u.tc0.prob];
+                for (int g = 0; g < pr.ngroups; ++g) {
+                    const TapGroup grp = P.groups[pr.grp_begin + g];
+                    for (int kc = 0; kc < P.kchunks; ++kc) {
                         for (int j = 0; j < grp.ntaps; ++j) {
                             mbar_wait(&b_empty[bs], bph ^ 1, P.err_flag, 5);
-                            mbar_expect_tx(&b_full[bs], C::kBBytes);
-                            tma_load_3d(b_smem + bs * C::kBBytes, &P.b_map, &b_full[bs], kc * kBlockK, u.tc0.nblk * BN,
-                                        P.gwidx[grp.tap_begin + j]);
-                            if (++bs == C::kBStages) { bs = 0; bph ^= 1; }
+                            uint8_t* sb = b_smem + bs * C::kBSlotBytes;
+                            if (elect_one()) {
+                                if constexpr (kPair) {
+                                    if (rank == 0) mbar_expect_tx(&b_full[bs], C::kBBytes);
+                                    tma_load_3d_pair(sb, &P.b_map, mapa_shared(smem_u32(&b_full[bs]), 0), kc * kBlockK, u.tc0.nblk * BN + b_row0,
+                                                     P.gwidx[grp.tap_begin + j]);
+                                } else {
+                                    mbar_expect_tx(&b_full[bs], C::kBBytes);
+                                    tma_load_3d(sb, &P.b_map, &b_full[bs], kc * kBlockK, u.tc0.nblk * BN, P.gwidx[grp.tap_begin + j]);
+                                }
+                            }
+                            __syncwarp();
+                            if (++bs == C::kBRing) { bs = 0; bph ^= 1; }
                         }
                     }
                 }
             }
-        } else if (warp == 1 && lane == 0) {
-            // ---------------------------------------------------------------- MMA issuer
+        } else if (kPair && warp == 1) {
+            // ---------------------------------------------------------------- MMA issuer of a CTA pair (leader only)
+            // (the whole warp walks the loop so that control flow and descriptors stay warp-uniform; one elected
+            // lane issues -- a single diverged lane makes the compiler wrap every MMA in a broadcast loop)
+            if (rank == 0) {
+                constexpr uint32_t idesc2 = make_idesc_bf16(2 * kBlockM, BN);
+                int as = 0, bs = 0;
+                uint32_t aph = 0, bph = 0;
+                int acc = 0;
+                uint32_t acc_phase = 0;
+                const bool dbg = P.dbg_clock && blockIdx.x == 0 && lane == 0;
+                int dbg_units = 0, dbg_step = 0;
+                if (dbg) P.dbg_clock[2] = global_timer_ns();
+                for (int t = t_begin; t < t_end;) {
+                    const Unit u = get_unit<2>(P, t, t_end);
+                    t += u.adv;
+                    if (u.mt == 0) continue;
+                    const TapProblem& pr = P.prob[u.tc0.prob];
+                    mbar_wait(&tempty_bar[acc], acc_phase ^ 1, P.err_flag, 2);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * C::kMtMax * BN);
+                    bool first = true;
+                    for (int g = 0; g < pr.ngroups; ++g) {
+                        const TapGroup grp = P.groups[pr.grp_begin + g];
+                        for (int kc = 0; kc < P.kchunks; ++kc) {
+                            mbar_wait(&a_full[as], aph, P.err_flag, 3);
+                            if (dbg && dbg_step < 28) P.dbg_clock[9 + 2 * dbg_step++] = global_timer_ns();
+                            const uint32_t sa = smem_u32(a_smem + as * a_slot_bytes);
+                            for (int j = 0; j < grp.ntaps; ++j) {
+                                mbar_wait(&b_full[bs], bph, P.err_flag, 6);
+                                tc_fence_after();
+                                if (dbg && first && dbg_units == 0) P.dbg_clock[3] = global_timer_ns();
+                                const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(b_smem + bs * C::kBSlotBytes));
+                                const uint64_t adesc = make_sw128_kmajor_desc(sa + P.gdyrel[grp.tap_begin + j] * dy_bytes);
+                                if (elect_one()) {
+#pragma unroll
+                                    for (int k = 0; k < kBlockK / 16; ++k)
+                                        umma_bf16_pair(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc2,
+                                                       (first && k == 0) ? 0u : 1u);
+                                    umma_commit_pair(&b_empty[bs]);
+                                }
+                                __syncwarp();
+                                first = false;
+                                if (++bs == C::kBRing) { bs = 0; bph ^= 1; }
+                            }
+                            if (elect_one()) umma_commit_pair(&a_empty[as]);
+                            __syncwarp();
+                            if (++as == a_stages) { as = 0; aph ^= 1; }
+                        }
+                    }
+                    if (elect_one()) umma_commit_pair(&tfull_bar[acc]);
+                    __syncwarp();
+                    if (dbg && dbg_units++ == 0) P.dbg_clock[4] = global_timer_ns();
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+                if (dbg) { P.dbg_clock[5] = global_timer_ns(); P.dbg_clock[6] = static_cast<unsigned long long>(dbg_units); }
+            }
+        } else if (warp == 1) {
+            // ---------------------------------------------------------------- MMA issuer (whole warp, one elected lane issues)
             constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN);
             int as = 0, bs = 0;
             uint32_t aph = 0, bph = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            const bool dbg = P.dbg_clock && blockIdx.x == 0 && lane == 0;
+            int dbg_units = 0, dbg_step = 0;
+            unsigned long long dbg_wait_acc = 0, dbg_wait_a = 0, dbg_wait_b = 0;
+            if (dbg) P.dbg_clock[2] = global_timer_ns();
             for (int t = t_begin; t < t_end;) {
                 const Unit u = get_unit<C::kMtMax>(P, t, t_end);
                 t += u.adv;
                 if (u.mt == 0) continue;
                 const TapProblem& pr = P.prob[u.tc0.prob];
+                unsigned long long w0 = dbg ? global_timer_ns() : 0ull;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1, P.err_flag, 2);
+                if (dbg) dbg_wait_acc += global_timer_ns() - w0;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * C::kMtMax * BN);
                 bool first = true;
                 for (int g = 0; g < pr.ngroups; ++g) {
                     const TapGroup grp = P.groups[pr.grp_begin + g];
                     for (int kc = 0; kc < P.kchunks; ++kc) {
+                        w0 = dbg ? global_timer_ns() : 0ull;
                         mbar_wait(&a_full[as], aph, P.err_flag, 3);
+                        if (dbg) dbg_wait_a += global_timer_ns() - w0;
+                        if (dbg && dbg_step < 28) P.dbg_clock[9 + 2 * dbg_step++] = global_timer_ns();
                         const uint32_t sa = smem_u32(a_smem + as * a_slot_bytes);
                         for (int j = 0; j < grp.ntaps; ++j) {
+                            w0 = dbg ? global_timer_ns() : 0ull;
                             mbar_wait(&b_full[bs], bph, P.err_flag, 6);
+                            if (dbg) dbg_wait_b += global_timer_ns() - w0;
                             tc_fence_after();
-                            const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(b_smem + bs * C::kBBytes));
+                            if (dbg && first && dbg_units == 0) P.dbg_clock[3] = global_timer_ns();
+                            const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(b_smem + bs * C::kBSlotBytes));
                             const uint32_t a_tap = sa + P.gdyrel[grp.tap_begin + j] * dy_bytes;
-                            for (int s = 0; s < u.mt; ++s) {
-                                const uint64_t adesc = make_sw128_kmajor_desc(a_tap + s * kASubBytes);
+                            if (elect_one()) {
+                                for (int s = 0; s < u.mt; ++s) {
+                                    const uint64_t adesc = make_sw128_kmajor_desc(a_tap + s * kASubBytes);
 #pragma unroll
-                                for (int k = 0; k < kBlockK / 16; ++k)
-                                    umma_bf16(d_tmem + static_cast<uint32_t>(s * BN), adesc + static_cast<uint64_t>(k * 2),
-                                              bdesc + static_cast<uint64_t>(k * 2), idesc, (first && k == 0) ? 0u : 1u);
+                                    for (int k = 0; k < kBlockK / 16; ++k)
+                                        umma_bf16(d_tmem + static_cast<uint32_t>(s * BN), adesc + static_cast<uint64_t>(k * 2),
+                                                  bdesc + static_cast<uint64_t>(k * 2), idesc, (first && k == 0) ? 0u : 1u);
+                                }
+                                umma_commit(&b_empty[bs]);
                             }
+                            __syncwarp();
                             first = false;
-                            umma_commit(&b_empty[bs]);
-                            if (++bs == C::kBStages) { bs = 0; bph ^= 1; }
+                            if (++bs == C::kBRing) { bs = 0; bph ^= 1; }
                         }
-                        umma_commit(&a_empty[as]);
+                        if (elect_one()) umma_commit(&a_empty[as]);
+                        __syncwarp();
                         if (++as == a_stages) { as = 0; aph ^= 1; }
                     }
                 }
-                umma_commit(&tfull_bar[acc]);
+                if (elect_one()) umma_commit(&tfull_bar[acc]);
+                __syncwarp();
+                if (dbg && dbg_units++ == 0) P.dbg_clock[4] = global_timer_ns();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+            if (dbg) {
+                P.dbg_clock[5] = global_timer_ns(); P.dbg_clock[6] = static_cast<unsigned long long>(dbg_units);
+                P.dbg_clock[60] = dbg_wait_acc; P.dbg_clock[61] = dbg_wait_a; P.dbg_clock[62] = dbg_wait_b;
             }
         }
     } else {
@@ -896,10 +1046,12 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
         const int q = e & 3, sub = e >> 2;          // TMEM lane quarter (= warp % 4), warp group
         if constexpr (EPI == kEpiBwd) {
             WarpSmem* ws = reinterpret_cast<WarpSmem*>(epi_smem) + e;
+            const uint32_t tempty_lead[2] = {pair ? mapa_shared(smem_u32(&tempty_bar[0]), 0) : 0u, pair ? mapa_shared(smem_u32(&tempty_bar[1]), 0) : 0u};
             auto tile_at = [&](int t, BwdTile& bt, int& adv) {
-                const Unit u = get_unit<C::kMtMax>(P, t, t_end);     // (the backward GEMMs are single-problem: never empty)
-                const EpiSplit<BN> sp = epi_split<BN>(u.mt, sub);
-                bt.tc = u.tile(sp.st); bt.step0 = sp.ch_begin; bt.nsteps = sp.ch_end - sp.ch_begin; bt.sub_tile = sp.st;
+                const Unit u = unit_at(t);     // (the backward GEMMs are single-problem: never empty)
+                const EpiSplit<BN> sp = epi_split<BN>(pair ? 1 : u.mt, sub);
+                bt.tc = pair ? pair_tile(u, rank) : u.tile(sp.st);
+                bt.step0 = sp.ch_begin; bt.nsteps = sp.ch_end - sp.ch_begin; bt.sub_tile = sp.st;
                 adv = u.adv;
             };
             auto chunk_loader = [&](int it, const BwdTile& bt) {
@@ -925,10 +1077,15 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
             };
             auto releaser = [&](int it) {
                 uint64_t* bar = &tempty_bar[it & 1];
+                const uint32_t lead = tempty_lead[it & 1];
+                const bool remote = pair && rank != 0;
                 return [=]() {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar);
+                    if (lane == 0) {
+                        if (remote) mbar_arrive_cluster(lead);
+                        else mbar_arrive(bar);
+                    }
                 };
             };
             if (P.split) bwd_warp_loop<BN, C::kBwdSteps, true>(P, q, lane, ws, t_begin, t_end, tile_at, chunk_loader, releaser);
@@ -938,11 +1095,11 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
             uint32_t acc_phase = 0;
             int coef_key = -1;
             for (int t = t_begin; t < t_end;) {
-                const Unit u = get_unit<C::kMtMax>(P, t, t_end);
+                const Unit u = unit_at(t);
                 t += u.adv;
                 if (u.mt == 0) continue;
-                const EpiSplit<BN> sp = epi_split<BN>(u.mt, sub);
-                const TileCoord tc = u.tile(sp.st);
+                const EpiSplit<BN> sp = epi_split<BN>(pair ? 1 : u.mt, sub);
+                const TileCoord tc = pair ? pair_tile(u, rank) : u.tile(sp.st);
                 const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                         static_cast<uint32_t>((acc * C::kMtMax + sp.st) * BN);
                 bool waited = false;
@@ -984,23 +1141,35 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
                 } else {
                     rowowner_warp_tile<BN, EPI, false>(P, tc, q, lane, sp.ch_begin, sp.ch_end, sp.whole ? 0 : sub, sp.whole, nullptr, nullptr, load_chunk);
                 }
+                if (!waited) {            // (a tile with every row masked may never have touched its accumulator)
+                    mbar_wait(&tfull_bar[acc], acc_phase, P.err_flag, 4);
+                    tc_fence_after();
+                }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                if (lane == 0) {
+                    if (pair && rank != 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
+                    else mbar_arrive(&tempty_bar[acc]);
+                }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) cluster_sync_all();       // no CTA may leave while its partner still arrives on its barriers or reads its operands
+    else __syncthreads();
     if (P.dbg_clock && blockIdx.x == 0 && threadIdx.x == 64) {
         unsigned long long t1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
         P.dbg_clock[0] = clock64() - dbg_c0;
         P.dbg_clock[1] = t1 - dbg_t0;
+        P.dbg_clock[7] = dbg_t0;
     }
-    if (warp == 2) tmem_dealloc<C::kTmemCols>(tmem_base);
+    if (warp == 2) {
+        if constexpr (kPair) tmem_dealloc_pair<C::kTmemCols>(tmem_base);
+        else tmem_dealloc<C::kTmemCols>(tmem_base);
+    }
 }
 
 // ------------------------------------------------------------------------------------
@@ -1268,15 +1437,20 @@ __global__ void __launch_bounds__(128) seed_bulk_kernel(const __grid_constant__ 
     }
 }
 
-template <int BN, int EPI>
-int launch_bn_epi(const TapGemmParams& p, int num_sms, cudaStream_t stream) {
+template <int BN, int EPI, bool kPair>
+int set_smem_attr() {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Cfg<BN, EPI>::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BN, EPI, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg<BN, EPI, kPair>::kSmemBytes);
         if (e != cudaSuccess) return static_cast<int>(e);
         attr_set = true;
     }
+    return 0;
+}
+
+template <int BN, int EPI>
+int launch_bn_epi(const TapGemmParams& p, int num_sms, cudaStream_t stream) {
     static_assert(Cfg<BN, EPI>::kSmemBytes <= 232448, "shared memory budget");
     const int total = p.m_tiles * p.n_blocks;
     int grid = total < num_sms ? total : num_sms;
@@ -1286,12 +1460,36 @@ int launch_bn_epi(const TapGemmParams& p, int num_sms, cudaStream_t stream) {
     if (p.halo != 0 && (p.halo != 2 || p.tw != 8 || p.nb != 1 || p.th != 16)) return static_cast<int>(cudaErrorInvalidValue);
     if (p.interleave && (p.epilogue == kEpiBwd || p.m_tiles % (2 * p.nprob))) return static_cast<int>(cudaErrorInvalidValue);
     if (p.nb * (p.th + p.halo) * p.tw * 128 > kASubBytes) return static_cast<int>(cudaErrorInvalidValue);
+    if (p.cta2) {
+        // CTA pairs: clusters of two CTAs (one TPC), each cluster walks a cost-balanced range of tile pairs
+        if constexpr (EPI == kEpiTopK) {
+            return static_cast<int>(cudaErrorInvalidValue);
+        } else {
+            if (p.interleave) return static_cast<int>(cudaErrorInvalidValue);
+            if (int r = set_smem_attr<BN, EPI, true>()) return r;
+            const int clusters = (total + 1) / 2 < num_sms / 2 ? (total + 1) / 2 : num_sms / 2;
+            TapGemmParams q = p;
+            q.no_pair = 0;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(static_cast<unsigned>(2 * clusters));
+            cfg.blockDim = dim3(kThreads);
+            cfg.dynamicSmemBytes = Cfg<BN, EPI, true>::kSmemBytes;
+            cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            return static_cast<int>(cudaLaunchKernelEx(&cfg, tapgemm_kernel<BN, EPI, true>, q));
+        }
+    }
+    if (int r = set_smem_attr<BN, EPI, false>()) return r;
     if (total <= num_sms && !p.no_pair) {       // one tile per CTA: nothing to pair, so run the deeper unpaired A ring
         TapGemmParams q = p;
         q.no_pair = 1;
-        tapgemm_kernel<BN, EPI><<<grid, kThreads, Cfg<BN, EPI>::kSmemBytes, stream>>>(q);
+        tapgemm_kernel<BN, EPI, false><<<grid, kThreads, Cfg<BN, EPI>::kSmemBytes, stream>>>(q);
     } else {
-        tapgemm_kernel<BN, EPI><<<grid, kThreads, Cfg<BN, EPI>::kSmemBytes, stream>>>(p);
+        tapgemm_kernel<BN, EPI, false><<<grid, kThreads, Cfg<BN, EPI>::kSmemBytes, stream>>>(p);
     }
     return static_cast<int>(cudaGetLastError());
 }

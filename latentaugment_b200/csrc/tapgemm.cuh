@@ -71,6 +71,7 @@ struct TapGemmParams {
     uint8_t gwidx[kMaxTaps];         // per grouped tap: weight matrix
     int halo;                        // extra rows of the A box (0 or 2); 2 needs tw == 8 and nb == 1
     int no_pair;                     // 1: never pair M tiles (tuning switch)
+    int cta2;                        // 1: CTA pairs (clusters of 2, cta_group::2 MMAs with M = 256): the b_map box holds HALF a column block
     int interleave;                  // 1: all problems share one tile grid (tiles_h/w equal, vh/vw mask) and are walked
                                      //    [column block][pair of spatial tiles][problem][tile of the pair], so that every
                                      //    CTA gets the same mix of cheap and expensive problems
@@ -139,7 +140,7 @@ struct TapGemmParams {
     int* cand_idx;                     // [n_queries][n_blocks][2][topk]
 
     int* err_flag;
-    unsigned long long* dbg_clock;     // optional [2]: SM cycles and nanoseconds CTA 0 spent in the kernel (clock-under-load experiments)
+    unsigned long long* dbg_clock;     // optional [64]: CTA 0 cycles, nanoseconds and MMA-thread timeline stamps (LA_DBG_CLK experiments)
 };
 
 // Groups the flat taps of every problem (call after taps / prob[].tap_begin / ntaps are set).  Returns 0 on success.
