@@ -276,7 +276,7 @@ int build_params(la_engine* e) {
         set_ops_dims(c.fwd_ops, c.res_in, c.res_in);
         c.fwd_ops.w = c.wf;
         const int bn = pick_bn(c.cout, F.m_tiles);
-        LA(make_b_map(F, c.wf, c.cin, c.cout, nmat * (split ? 2 : 1), bn));
+        LA(make_b_map(F, c.wf, c.cin, c.cout, nmat * (split ? 2 : 1), bn, c.split_up ? 0 : 1));
         int nt = 0;
         for (int ph = 0; ph < F.nprob; ++ph) {
             F.prob[ph].tap_begin = nt;

@@ -39,9 +39,10 @@ inline int make_a_map(CUtensorMap* m, const void* base, int C, int W, int H, int
     uint32_t box[4] = {64, static_cast<uint32_t>(tw), static_cast<uint32_t>(th), static_cast<uint32_t>(nb)};
     return encode_tmap_bf16(m, base, 4, dims, strides, box);
 }
-// CTA pairs (cta_group::2, M = 256 MMAs over two SMs) wherever the column block is not 128 wide: measured on the
-// C2 layers they are 8-12 % faster at BN = 256 / 64 (each SM reads half the weight tile), but slower at BN = 128,
-// where the single-CTA kernel pairs two M tiles per CTA and gives every epilogue warp group a whole tile.
+// CTA pairs (cta_group::2, M = 256 MMAs over two SMs, each SM reading half the weight tile): measured on the C2
+// layers 8-12 % faster at BN = 256 / 64.  At BN = 128 a pair works on four M tiles (two per CTA); that wins for
+// the plain forward convolutions (-13 %), and loses or ties for the data-gradient and up-sampling launches, whose
+// epilogues set the pace -- those stay on the single-CTA kernel (callers say which with pair128).
 // LA_CTA2=0: never, LA_CTA2=2: always (tuning / A-B switch).
 inline int pair_mode() {
     static const int v = getenv("LA_CTA2") ? atoi(getenv("LA_CTA2")) : 1;
@@ -49,8 +50,8 @@ inline int pair_mode() {
 }
 // Weight tensor map of a launch [K, rows, nmat]; decides the CTA-pair mode of the launch: a pair's CTAs load
 // half a column block each.
-inline int make_b_map(TapGemmParams& P, const void* base, int K, int rows, int nmat, int bn) {
-    P.cta2 = (pair_mode() == 2 || (pair_mode() == 1 && bn != 128)) ? 1 : 0;
+inline int make_b_map(TapGemmParams& P, const void* base, int K, int rows, int nmat, int bn, int pair128 = 0) {
+    P.cta2 = (pair_mode() == 2 || (pair_mode() == 1 && (bn != 128 || pair128))) ? 1 : 0;
     uint64_t dims[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(rows), static_cast<uint64_t>(nmat)};
     uint64_t strides[2] = {static_cast<uint64_t>(K) * 2, static_cast<uint64_t>(K) * rows * 2};
     uint32_t box[3] = {64, static_cast<uint32_t>(P.cta2 ? bn / 2 : bn), 1};

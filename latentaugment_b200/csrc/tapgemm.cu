@@ -125,12 +125,32 @@ __device__ __forceinline__ TileCoord pair_tile(const Unit& u, uint32_t rank) {
     return tc;
 }
 
+// Work item of a CTA pair: unit a (its tiles go to the leader / the peer) and, where two M tiles fit a CTA (BN <= 128),
+// the next unit b of the same (column block, problem) as second sub-tile -- four M tiles share every weight tile.
+struct PairWork {
+    Unit a, b;
+    int nsub, adv;
+};
+template <int MTMAX>
+__device__ __forceinline__ PairWork get_pair_work(const TapGemmParams& P, int t, int t_end) {
+    PairWork w;
+    w.a = get_unit<2>(P, t, t_end);
+    w.b = w.a;
+    w.nsub = 1;
+    w.adv = w.a.adv;
+    if (MTMAX == 2 && w.a.mt == 2 && t + 2 < t_end) {
+        const Unit n = get_unit<2>(P, t + 2, t_end);
+        if (n.tc0.nblk == w.a.tc0.nblk && n.tc0.prob == w.a.tc0.prob) { w.b = n; w.nsub = 2; w.adv += n.adv; }
+    }
+    return w;
+}
+
 // Contiguous, COST-balanced tile range of this CTA.  The phases of the transposed convolution have 4 / 2 / 2 / 1
 // taps; a tile costs (taps x K chunks) MMA steps plus a fixed epilogue share worth about four steps (measured:
 // with taps alone the CTAs that own the one-tap phase finish 35 % after the others).  Tiles are ordered
 // [nblk][problem][tile].
 __device__ __forceinline__ long long tile_cost(const TapGemmParams& P, const TapProblem& pr) {
-    return pr.ntaps > 0 ? static_cast<long long>(pr.ntaps) * P.kchunks + 4 : 1;
+    return pr.ntaps > 0 ? static_cast<long long>(pr.ntaps) * P.kchunks + P.cost_fixed : 1;
 }
 __device__ __forceinline__ long long tiles_before(const TapGemmParams& P, long long cost_per_nblk, long long x) {
     long long nb_full = x / cost_per_nblk;
@@ -801,7 +821,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     constexpr bool pair = kPair;                                    // CTA pair: M = 256 MMAs issued by cluster rank 0
     uint32_t rank = 0u;
     if constexpr (kPair) rank = cluster_ctarank();
-    const int a_slot_bytes = (C::kMtMax == 2 && !P.no_pair && !pair) ? 2 * kASubBytes : kASubBytes;
+    const int a_slot_bytes = (C::kMtMax == 2 && (pair || !P.no_pair)) ? 2 * kASubBytes : kASubBytes;
     const int a_stages = min(kMaxAStages, C::kABytes / a_slot_bytes);
 
     const int warp = threadIdx.x >> 5;
@@ -809,7 +829,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     int t_begin, t_end;
     if (pair) tile_range(P, t_begin, t_end, static_cast<int>(blockIdx.x >> 1), static_cast<int>(gridDim.x >> 1));
     else tile_range(P, t_begin, t_end);
-    auto unit_at = [&](int t) { return pair ? get_unit<2>(P, t, t_end) : get_unit<C::kMtMax>(P, t, t_end); };
+    auto unit_at = [&](int t) { return get_unit<C::kMtMax>(P, t, t_end); };                    // single-CTA launches
+    auto pair_at = [&](int t) { return get_pair_work<C::kMtMax>(P, t, t_end); };                // CTA-pair launches
     unsigned long long dbg_c0 = 0, dbg_t0 = 0;
     if (P.dbg_clock && blockIdx.x == 0 && threadIdx.x == 64) {
         dbg_c0 = clock64();
@@ -854,10 +875,22 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
             const bool dbg = P.dbg_clock && blockIdx.x == 0 && lane == 0;
             int dbg_step = 0;
             for (int t = t_begin; t < t_end;) {
-                const Unit u = unit_at(t);
-                t += u.adv;
-                if (u.mt == 0) continue;
-                const TileCoord tc0 = kPair ? pair_tile(u, rank) : u.tc0;      // (pair: this CTA's own M tile)
+                Unit u;
+                TileCoord tc0, tc1;          // pair: this CTA's own M tile(s)
+                int nsub = 1;
+                if constexpr (kPair) {
+                    const PairWork w = pair_at(t);
+                    t += w.adv;
+                    u = w.a;
+                    nsub = w.nsub;
+                    tc0 = pair_tile(w.a, rank);
+                    tc1 = pair_tile(w.b, rank);
+                } else {
+                    u = unit_at(t);
+                    t += u.adv;
+                    if (u.mt == 0) continue;
+                    tc0 = u.tc0; tc1 = u.tc1;
+                }
                 const TapProblem& pr = P.prob[tc0.prob];
                 for (int g = 0; g < pr.ngroups; ++g) {
                     const TapGroup grp = P.groups[pr.grp_begin + g];
@@ -869,13 +902,14 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
                         if (elect_one()) {
                             if constexpr (kPair) {
                                 // all bytes of the pair are counted on the LEADER's barrier; it alone posts the expected total
-                                if (rank == 0) mbar_expect_tx(&a_full[as], 2 * a_tx_bytes);
-                                tma_load_4d_pair(sa, amap, mapa_shared(smem_u32(&a_full[as]), 0), kc * kBlockK, tc0.w0 + grp.dx, tc0.h0 + grp.dy0, tc0.n0);
+                                const uint32_t lead = mapa_shared(smem_u32(&a_full[as]), 0);
+                                if (rank == 0) mbar_expect_tx(&a_full[as], 2 * nsub * a_tx_bytes);
+                                tma_load_4d_pair(sa, amap, lead, kc * kBlockK, tc0.w0 + grp.dx, tc0.h0 + grp.dy0, tc0.n0);
+                                if (nsub == 2) tma_load_4d_pair(sa + kASubBytes, amap, lead, kc * kBlockK, tc1.w0 + grp.dx, tc1.h0 + grp.dy0, tc1.n0);
                             } else {
                                 mbar_expect_tx(&a_full[as], a_tx_bytes * u.mt);
-                                tma_load_4d(sa, amap, &a_full[as], kc * kBlockK, u.tc0.w0 + grp.dx, u.tc0.h0 + grp.dy0, u.tc0.n0);
-                                if (u.mt == 2)
-                                    tma_load_4d(sa + kASubBytes, amap, &a_full[as], kc * kBlockK, u.tc1.w0 + grp.dx, u.tc1.h0 + grp.dy0, u.tc1.n0);
+                                tma_load_4d(sa, amap, &a_full[as], kc * kBlockK, tc0.w0 + grp.dx, tc0.h0 + grp.dy0, tc0.n0);
+                                if (u.mt == 2) tma_load_4d(sa + kASubBytes, amap, &a_full[as], kc * kBlockK, tc1.w0 + grp.dx, tc1.h0 + grp.dy0, tc1.n0);
                             }
                         }
                         __syncwarp();
@@ -889,9 +923,16 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
             uint32_t bph = 0;
             const int b_row0 = kPair ? static_cast<int>(rank) * (BN / 2) : 0;      // (pair: this CTA's half of the column block)
             for (int t = t_begin; t < t_end;) {
-                const Unit u = unit_at(t);
-                t += u.adv;
-                if (u.mt == 0) continue;
+                Unit u;
+                if constexpr (kPair) {
+                    const PairWork w = pair_at(t);
+                    t += w.adv;
+                    u = w.a;
+                } else {
+                    u = unit_at(t);
+                    t += u.adv;
+                    if (u.mt == 0) continue;
+                }
                 const TapProblem& pr = P.prob[u.tc0.prob];
                 for (int g = 0; g < pr.ngroups; ++g) {
                     const TapGroup grp = P.groups[pr.grp_begin + g];
@@ -927,33 +968,43 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
                 uint32_t acc_phase = 0;
                 const bool dbg = P.dbg_clock && blockIdx.x == 0 && lane == 0;
                 int dbg_units = 0, dbg_step = 0;
+                unsigned long long dbg_wait_acc = 0, dbg_wait_a = 0, dbg_wait_b = 0, w0 = 0;
                 if (dbg) P.dbg_clock[2] = global_timer_ns();
                 for (int t = t_begin; t < t_end;) {
-                    const Unit u = get_unit<2>(P, t, t_end);
-                    t += u.adv;
-                    if (u.mt == 0) continue;
-                    const TapProblem& pr = P.prob[u.tc0.prob];
+                    const PairWork w = pair_at(t);
+                    t += w.adv;
+                    const int nsub = w.nsub;
+                    const TapProblem& pr = P.prob[w.a.tc0.prob];
+                    if (dbg) w0 = global_timer_ns();
                     mbar_wait(&tempty_bar[acc], acc_phase ^ 1, P.err_flag, 2);
+                    if (dbg) dbg_wait_acc += global_timer_ns() - w0;
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * C::kMtMax * BN);
                     bool first = true;
                     for (int g = 0; g < pr.ngroups; ++g) {
                         const TapGroup grp = P.groups[pr.grp_begin + g];
                         for (int kc = 0; kc < P.kchunks; ++kc) {
+                            if (dbg) w0 = global_timer_ns();
                             mbar_wait(&a_full[as], aph, P.err_flag, 3);
+                            if (dbg) dbg_wait_a += global_timer_ns() - w0;
                             if (dbg && dbg_step < 28) P.dbg_clock[9 + 2 * dbg_step++] = global_timer_ns();
                             const uint32_t sa = smem_u32(a_smem + as * a_slot_bytes);
                             for (int j = 0; j < grp.ntaps; ++j) {
+                                if (dbg) w0 = global_timer_ns();
                                 mbar_wait(&b_full[bs], bph, P.err_flag, 6);
+                                if (dbg) dbg_wait_b += global_timer_ns() - w0;
                                 tc_fence_after();
                                 if (dbg && first && dbg_units == 0) P.dbg_clock[3] = global_timer_ns();
                                 const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(b_smem + bs * C::kBSlotBytes));
-                                const uint64_t adesc = make_sw128_kmajor_desc(sa + P.gdyrel[grp.tap_begin + j] * dy_bytes);
+                                const uint32_t a_tap = sa + P.gdyrel[grp.tap_begin + j] * dy_bytes;
                                 if (elect_one()) {
+                                    for (int sb = 0; sb < nsub; ++sb) {
+                                        const uint64_t adesc = make_sw128_kmajor_desc(a_tap + sb * kASubBytes);
 #pragma unroll
-                                    for (int k = 0; k < kBlockK / 16; ++k)
-                                        umma_bf16_pair(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc2,
-                                                       (first && k == 0) ? 0u : 1u);
+                                        for (int k = 0; k < kBlockK / 16; ++k)
+                                            umma_bf16_pair(d_tmem + static_cast<uint32_t>(sb * BN), adesc + static_cast<uint64_t>(k * 2),
+                                                           bdesc + static_cast<uint64_t>(k * 2), idesc2, (first && k == 0) ? 0u : 1u);
+                                    }
                                     umma_commit_pair(&b_empty[bs]);
                                 }
                                 __syncwarp();
@@ -970,7 +1021,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
                     if (dbg && dbg_units++ == 0) P.dbg_clock[4] = global_timer_ns();
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
-                if (dbg) { P.dbg_clock[5] = global_timer_ns(); P.dbg_clock[6] = static_cast<unsigned long long>(dbg_units); }
+                if (dbg) {
+                    P.dbg_clock[5] = global_timer_ns(); P.dbg_clock[6] = static_cast<unsigned long long>(dbg_units);
+                    P.dbg_clock[60] = dbg_wait_acc; P.dbg_clock[61] = dbg_wait_a; P.dbg_clock[62] = dbg_wait_b;
+                }
             }
         } else if (warp == 1) {
             // ---------------------------------------------------------------- MMA issuer (whole warp, one elected lane issues)
@@ -1048,11 +1102,19 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
             WarpSmem* ws = reinterpret_cast<WarpSmem*>(epi_smem) + e;
             const uint32_t tempty_lead[2] = {pair ? mapa_shared(smem_u32(&tempty_bar[0]), 0) : 0u, pair ? mapa_shared(smem_u32(&tempty_bar[1]), 0) : 0u};
             auto tile_at = [&](int t, BwdTile& bt, int& adv) {
-                const Unit u = unit_at(t);     // (the backward GEMMs are single-problem: never empty)
-                const EpiSplit<BN> sp = epi_split<BN>(pair ? 1 : u.mt, sub);
-                bt.tc = pair ? pair_tile(u, rank) : u.tile(sp.st);
+                EpiSplit<BN> sp;
+                if constexpr (kPair) {
+                    const PairWork w = pair_at(t);
+                    sp = epi_split<BN>(w.nsub, sub);
+                    bt.tc = pair_tile(sp.st ? w.b : w.a, rank);
+                    adv = w.adv;
+                } else {
+                    const Unit u = unit_at(t);     // (the backward GEMMs are single-problem: never empty)
+                    sp = epi_split<BN>(u.mt, sub);
+                    bt.tc = u.tile(sp.st);
+                    adv = u.adv;
+                }
                 bt.step0 = sp.ch_begin; bt.nsteps = sp.ch_end - sp.ch_begin; bt.sub_tile = sp.st;
-                adv = u.adv;
             };
             auto chunk_loader = [&](int it, const BwdTile& bt) {
                 const int acc = it & 1;
@@ -1095,11 +1157,20 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
             uint32_t acc_phase = 0;
             int coef_key = -1;
             for (int t = t_begin; t < t_end;) {
-                const Unit u = unit_at(t);
-                t += u.adv;
-                if (u.mt == 0) continue;
-                const EpiSplit<BN> sp = epi_split<BN>(pair ? 1 : u.mt, sub);
-                const TileCoord tc = pair ? pair_tile(u, rank) : u.tile(sp.st);
+                EpiSplit<BN> sp;
+                TileCoord tc;
+                if constexpr (kPair) {
+                    const PairWork w = pair_at(t);
+                    t += w.adv;
+                    sp = epi_split<BN>(w.nsub, sub);
+                    tc = pair_tile(sp.st ? w.b : w.a, rank);
+                } else {
+                    const Unit u = unit_at(t);
+                    t += u.adv;
+                    if (u.mt == 0) continue;
+                    sp = epi_split<BN>(u.mt, sub);
+                    tc = u.tile(sp.st);
+                }
                 const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                         static_cast<uint32_t>((acc * C::kMtMax + sp.st) * BN);
                 bool waited = false;
@@ -1460,6 +1531,7 @@ int launch_bn_epi(const TapGemmParams& p, int num_sms, cudaStream_t stream) {
     if (p.halo != 0 && (p.halo != 2 || p.tw != 8 || p.nb != 1 || p.th != 16)) return static_cast<int>(cudaErrorInvalidValue);
     if (p.interleave && (p.epilogue == kEpiBwd || p.m_tiles % (2 * p.nprob))) return static_cast<int>(cudaErrorInvalidValue);
     if (p.nb * (p.th + p.halo) * p.tw * 128 > kASubBytes) return static_cast<int>(cudaErrorInvalidValue);
+    static const int cost_env = getenv("LA_TILE_COST") ? atoi(getenv("LA_TILE_COST")) : 0;      // tuning switch
     if (p.cta2) {
         // CTA pairs: clusters of two CTAs (one TPC), each cluster walks a cost-balanced range of tile pairs
         if constexpr (EPI == kEpiTopK) {
@@ -1470,6 +1542,8 @@ int launch_bn_epi(const TapGemmParams& p, int num_sms, cudaStream_t stream) {
             const int clusters = (total + 1) / 2 < num_sms / 2 ? (total + 1) / 2 : num_sms / 2;
             TapGemmParams q = p;
             q.no_pair = 0;
+            // (range balance: with the MMAs this much faster the fixed per-tile share weighs more; measured optimum)
+            q.cost_fixed = cost_env ? cost_env : (BN == 128 ? 20 : 12);
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(static_cast<unsigned>(2 * clusters));
             cfg.blockDim = dim3(kThreads);
@@ -1484,13 +1558,10 @@ int launch_bn_epi(const TapGemmParams& p, int num_sms, cudaStream_t stream) {
         }
     }
     if (int r = set_smem_attr<BN, EPI, false>()) return r;
-    if (total <= num_sms && !p.no_pair) {       // one tile per CTA: nothing to pair, so run the deeper unpaired A ring
-        TapGemmParams q = p;
-        q.no_pair = 1;
-        tapgemm_kernel<BN, EPI, false><<<grid, kThreads, Cfg<BN, EPI>::kSmemBytes, stream>>>(q);
-    } else {
-        tapgemm_kernel<BN, EPI, false><<<grid, kThreads, Cfg<BN, EPI>::kSmemBytes, stream>>>(p);
-    }
+    TapGemmParams q = p;
+    q.cost_fixed = 4;
+    if (total <= num_sms && !p.no_pair) q.no_pair = 1;       // one tile per CTA: nothing to pair, so run the deeper unpaired A ring
+    tapgemm_kernel<BN, EPI, false><<<grid, kThreads, Cfg<BN, EPI>::kSmemBytes, stream>>>(q);
     return static_cast<int>(cudaGetLastError());
 }
 
