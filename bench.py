@@ -293,7 +293,7 @@ def main():
         traffic = None          # DRAM bytes (read + write) of the same 26 launches, from the committed ncu capture of this workload
         if args.config == 'c2' and args.precision == 'bf16':
             try:
-                traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r1b_tapgemm_traffic.json')))['dram_bytes_read_plus_write']
+                traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r1c_tapgemm_traffic.json')))['dram_bytes_read_plus_write']
             except (OSError, KeyError, ValueError):
                 pass
         roof = {'bound': 'tensor', 'kernel': 'tapgemm_kernel (26 launches of one Adam step: 13 forward + 13 data-gradient)',
