@@ -101,73 +101,111 @@ __global__ void prep_const_kernel(const float* __restrict__ cst, int C, int hw, 
     split_store(hi, lo, idx, v);
 }
 
-// ------------------------------------------------------------------------- styles
-// warp per affine row; the row stays in registers while the warp walks the batch.
-constexpr int kMaxRowRegs = 32;   // rows up to 1024 floats
+constexpr int kMaxRowRegs = 32;   // mapping network: a weight row of up to 1024 floats stays in a warp's registers
 
-constexpr int kSampleUnroll = 4;
-__global__ void styles_kernel(LayerTable T, const float* __restrict__ ws, long long sn, long long sidx,
-                              const float* __restrict__ a_cat, const float* __restrict__ b_cat, int w_dim, int batch,
-                              float* s_cat) {
+// ------------------------------------------------------------------------- style GEMMs
+// The three per-step style products are small GEMMs  out[n, j] = epi( sum_k X[n, k] * M[j, k] )  over the batch:
+//   styles      : X = w (per layer row of ws),        M = affine rows A_cat,  epi = + bias
+//   demodulation: X = s^2,                            M = W2  [cout][cin],    epi = rsqrt(. + 1e-8)
+//   style grad  : X = red_d * d^2,                    M = W2t [cin][cout],    epi = red_s - s * .
+// One block = 32 rows j x 32 samples, K walked in 32-wide slabs staged k-major in shared memory (the next slab is
+// fetched into registers while the current one computes); a thread owns a 2 x 4 register tile.  (The earlier warp-per-row kernels re-read every sample vector
+// once per row: 0.45 ms per Adam step for 0.5 GFLOP.)
+constexpr int kSgRows = 32, kSgK = 32, kSgSamples = 32;
+enum { kSgStyles = 0, kSgDemod = 1, kSgGrad = 2 };
+struct StyleGemmArgs {
+    const float* ws; long long sn, sidx; const float* a_cat; const float* b_cat; int w_dim;     // styles
+    const float* s_cat; const float* d_cat; const float* red_s; const float* red_d;           // demod / grad
+    float* out;
+};
+template <int MODE>
+__global__ void __launch_bounds__(128) style_gemm_kernel(LayerTable T, int batch, StyleGemmArgs A) {
+    __shared__ __align__(16) float Ms[kSgK][kSgRows + 4];
+    __shared__ __align__(16) float Xs[kSgK][kSgSamples + 4];
     const int L = blockIdx.y;
-    int cin, soff, widx;
-    if (L < T.nconv) { cin = T.conv[L].cin; soff = T.conv[L].soff; widx = T.conv[L].ws_idx; }
-    else { cin = T.rgb[L - T.nconv].cin; soff = T.rgb[L - T.nconv].soff; widx = T.rgb[L - T.nconv].ws_idx; }
-    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (i >= cin) return;
-    float a[kMaxRowRegs];
-    const float* arow = a_cat + static_cast<long long>(soff + i) * w_dim;
-#pragma unroll
-    for (int r = 0; r < kMaxRowRegs; ++r) a[r] = (lane + 32 * r < w_dim) ? arow[lane + 32 * r] : 0.f;
-    const float b = b_cat[soff + i];
-    for (int n0 = 0; n0 < batch; n0 += kSampleUnroll) {
-        float acc[kSampleUnroll];
-#pragma unroll
-        for (int u = 0; u < kSampleUnroll; ++u) {
-            acc[u] = 0.f;
-            if (n0 + u < batch) {
-                const float* wrow = ws + (n0 + u) * sn + widx * sidx;
-#pragma unroll
-                for (int r = 0; r < kMaxRowRegs; ++r)
-                    if (lane + 32 * r < w_dim) acc[u] = fmaf(a[r], wrow[lane + 32 * r], acc[u]);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < kSampleUnroll; ++u) acc[u] = warp_sum(acc[u]);
-#pragma unroll
-        for (int u = 0; u < kSampleUnroll; ++u)
-            if (lane == 0 && n0 + u < batch) s_cat[static_cast<long long>(batch) * soff + static_cast<long long>(n0 + u) * cin + i] = acc[u] + b;
+    int J, K;
+    const float* M;
+    long long xbase = 0, obase = 0;       // sample stride of out is J
+    long long xs_n = 0;
+    int soff = 0;
+    if (MODE == kSgStyles) {
+        int widx;
+        if (L < T.nconv) { J = T.conv[L].cin; soff = T.conv[L].soff; widx = T.conv[L].ws_idx; }
+        else { J = T.rgb[L - T.nconv].cin; soff = T.rgb[L - T.nconv].soff; widx = T.rgb[L - T.nconv].ws_idx; }
+        K = A.w_dim;
+        M = A.a_cat + static_cast<long long>(soff) * K;
+        xbase = widx * A.sidx; xs_n = A.sn;
+        obase = static_cast<long long>(batch) * soff;
+    } else {
+        const ConvDesc D = T.conv[L];
+        if (MODE == kSgDemod) { J = D.cout; K = D.cin; M = D.w2; xbase = static_cast<long long>(batch) * D.soff; obase = static_cast<long long>(batch) * D.doff; }
+        else { J = D.cin; K = D.cout; M = D.w2t; xbase = static_cast<long long>(batch) * D.doff; obase = static_cast<long long>(batch) * D.soff; }
+        xs_n = K;
     }
-}
-
-__global__ void demod_kernel(LayerTable T, int batch, const float* __restrict__ s_cat, float* d_cat) {
-    const ConvDesc D = T.conv[blockIdx.y];
-    const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (o >= D.cout) return;
-    float a[kMaxRowRegs];
-    const float* row = D.w2 + static_cast<long long>(o) * D.cin;
+    const int j0 = blockIdx.x * kSgRows;
+    if (j0 >= J) return;
+    const int n0 = blockIdx.z * kSgSamples;
+    const int t = threadIdx.x;
+    const int rg = t >> 3, sg = t & 7;          // rows 2*rg.., samples 4*sg..
+    const int lk = t & 31, lr = t >> 5;         // loader: k within the slab, first row / sample
+    float acc[2][4];
 #pragma unroll
-    for (int r = 0; r < kMaxRowRegs; ++r) a[r] = (lane + 32 * r < D.cin) ? row[lane + 32 * r] : 0.f;
-    for (int n0 = 0; n0 < batch; n0 += kSampleUnroll) {      // several samples in flight: the loop is latency-bound otherwise
-        float acc[kSampleUnroll];
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int u = 0; u < kSampleUnroll; ++u) {
-            acc[u] = 0.f;
-            if (n0 + u < batch) {
-                const float* s = s_cat + static_cast<long long>(batch) * D.soff + static_cast<long long>(n0 + u) * D.cin;
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    float mreg[kSgRows / 4], xreg[kSgSamples / 4];
+    auto fetch = [&](int k0) {               // the next slab travels in registers while this one computes
+        const int k = k0 + lk;
+        const bool kok = k < K;
 #pragma unroll
-                for (int r = 0; r < kMaxRowRegs; ++r)
-                    if (lane + 32 * r < D.cin) { const float v = s[lane + 32 * r]; acc[u] = fmaf(a[r], v * v, acc[u]); }
-            }
+        for (int i = 0; i < kSgRows / 4; ++i) {
+            const int r = lr + 4 * i;
+            mreg[i] = (kok && j0 + r < J) ? __ldg(M + static_cast<long long>(j0 + r) * K + k) : 0.f;
         }
 #pragma unroll
-        for (int u = 0; u < kSampleUnroll; ++u) acc[u] = warp_sum(acc[u]);
+        for (int i = 0; i < kSgSamples / 4; ++i) {
+            const int n = lr + 4 * i;
+            float v = 0.f;
+            if (kok && n0 + n < batch) {
+                const long long e = xbase + static_cast<long long>(n0 + n) * xs_n + k;
+                if (MODE == kSgStyles) v = __ldg(A.ws + e);
+                else if (MODE == kSgDemod) { v = __ldg(A.s_cat + e); v = v * v; }
+                else { const float d = __ldg(A.d_cat + e); v = __ldg(A.red_d + e) * d * d; }
+            }
+            xreg[i] = v;
+        }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < K; k0 += kSgK) {
 #pragma unroll
-        for (int u = 0; u < kSampleUnroll; ++u)
-            if (lane == 0 && n0 + u < batch)
-                d_cat[static_cast<long long>(batch) * D.doff + static_cast<long long>(n0 + u) * D.cout + o] = rsqrtf(acc[u] + 1e-8f);
+        for (int i = 0; i < kSgRows / 4; ++i) Ms[lk][lr + 4 * i] = mreg[i];
+#pragma unroll
+        for (int i = 0; i < kSgSamples / 4; ++i) Xs[lk][lr + 4 * i] = xreg[i];
+        __syncthreads();
+        if (k0 + kSgK < K) fetch(k0 + kSgK);
+#pragma unroll 8
+        for (int kk = 0; kk < kSgK; ++kk) {
+            const float2 m = *reinterpret_cast<const float2*>(&Ms[kk][2 * rg]);
+            const float4 x = *reinterpret_cast<const float4*>(&Xs[kk][4 * sg]);
+            const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int b = 0; b < 4; ++b) { acc[0][b] = fmaf(m.x, xv[b], acc[0][b]); acc[1][b] = fmaf(m.y, xv[b], acc[1][b]); }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const int n = n0 + 4 * sg + b;
+        if (n >= batch) continue;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int j = j0 + 2 * rg + a;
+            if (j >= J) continue;
+            const long long o = obase + static_cast<long long>(n) * J + j;
+            if (MODE == kSgStyles) A.out[o] = acc[a][b] + __ldg(A.b_cat + soff + j);
+            else if (MODE == kSgDemod) A.out[o] = rsqrtf(acc[a][b] + 1e-8f);
+            else A.out[o] = __ldg(A.red_s + o) - __ldg(A.s_cat + o) * acc[a][b];
+        }
     }
 }
 
@@ -629,43 +667,7 @@ __global__ void pix_loss_kernel(const float4* __restrict__ img, const float4* __
 }
 
 // ------------------------------------------------------------------------- style gradients
-// conv layer:  g_s[n,i] = red_s[n,i] - s[n,i] * sum_o red_d[n,o] * d[n,o]^2 * W2[o,i]      
-__global__ void style_grad_conv_kernel(LayerTable T, int batch, const float* __restrict__ s_cat, const float* __restrict__ d_cat,
-                                       const float* __restrict__ red_s, const float* __restrict__ red_d, float* g_s) {
-    const ConvDesc D = T.conv[blockIdx.y];
-    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (i >= D.cin) return;
-    float a[kMaxRowRegs];
-    const float* row = D.w2t + static_cast<long long>(i) * D.cout;
-#pragma unroll
-    for (int r = 0; r < kMaxRowRegs; ++r) a[r] = (lane + 32 * r < D.cout) ? row[lane + 32 * r] : 0.f;
-    for (int n0 = 0; n0 < batch; n0 += kSampleUnroll) {
-        float acc[kSampleUnroll];
-#pragma unroll
-        for (int u = 0; u < kSampleUnroll; ++u) {
-            acc[u] = 0.f;
-            if (n0 + u < batch) {
-                const long long dbase = static_cast<long long>(batch) * D.doff + static_cast<long long>(n0 + u) * D.cout;
-#pragma unroll
-                for (int r = 0; r < kMaxRowRegs; ++r)
-                    if (lane + 32 * r < D.cout) {
-                        const float d = d_cat[dbase + lane + 32 * r];
-                        acc[u] = fmaf(a[r], red_d[dbase + lane + 32 * r] * d * d, acc[u]);
-                    }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < kSampleUnroll; ++u) acc[u] = warp_sum(acc[u]);
-#pragma unroll
-        for (int u = 0; u < kSampleUnroll; ++u)
-            if (lane == 0 && n0 + u < batch) {
-                const long long si = static_cast<long long>(batch) * D.soff + static_cast<long long>(n0 + u) * D.cin + i;
-                g_s[si] = red_s[si] - s_cat[si] * acc[u];
-            }
-    }
-}
-
+// conv layer:  g_s[n,i] = red_s[n,i] - s[n,i] * sum_o red_d[n,o] * d[n,o]^2 * W2[o,i]      (SURVEY.md App. A.4): style_gemm_kernel<kSgGrad>
 // toRGB layer:  g_s[n,i] = sum_c W_rgb[c,i] * red_rgb[c][n,i]
 __global__ void style_grad_rgb_kernel(LayerTable T, int batch, const float* __restrict__ red_rgb, float* g_s) {
     const RgbDesc D = T.rgb[blockIdx.y];
@@ -980,16 +982,18 @@ int upfir_backward(const UpFirParams& p, cudaStream_t s) { return upfir_launch(p
 
 int styles_forward(const LayerTable& T, const float* ws, long long sn, long long sidx, const float* a_cat, const float* b_cat,
                    int w_dim, int batch, float* s_cat, cudaStream_t s) {
-    if (w_dim > 32 * kMaxRowRegs) return static_cast<int>(cudaErrorInvalidValue);
-    dim3 grid(cdiv(max_cin(T, true, true), 4), T.nconv + T.nrgb);
-    styles_kernel<<<grid, 128, 0, s>>>(T, ws, sn, sidx, a_cat, b_cat, w_dim, batch, s_cat);
+    StyleGemmArgs A{};
+    A.ws = ws; A.sn = sn; A.sidx = sidx; A.a_cat = a_cat; A.b_cat = b_cat; A.w_dim = w_dim; A.out = s_cat;
+    dim3 grid(cdiv(max_cin(T, true, true), kSgRows), T.nconv + T.nrgb, cdiv(batch, kSgSamples));
+    style_gemm_kernel<kSgStyles><<<grid, 128, 0, s>>>(T, batch, A);
     return last_err();
 }
 int demod_rgbw_forward(const LayerTable& T, int batch, const float* s_cat, float* d_cat, float4* rgbw, cudaStream_t s) {
     int mco = 0;
     for (int i = 0; i < T.nconv; ++i) mco = T.conv[i].cout > mco ? T.conv[i].cout : mco;
-    if (max_cin(T, true, false) > 32 * kMaxRowRegs) return static_cast<int>(cudaErrorInvalidValue);
-    demod_kernel<<<dim3(cdiv(mco, 4), T.nconv), 128, 0, s>>>(T, batch, s_cat, d_cat);
+    StyleGemmArgs A{};
+    A.s_cat = s_cat; A.out = d_cat;
+    style_gemm_kernel<kSgDemod><<<dim3(cdiv(mco, kSgRows), T.nconv, cdiv(batch, kSgSamples)), 128, 0, s>>>(T, batch, A);
     int e = last_err();
     if (e) return e;
     rgbw_kernel<<<dim3(cdiv(max_cin(T, false, true), 128), T.nrgb, batch), 128, 0, s>>>(T, batch, s_cat, rgbw);
@@ -1026,8 +1030,10 @@ int style_grad(const LayerTable& T, int batch, const float* s_cat, const float* 
                const float* red_rgb, float* g_s, cudaStream_t s) {
     int mco = 0;
     for (int i = 0; i < T.nconv; ++i) mco = T.conv[i].cout > mco ? T.conv[i].cout : mco;
-    if (mco > 32 * kMaxRowRegs) return static_cast<int>(cudaErrorInvalidValue);
-    style_grad_conv_kernel<<<dim3(cdiv(max_cin(T, true, false), 4), T.nconv), 128, 0, s>>>(T, batch, s_cat, d_cat, red_s, red_d, g_s);
+    (void)mco;
+    StyleGemmArgs A{};
+    A.s_cat = s_cat; A.d_cat = d_cat; A.red_s = red_s; A.red_d = red_d; A.out = g_s;
+    style_gemm_kernel<kSgGrad><<<dim3(cdiv(max_cin(T, true, false), kSgRows), T.nconv, cdiv(batch, kSgSamples)), 128, 0, s>>>(T, batch, A);
     int e = last_err();
     if (e) return e;
     style_grad_rgb_kernel<<<dim3(cdiv(max_cin(T, false, true), 128), T.nrgb, batch), 128, 0, s>>>(T, batch, red_rgb, g_s);

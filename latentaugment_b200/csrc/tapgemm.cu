@@ -138,7 +138,7 @@ __device__ __forceinline__ PairWork get_pair_work(const TapGemmParams& P, int t,
     w.b = w.a;
     w.nsub = 1;
     w.adv = w.a.adv;
-    if (MTMAX == 2 && w.a.mt == 2 && t + 2 < t_end) {
+    if (MTMAX == 2 && !P.no_quad && w.a.mt == 2 && t + 2 < t_end) {
         const Unit n = get_unit<2>(P, t + 2, t_end);
         if (n.tc0.nblk == w.a.tc0.nblk && n.tc0.prob == w.a.tc0.prob) { w.b = n; w.nsub = 2; w.adv += n.adv; }
     }
@@ -821,7 +821,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     constexpr bool pair = kPair;                                    // CTA pair: M = 256 MMAs issued by cluster rank 0
     uint32_t rank = 0u;
     if constexpr (kPair) rank = cluster_ctarank();
-    const int a_slot_bytes = (C::kMtMax == 2 && (pair || !P.no_pair)) ? 2 * kASubBytes : kASubBytes;
+    const int a_slot_bytes = (C::kMtMax == 2 && !(pair ? P.no_quad : P.no_pair)) ? 2 * kASubBytes : kASubBytes;
     const int a_stages = min(kMaxAStages, C::kABytes / a_slot_bytes);
 
     const int warp = threadIdx.x >> 5;
@@ -1541,7 +1541,10 @@ int launch_bn_epi(const TapGemmParams& p, int num_sms, cudaStream_t stream) {
             if (int r = set_smem_attr<BN, EPI, true>()) return r;
             const int clusters = (total + 1) / 2 < num_sms / 2 ? (total + 1) / 2 : num_sms / 2;
             TapGemmParams q = p;
+            // launches with at most one M tile per CTA never form four-tile work items: one-tile A slots, a ring twice
+            // as deep (the K loop of the <= 16^2 layers is bound by the latency of the A loads in flight)
             q.no_pair = 0;
+            q.no_quad = total <= num_sms ? 1 : 0;
             // (range balance: with the MMAs this much faster the fixed per-tile share weighs more; measured optimum)
             q.cost_fixed = cost_env ? cost_env : (BN == 128 ? 20 : 12);
             cudaLaunchConfig_t cfg = {};

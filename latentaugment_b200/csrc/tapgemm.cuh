@@ -72,6 +72,7 @@ struct TapGemmParams {
     int halo;                        // extra rows of the A box (0 or 2); 2 needs tw == 8 and nb == 1
     int no_pair;                     // 1: never pair M tiles (tuning switch)
     int cost_fixed;                  // set by the launcher: fixed (epilogue) share of a tile's cost in K steps, for the range balance
+    int no_quad;                     // set by the launcher (pair launches): one M tile per CTA, never four-tile work items
     int cta2;                        // 1: CTA pairs (clusters of 2, cta_group::2 MMAs with M = 256): the b_map box holds HALF a column block
     int interleave;                  // 1: all problems share one tile grid (tiles_h/w equal, vh/vw mask) and are walked
                                      //    [column block][pair of spatial tiles][problem][tile of the pair], so that every
