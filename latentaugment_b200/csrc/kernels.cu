@@ -437,87 +437,184 @@ __global__ void __launch_bounds__(160) upfir_tma_kernel(const __grid_constant__ 
     const float clampv = P.act_clamp >= 0.f ? P.act_clamp : __int_as_float(0x7f800000);
     const int px0 = warp * 8;                                    // this warp's first output pixel inside the strip
     uint8_t* my_stage = stage + warp * 4096;
-    for (int j = 0; j < 3; ++j) mbar_wait(&full[j % kFirRing], (j / kFirRing) & 1, nullptr, 0);
-    for (int r = r0; r < r1; ++r) {
-        const int j0 = r - r0;
-        mbar_wait(&full[(j0 + 3) % kFirRing], ((j0 + 3) / kFirRing) & 1, nullptr, 0);
-        // vertical pass: 11 window columns, 2 channels each
-        float2 cs[11];
-#pragma unroll
-        for (int q = 0; q < 11; ++q) cs[q] = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const unsigned* row = reinterpret_cast<const unsigned*>(ring + ((j0 + k) % kFirRing) * kFirSlotBytes) + px0 * 32 + lane;
+    if constexpr (!FWD) {
+        // Separable FIR, horizontal pass first: every input row is read from the ring ONCE, turned into 8 horizontally
+        // filtered pixels (x 2 channels) and released; the vertical pass combines the last four such rows, which roll
+        // through four register sets (the row loop is unrolled by four so the rotation is a renaming).
+        float2 ha[8], hb[8], hc[8], hd[8];
+        auto hpass = [&](int j, float2 (&h)[8]) {
+            mbar_wait(&full[j % kFirRing], (j / kFirRing) & 1, nullptr, 0);
+            const unsigned* row = reinterpret_cast<const unsigned*>(ring + (j % kFirRing) * kFirSlotBytes) + px0 * 32 + lane;
+            float2 in[11];
 #pragma unroll
             for (int q = 0; q < 11; ++q) {
                 const unsigned u = row[q * 32];
-                cs[q].x = fmaf(wy[k], __uint_as_float(u << 16), cs[q].x);
-                cs[q].y = fmaf(wy[k], __uint_as_float(u & 0xffff0000u), cs[q].y);
+                in[q] = make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
             }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[j0 % kFirRing]);       // the oldest row of the window is done
-        float nzv[8];
-        unsigned svv[8];
-        if (FWD && P.act_saved) {
-            const unsigned* sp = reinterpret_cast<const unsigned*>(P.act_saved) +
-                                 ((static_cast<long long>(n) * P.OH + r) * P.OW) * (P.C >> 1) + (c0 >> 1) + lane;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[j % kFirRing]);         // the row lives in registers now
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int x = x0 + px0 + i;
-                svv[i] = x < P.OW ? __ldg(sp + static_cast<long long>(x) * (P.C >> 1)) : 0u;
+                float a0 = wx[0] * in[i].x, a1 = wx[0] * in[i].y;
+#pragma unroll
+                for (int k = 1; k < 4; ++k) { a0 = fmaf(wx[k], in[i + k].x, a0); a1 = fmaf(wx[k], in[i + k].y, a1); }
+                h[i] = make_float2(a0, a1);
             }
-        }
-        if (FWD && P.noise && !P.act_saved) {
-            const float4* np = reinterpret_cast<const float4*>(P.noise + n * P.noise_stride_n + static_cast<long long>(r) * P.OW + x0 + px0);
-            const bool in = x0 + px0 + 8 <= P.OW;
-            const float4 a = in ? __ldg(np) : make_float4(0.f, 0.f, 0.f, 0.f), b = in ? __ldg(np + 1) : a;
-            nzv[0] = a.x; nzv[1] = a.y; nzv[2] = a.z; nzv[3] = a.w; nzv[4] = b.x; nzv[5] = b.y; nzv[6] = b.z; nzv[7] = b.w;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) nzv[i] *= P.noise_scale;
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) nzv[i] = 0.f;
-        }
-        uint8_t* sx = my_stage + (j0 & 1) * 2048;                // [x | xs] x 1 KB, double-buffered by row parity
-        if (lane == 0) bulk_wait_read<1>();                       // the stores of two rows ago have read this buffer
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { a0 = fmaf(wx[k], cs[i + k].x, a0); a1 = fmaf(wx[k], cs[i + k].y, a1); }
+        };
+        auto out_row = [&](int r, const float2 (&h0)[8], const float2 (&h1)[8], const float2 (&h2)[8], float2 (&h3)[8]) {
+            const int j0 = r - r0;
+            hpass(j0 + 3, h3);
+            float nzv[8];
+            unsigned svv[8];
             if (FWD && P.act_saved) {
-                const float s0 = __uint_as_float(svv[i] << 16), s1 = __uint_as_float(svv[i] & 0xffff0000u);
-                float g0 = a0 * P.act_gain * (s0 > 0.f ? 1.f : P.act_slope), g1 = a1 * P.act_gain * (s1 > 0.f ? 1.f : P.act_slope);
-                g0 = fabsf(s0) < clampv ? g0 : 0.f;
-                g1 = fabsf(s1) < clampv ? g1 : 0.f;
-                reinterpret_cast<unsigned*>(sx)[i * 32 + lane] = pack2(g0, g1);
-            } else if (FWD) {
-                float z0 = fmaf(a0, dm.x, nzv[i]) + bs.x, z1 = fmaf(a1, dm.y, nzv[i]) + bs.y;
-                z0 = (z0 > 0.f ? z0 : z0 * P.act_slope) * P.act_gain;
-                z1 = (z1 > 0.f ? z1 : z1 * P.act_slope) * P.act_gain;
-                z0 = fminf(fmaxf(z0, -clampv), clampv);
-                z1 = fminf(fmaxf(z1, -clampv), clampv);
-                reinterpret_cast<unsigned*>(sx)[i * 32 + lane] = pack2(z0, z1);
-                reinterpret_cast<unsigned*>(sx + 1024)[i * 32 + lane] = pack2(z0 * sn.x, z1 * sn.y);
+                const unsigned* sp = reinterpret_cast<const unsigned*>(P.act_saved) +
+                                     ((static_cast<long long>(n) * P.OH + r) * P.OW) * (P.C >> 1) + (c0 >> 1) + lane;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int x = x0 + px0 + i;
+                    svv[i] = x < P.OW ? __ldg(sp + static_cast<long long>(x) * (P.C >> 1)) : 0u;
+                }
+            }
+            if (FWD && P.noise && !P.act_saved) {
+                const float4* np = reinterpret_cast<const float4*>(P.noise + n * P.noise_stride_n + static_cast<long long>(r) * P.OW + x0 + px0);
+                const bool in = x0 + px0 + 8 <= P.OW;
+                const float4 a = in ? __ldg(np) : make_float4(0.f, 0.f, 0.f, 0.f), b = in ? __ldg(np + 1) : a;
+                nzv[0] = a.x; nzv[1] = a.y; nzv[2] = a.z; nzv[3] = a.w; nzv[4] = b.x; nzv[5] = b.y; nzv[6] = b.z; nzv[7] = b.w;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) nzv[i] *= P.noise_scale;
             } else {
-                reinterpret_cast<unsigned*>(sx)[i * 32 + lane] = pack2(a0, a1);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) nzv[i] = 0.f;
+            }
+            uint8_t* sx = my_stage + (j0 & 1) * 2048;                // [x | xs] x 1 KB, double-buffered by row parity
+            if (lane == 0) bulk_wait_read<1>();                       // the stores of two rows ago have read this buffer
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float a0 = fmaf(wy[3], h3[i].x, fmaf(wy[2], h2[i].x, fmaf(wy[1], h1[i].x, wy[0] * h0[i].x)));
+                const float a1 = fmaf(wy[3], h3[i].y, fmaf(wy[2], h2[i].y, fmaf(wy[1], h1[i].y, wy[0] * h0[i].y)));
+                if (FWD && P.act_saved) {
+                    const float s0 = __uint_as_float(svv[i] << 16), s1 = __uint_as_float(svv[i] & 0xffff0000u);
+                    float g0 = a0 * P.act_gain * (s0 > 0.f ? 1.f : P.act_slope), g1 = a1 * P.act_gain * (s1 > 0.f ? 1.f : P.act_slope);
+                    g0 = fabsf(s0) < clampv ? g0 : 0.f;
+                    g1 = fabsf(s1) < clampv ? g1 : 0.f;
+                    reinterpret_cast<unsigned*>(sx)[i * 32 + lane] = pack2(g0, g1);
+                } else if (FWD) {
+                    float z0 = fmaf(a0, dm.x, nzv[i]) + bs.x, z1 = fmaf(a1, dm.y, nzv[i]) + bs.y;
+                    z0 = (z0 > 0.f ? z0 : z0 * P.act_slope) * P.act_gain;
+                    z1 = (z1 > 0.f ? z1 : z1 * P.act_slope) * P.act_gain;
+                    z0 = fminf(fmaxf(z0, -clampv), clampv);
+                    z1 = fminf(fmaxf(z1, -clampv), clampv);
+                    reinterpret_cast<unsigned*>(sx)[i * 32 + lane] = pack2(z0, z1);
+                    reinterpret_cast<unsigned*>(sx + 1024)[i * 32 + lane] = pack2(z0 * sn.x, z1 * sn.y);
+                } else {
+                    reinterpret_cast<unsigned*>(sx)[i * 32 + lane] = pack2(a0, a1);
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                if (FWD) {
+                    tma_store_4d(&P.fwd_out_x, sx, c0, x0 + px0, r, n);
+                    if (P.s_next && !P.act_saved) tma_store_4d(&P.fwd_out_xs, sx + 1024, c0, x0 + px0, r, n);
+                } else {
+                    tma_store_4d(&P.bwd_out, sx, c0, x0 + px0, r, n);
+                }
+                bulk_commit();
+            }
+        };
+        if (r0 < r1) { hpass(0, ha); hpass(1, hb); hpass(2, hc); }
+        for (int r = r0; r < r1; r += 4) {
+            out_row(r, ha, hb, hc, hd);
+            if (r + 1 < r1) out_row(r + 1, hb, hc, hd, ha);
+            if (r + 2 < r1) out_row(r + 2, hc, hd, ha, hb);
+            if (r + 3 < r1) out_row(r + 3, hd, ha, hb, hc);
+        }
+    } else {
+        // (the forward pass keeps the vertical-first order: with the epilogue state the rolling window needs 136 registers,
+        // which costs a resident CTA -- measured slower than the extra arithmetic)
+        for (int j = 0; j < 3; ++j) mbar_wait(&full[j % kFirRing], (j / kFirRing) & 1, nullptr, 0);
+        for (int r = r0; r < r1; ++r) {
+            const int j0 = r - r0;
+            mbar_wait(&full[(j0 + 3) % kFirRing], ((j0 + 3) / kFirRing) & 1, nullptr, 0);
+            // vertical pass: 11 window columns, 2 channels each
+            float2 cs[11];
+#pragma unroll
+            for (int q = 0; q < 11; ++q) cs[q] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned* row = reinterpret_cast<const unsigned*>(ring + ((j0 + k) % kFirRing) * kFirSlotBytes) + px0 * 32 + lane;
+#pragma unroll
+                for (int q = 0; q < 11; ++q) {
+                    const unsigned u = row[q * 32];
+                    cs[q].x = fmaf(wy[k], __uint_as_float(u << 16), cs[q].x);
+                    cs[q].y = fmaf(wy[k], __uint_as_float(u & 0xffff0000u), cs[q].y);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[j0 % kFirRing]);       // the oldest row of the window is done
+            float nzv[8];
+            unsigned svv[8];
+            if (FWD && P.act_saved) {
+                const unsigned* sp = reinterpret_cast<const unsigned*>(P.act_saved) +
+                                     ((static_cast<long long>(n) * P.OH + r) * P.OW) * (P.C >> 1) + (c0 >> 1) + lane;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int x = x0 + px0 + i;
+                    svv[i] = x < P.OW ? __ldg(sp + static_cast<long long>(x) * (P.C >> 1)) : 0u;
+                }
+            }
+            if (FWD && P.noise && !P.act_saved) {
+                const float4* np = reinterpret_cast<const float4*>(P.noise + n * P.noise_stride_n + static_cast<long long>(r) * P.OW + x0 + px0);
+                const bool in = x0 + px0 + 8 <= P.OW;
+                const float4 a = in ? __ldg(np) : make_float4(0.f, 0.f, 0.f, 0.f), b = in ? __ldg(np + 1) : a;
+                nzv[0] = a.x; nzv[1] = a.y; nzv[2] = a.z; nzv[3] = a.w; nzv[4] = b.x; nzv[5] = b.y; nzv[6] = b.z; nzv[7] = b.w;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) nzv[i] *= P.noise_scale;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) nzv[i] = 0.f;
+            }
+            uint8_t* sx = my_stage + (j0 & 1) * 2048;                // [x | xs] x 1 KB, double-buffered by row parity
+            if (lane == 0) bulk_wait_read<1>();                       // the stores of two rows ago have read this buffer
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { a0 = fmaf(wx[k], cs[i + k].x, a0); a1 = fmaf(wx[k], cs[i + k].y, a1); }
+                if (FWD && P.act_saved) {
+                    const float s0 = __uint_as_float(svv[i] << 16), s1 = __uint_as_float(svv[i] & 0xffff0000u);
+                    float g0 = a0 * P.act_gain * (s0 > 0.f ? 1.f : P.act_slope), g1 = a1 * P.act_gain * (s1 > 0.f ? 1.f : P.act_slope);
+                    g0 = fabsf(s0) < clampv ? g0 : 0.f;
+                    g1 = fabsf(s1) < clampv ? g1 : 0.f;
+                    reinterpret_cast<unsigned*>(sx)[i * 32 + lane] = pack2(g0, g1);
+                } else if (FWD) {
+                    float z0 = fmaf(a0, dm.x, nzv[i]) + bs.x, z1 = fmaf(a1, dm.y, nzv[i]) + bs.y;
+                    z0 = (z0 > 0.f ? z0 : z0 * P.act_slope) * P.act_gain;
+                    z1 = (z1 > 0.f ? z1 : z1 * P.act_slope) * P.act_gain;
+                    z0 = fminf(fmaxf(z0, -clampv), clampv);
+                    z1 = fminf(fmaxf(z1, -clampv), clampv);
+                    reinterpret_cast<unsigned*>(sx)[i * 32 + lane] = pack2(z0, z1);
+                    reinterpret_cast<unsigned*>(sx + 1024)[i * 32 + lane] = pack2(z0 * sn.x, z1 * sn.y);
+                } else {
+                    reinterpret_cast<unsigned*>(sx)[i * 32 + lane] = pack2(a0, a1);
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                if (FWD) {
+                    tma_store_4d(&P.fwd_out_x, sx, c0, x0 + px0, r, n);
+                    if (P.s_next && !P.act_saved) tma_store_4d(&P.fwd_out_xs, sx + 1024, c0, x0 + px0, r, n);
+                } else {
+                    tma_store_4d(&P.bwd_out, sx, c0, x0 + px0, r, n);
+                }
+                bulk_commit();
             }
         }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-            if (FWD) {
-                tma_store_4d(&P.fwd_out_x, sx, c0, x0 + px0, r, n);
-                if (P.s_next && !P.act_saved) tma_store_4d(&P.fwd_out_xs, sx + 1024, c0, x0 + px0, r, n);
-            } else {
-                tma_store_4d(&P.bwd_out, sx, c0, x0 + px0, r, n);
-            }
-            bulk_commit();
-        }
+        // the last three window rows were never released: nobody waits for them
     }
-    // the last three window rows were never released: nobody waits for them
     if (lane == 0) bulk_wait_read<0>();
 }
 
