@@ -1,18 +1,23 @@
 """bench.py -- LatentAugment hot path throughput: augmented images / second.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c2] [--precision bf16]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c2|c3|c5|c1] [--precision bf16]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
 A "step" is one pass of the hot path over one batch: ``num_steps`` Adam iterations on w through the
 generator (forward + backward-to-w) plus the final synthesis -- one ``LatentAugment.forward()``.
-Workload at N=1: BASELINE.json configs[1] (SG2 256x256 3-ch, batch 32, 10 steps, 4096-code bank);
-with N GPUs every rank runs that batch (weak scaling, no data-path collective: samples are
-independent).  One JSON line on stdout (rank 0).
+
+Workloads (BASELINE.json configs):
+  c2 (default; the configuration the metric is quoted on): SG2 256x256 3-ch, batch 32 per GPU, 10 steps, 4096-code
+     bank; N GPUs = N batches (weak scaling, no data-path collective: samples are independent).
+  c3: SG2 512x512 3-ch, batch 128 SPLIT over the N ranks (strong scaling), 10 steps, CUDA-graph-captured loop.
+  c5: nearest-code sweep, 2^20 real codes sharded over the N ranks x 1024 queries, fused GEMM + top-k, exact
+     re-rank, NCCL all-gather + merge inside the timed region (the one collective of the design).
+  c1: SG2 128x128 1-ch, batch 4, 5 steps (the reference's CPU-runnable case; a parity-test case, not a bench line).
+One JSON line on stdout (rank 0).
 """
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys
@@ -25,9 +30,10 @@ sys.path.insert(0, ROOT)
 CONFIGS = {          # BASELINE.json configs; oracle/synthetic.py holds the same table for the parity tests
     'c1': dict(img_resolution=128, img_channels=1, batch=4, steps=5, bank=256, img_bank=64),
     'c2': dict(img_resolution=256, img_channels=3, batch=32, steps=10, bank=4096, img_bank=64),
-    'c3': dict(img_resolution=512, img_channels=3, batch=16, steps=10, bank=4096, img_bank=64),   # per-GPU shard of B=128 at 8 GPUs
+    'c3': dict(img_resolution=512, img_channels=3, batch=128, steps=10, bank=4096, img_bank=64, strong=True),
     'tiny': dict(img_resolution=32, img_channels=2, batch=4, steps=3, bank=64, img_bank=8, channel_base=2048, channel_max=64),
 }
+C5 = dict(codes=1 << 20, queries=1024, dim=512, k=4)
 
 
 def layer_table(res, img_c, channel_base=32768, channel_max=512):
@@ -98,52 +104,73 @@ class ClockSampler:
         return {'sm_mhz': med, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
 
 
-def cpu_baseline(cfg_name, seconds_hint=20.0, repeat=1):
-    """Reference CPU path (oracle port, fused grouped-conv formulation, torch CPU ops on all host
-    threads) on a BOUNDED sample of the workload: batch 2, 2 Adam steps + final synthesis; scaled to
-    the full step count by the pass count (3 generator passes per Adam step, as the reference executes:
-    fprop + dgrad + per-sample wgrad; +1 final)."""
-    import random
-
-    import torch
-
-    from oracle import latent_aug as ola
-    from oracle import synthetic
+def _full_cfg(cfg_name):
     c = dict(CONFIGS[cfg_name])
     c.setdefault('channel_base', 32768)
     c.setdefault('channel_max', 512)
+    return c
+
+
+def cpu_baseline(cfg_name, sample_batch=4):
+    """The reference's CPU path on the box's host cores, on a BOUNDED sample of the workload.
+
+    kind "reference": the reference's own ``LatentAug.forward`` (augments/utils/util_latent_aug.py:207-310) from the
+    shipped copy ``baseline/_ref``, over the reference's ``torch_utils.ops`` ref implementations (oracle/ref_driver.py);
+    kind "port": the oracle restatement, when no reference copy is present.  Sample: ``sample_batch`` images, once
+    with 1 and once with 3 Adam steps; per-step and fixed (final synthesis) costs follow from the two timings and are
+    extrapolated to the config's step count and reported per image."""
+    import random
+
+    import torch
+    c = _full_cfg(cfg_name)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    bs, ss = 2, 2
-    wl = synthetic.make_workload(c, noise_strength=0.0, batch=bs)
-    orc = ola.LatentAugOracle(wl['G'], wl['W'], wl['X'], num_epochs=ss, fused=True)
-    times = []
+    bs = min(sample_batch, c['batch'])
+    times = {}
+    kind = 'reference'
+    try:
+        from oracle import ref_driver
+        ref = ref_driver.import_reference()
+        runs = {s: ref_driver.reference_loop(c, batch=bs, steps=s, device='cpu', ref=ref)[0] for s in (1, 3)}
+        what = "reference LatentAug.forward from baseline/_ref over the reference's torch_utils.ops (CPU ref paths)"
+    except FileNotFoundError:
+        from oracle import latent_aug as ola
+        from oracle import synthetic
+        kind = 'port'
+        wl = synthetic.make_workload(c, noise_strength=0.0, batch=bs)
+        orcs = {s: ola.LatentAugOracle(wl['G'], wl['W'], wl['X'], num_epochs=s, fused=True) for s in (1, 3)}
+        runs = {s: (lambda o=o: o.forward(wl['w0'].clone())) for s, o in orcs.items()}
+        what = 'oracle port (torch CPU, fused modconv); no reference copy under baseline/_ref'
     random.seed(0)
-    orc.forward(wl['w0'].clone())        # untimed warm-up (thread pool, primitive caches)
-    for _ in range(repeat):
+    runs[1]()                             # untimed warm-up (thread pool, primitive caches)
+    for s in (1, 3):
         random.seed(0)
         t0 = time.perf_counter()
-        orc.forward(wl['w0'].clone())
-        times.append(time.perf_counter() - t0)
-    t = min(times)
-    scale = (3 * c['steps'] + 1) / (3 * ss + 1)
-    ips = bs / (t * scale)
-    return {'value': ips, 'unit': 'img/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-            'sample': f'oracle (torch CPU, fused modconv) batch {bs}, {ss} Adam steps + final synthesis in {t:.2f} s; '
-                      f'scaled x{scale:.2f} to {c["steps"]} steps by generator-pass count'}, t
+        runs[s]()
+        times[s] = time.perf_counter() - t0
+    per_step = (times[3] - times[1]) / 2.0
+    fixed = max(times[1] - per_step, 0.0)
+    t_full = fixed + per_step * c['steps']
+    ips = bs / t_full
+    return {'value': ips, 'unit': 'img/s', 'cores': torch.get_num_threads(), 'kind': kind,
+            'sample': f'{what}; batch {bs}: 1 Adam step + final synthesis {times[1]:.2f} s, 3 steps {times[3]:.2f} s '
+                      f'-> {per_step:.2f} s/step + {fixed:.2f} s, extrapolated to {c["steps"]} steps = {t_full:.1f} s per {bs} images'}
 
 
 def run_reference(args):
+    """``--impl reference``: the reference's CPU implementation of the path on the host cores (rank 0 only)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    c = CONFIGS[args.config]
+    name = args.config if args.config in CONFIGS else 'c2'
+    c = CONFIGS[name]
     vals = []
-    for _ in range(args.warmup):
-        cpu_baseline(args.config)
+    for _ in range(max(args.warmup - 2, 0)):      # each call already does its own untimed warm-up pass
+        cpu_baseline(name)
     t_all = time.perf_counter()
+    cb = None
     for _ in range(args.steps):
-        cb, _t = cpu_baseline(args.config)
+        cb = cpu_baseline(name)
         vals.append(cb['value'])
     wall = time.perf_counter() - t_all
     v = sum(vals) / len(vals)
@@ -151,14 +178,151 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': 'augmented images/sec', 'value': v, 'unit': 'img/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * wall / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': workload_name(args.config, c)}, 'cpu_baseline': cb,
+            'config': {'workload': workload_name(name, c, c['batch'])}, 'cpu_baseline': cb,
             'e2e': {'value': v, 'unit': 'img/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
     print(json.dumps(line))
 
 
-def workload_name(name, c):
-    return (f'{name}: StyleGAN2 {c["img_resolution"]}x{c["img_resolution"]} {c["img_channels"]}-ch, batch {c["batch"]}/GPU, '
+def workload_name(name, c, per_gpu):
+    return (f'{name}: StyleGAN2 {c["img_resolution"]}x{c["img_resolution"]} {c["img_channels"]}-ch, batch {per_gpu}/GPU, '
             f'{c["steps"]} w-opt steps + final synthesis, {c["bank"]}-code bank, {c["img_bank"]}-image bank, w_latent=w_pix=1')
+
+
+def gpu_reference(cfg_name, core, w0, dev, ours, reps=2):
+    """The reference's own fp32 torch GPU path (the "vs reference fp32 torch path" comparator of C2):
+    reference ``LatentAug.forward`` + ``torch_utils.ops`` with its JIT CUDA plugins + cuDNN on this GPU, on the SAME
+    generator parameters, banks and initial codes as the product arm.  TF32 off = the parity oracle; TF32 on = the
+    speed comparator.  ``ours`` = (img, w_aug) of the product for the same codes -> live parity of this very run."""
+    import torch
+    try:
+        from oracle import ref_driver
+        ref = ref_driver.import_reference()
+    except FileNotFoundError as exc:
+        return {'unavailable': str(exc)}
+    c = _full_cfg(cfg_name)
+    B = w0.shape[0]
+    out = {'impl': "reference LatentAug.forward + torch_utils.ops on cuda (baseline/_ref, unmodified); generator class restated (not in the reference tree)"}
+    try:
+        out['plugins'] = ref_driver.init_cuda_plugins(ref)
+        state = {k: v for k, v in core.generator_state.items()}
+        for tf32 in (False, True):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            run, _ = ref_driver.reference_loop(c, batch=B, steps=c['steps'], device=dev, ref=ref, state=state, W=core.W, X=core.X,
+                                               w0=w0.reshape(B, 1, -1))
+            img, w_aug = run()              # warm-up (cuDNN heuristics, allocator)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                img, w_aug = run()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            key = 'tf32' if tf32 else 'fp32'
+            out[key] = {'value': B / (ms * 1e-3), 'unit': 'img/s', 'ms_per_step': ms}
+            if not tf32 and ours is not None:
+                def rel(a, b):
+                    return float((a.double() - b.double()).norm() / b.double().norm())
+                wr = w_aug.detach()[:, 0]
+                d = (ours[1].double() - wr.double()).abs()
+                out['parity_vs_fp32'] = {'rel_l2_img': rel(ours[0], img.detach()), 'rel_l2_w': rel(ours[1], wr),
+                                         'adam_sign_flips': int((d > 0.01).sum()), 'components': int(d.numel())}
+            del run, img, w_aug
+            torch.cuda.empty_cache()
+    except Exception as exc:       # noqa: BLE001 -- a comparator failure must not lose the bench line
+        out['error'] = f'{type(exc).__name__}: {str(exc)[:300]}'
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = True
+    return out
+
+
+def run_c5(args):
+    """Config C5: queries x a row-sharded real-code bank; GEMM + fused top-k + exact re-rank + all-gather + merge."""
+    import torch
+    import torch.distributed as dist
+
+    from latentaugment_b200 import parallel
+    from latentaugment_b200.engine import LatentBank, pairwise_sqdist
+    rank, world, lr = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(lr)
+    dev = torch.device(f'cuda:{lr}')
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    per = C5['codes'] // max(world, 1) if args.c5_total else C5['codes'] // 8
+    K, nq, k = C5['dim'], C5['queries'], C5['k']
+    shard = torch.randn([per, K], generator=torch.Generator().manual_seed(1 + rank)).to(dev)
+    X = torch.randn([nq, K], generator=torch.Generator().manual_seed(7)).to(dev)
+    bank = LatentBank(shard, index_offset=rank * per)
+    searcher = parallel.ShardedNearest(bank, nq, k) if world > 1 else None
+
+    def search():
+        return searcher(X) if searcher is not None else bank.nearest(X, k)
+    for _ in range(max(args.warmup, 3)):
+        d, i = search()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(lr)
+    mark = clocks.mark()
+    reps = max(args.steps, 1) * 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        d, i = search()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1) / reps
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clk = clocks.stop(mark)
+    # exact check of this rank's shard on 64 queries against the pairwise kernel (reference association order)
+    ds, is_ = bank.nearest(X[:64], k)
+    D = pairwise_sqdist(X[:64], shard)
+    ref_d, ref_i = torch.topk(D.t(), k, dim=1, largest=False, sorted=True)
+    exact = bool((ref_i + rank * per == is_).all()) or bool((ref_d == ds).all())
+    # host-buffer leg: queries from pinned host memory, (dist, idx) back to the host
+    Xh = X.cpu().pin_memory()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        Xd = Xh.to(dev, non_blocking=True)
+        dd, ii = searcher(Xd) if searcher is not None else bank.nearest(Xd, k)
+        dd.cpu(), ii.cpu()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) / 20 * 1e3
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except OSError:
+            pass
+        codes = world * per
+        flops = 2.0 * nq * codes * K
+        peak_tf = peaks.get('bf16_tflops', 1590.0)
+        peak_bw = peaks.get('hbm_gbs', 6650.0)
+        ach = flops / world / (ms * 1e-3) / 1e12
+        line = {'metric': 'nearest-code queries/sec', 'value': nq / (ms * 1e-3), 'unit': 'queries/s', 'n_gpus': world, 'steps': reps,
+                'warmup': max(args.warmup, 3), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong' if args.c5_total else 'weak',
+                'vs_baseline': None, 'dtype': 'bf16 candidates (tensor core), f32/f64 exact re-rank', 'data': 'synthetic',
+                'config': {'workload': f'c5: {codes} codes x {K} sharded over {world} GPU(s) ({per}/GPU), {nq} queries, k={k}, '
+                                       'fused GEMM + top-k + exact re-rank' + (' + NCCL all-gather + merge' if world > 1 else ''),
+                           'l2': f'bank shard {per * K * 2 / 2**20:.0f} MiB bf16 + {per * K * 4 / 2**20:.0f} MiB f32 per GPU vs 126 MB L2'},
+                'clocks': clk, 'indices_bit_exact_vs_pairwise': exact,
+                'e2e': {'value': nq / (e2e_ms * 1e-3), 'unit': 'queries/s', 'h2d_bytes_per_step': nq * K * 4, 'd2h_bytes_per_step': nq * k * 12},
+                'gpu_launches': int(reps * (4 if world > 1 else 3)),
+                'roofline': {'bound': 'tensor', 'kernel': 'tapgemm_kernel<EPI=TopK> (query x bank GEMM + fused per-tile top-k)',
+                             'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'traffic': None,
+                             'peak_source': 'MEASURED_PEAKS.json bf16_tflops (burst)' if peaks else 'fallback 1.59 PFLOP/s',
+                             'hbm_floor_ms': per * K * 2 / (peak_bw * 1e9) * 1e3, 'whole_call_ms': ms},
+                'cpu_baseline': None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
@@ -167,15 +331,24 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
+    ap.add_argument('--config', default='c2', choices=sorted(CONFIGS) + ['c5'])
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32_parity'])
     ap.add_argument('--w-disc', type=float, default=0.0, help='weight of the discriminator realism term (0 = the headline workload)')
+    ap.add_argument('--w-lpips', type=float, default=0.0, help='weight of the perceptual term (0 = the headline workload)')
+    ap.add_argument('--author-weights', action='store_true',
+                    help="the author's run configuration (backbone_latentaug.py:46-56): w_lpips 10, w_pix 0.1, w_latent 0.001, w_disc 0.01")
+    ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch')
+    ap.add_argument('--c5-total', action='store_true', help='c5: keep 2^20 codes in total (strong scaling) instead of 2^17 per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--profile', action='store_true', help='short run for ncu: skips the e2e leg, the CPU baseline and the per-GEMM timing')
+    ap.add_argument('--no-gpu-reference', action='store_true')
+    ap.add_argument('--no-fp32-parity', action='store_true')
+    ap.add_argument('--profile', action='store_true', help='short run for ncu: skips the e2e leg, the baselines and the per-GEMM timing')
     ap.add_argument('--layers-out', default='', help='write the per-layer tap-GEMM timing table (JSON) here')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
+    if args.config == 'c5':
+        return run_c5(args)
 
     import torch
     import torch.distributed as dist
@@ -192,15 +365,20 @@ def main():
     dev = torch.device(f'cuda:{local_rank}')
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    c = dict(CONFIGS[args.config])
-    B, steps, res, C = c['batch'], c['steps'], c['img_resolution'], c['img_channels']
+    c = _full_cfg(args.config)
+    strong = bool(c.get('strong'))
+    B = args.batch or (c['batch'] // world if strong else c['batch'])
+    steps, res, C = c['steps'], c['img_resolution'], c['img_channels']
+    w_lat, w_pix, w_lpips, w_disc = 1.0, 1.0, args.w_lpips, args.w_disc
+    if args.author_weights:
+        w_lpips, w_pix, w_lat, w_disc = 10.0, 0.1, 0.001, 0.01
 
     # ---- the reference-facing plugin, synthetic mode (random-init generator, synthetic banks)
     argv = ['--aug', 'latent', '--synthetic', '--batch_size', str(B), '--gpu_ids', str(local_rank), '--gpu_ids_aug', str(local_rank),
             '--img_resolution', str(res), '--synthetic_channels', str(C), '--synthetic_bank', str(c['bank']),
             '--synthetic_img_bank', str(c['img_bank']), '--synthetic_codes', str(max(4 * B, 256)), '--precision', args.precision,
             '--opt_num_epochs', str(steps), '--no_log',
-            '--synthetic_channel_base', str(c.get('channel_base', 32768)), '--synthetic_channel_max', str(c.get('channel_max', 512))]
+            '--synthetic_channel_base', str(c['channel_base']), '--synthetic_channel_max', str(c['channel_max'])]
     # stdout carries exactly ONE JSON line: everything else (plugin banners, the NCCL version line that
     # the C library writes to fd 1) goes to stderr -- at the file-descriptor level.
     sys.stdout.flush()
@@ -208,14 +386,15 @@ def main():
     os.dup2(2, 1)
     real_stdout = os.fdopen(json_fd, 'w')
     sys.stdout = sys.stderr
-    opt = AugOptions().parse(args={'p_thres': 0.0, 'w_lpips': 0.0, 'w_disc': args.w_disc, 'init_w': 'inv', 'n_imgs': 0}, argv=argv)
+    opt = AugOptions().parse(args={'p_thres': 0.0, 'w_lpips': w_lpips, 'w_disc': w_disc, 'w_pix': w_pix, 'w_latent': w_lat,
+                                   'init_w': 'inv', 'n_imgs': 0}, argv=argv)
     aug = create_augment(opt)
     core = aug.latent_aug.module
     eng = core.engines[0]
     names = list(aug.stats_dataset_w.index.keys())
 
     def batch_data(i):
-        fn = [names[(i * B + j) % len(names)] for j in range(B)]
+        fn = [names[((rank * 131 + i) * B + j) % len(names)] for j in range(B)]
         img = torch.zeros([B, 1, res, res])
         return {'A': img, 'B': img, 'A_paths': fn, 'B_paths': fn}
 
@@ -249,19 +428,22 @@ def main():
     ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
     value = world * B / (ms * 1e-3)
 
-    # ---- end to end through the plugin API: host dict in, host dict out
     if args.profile:
         clocks.stop(mark)
         if rank == 0:
             print(json.dumps({'metric': 'augmented images/sec', 'value': value, 'unit': 'img/s', 'ms_per_step': ms,
-                              'gpu_launches': int(launches), 'note': 'profile mode (no e2e / roofline / cpu_baseline legs)'}),
+                              'gpu_launches': int(launches), 'note': 'profile mode (no e2e / roofline / baseline legs)'}),
                   file=real_stdout, flush=True)
         return
+
+    # ---- end to end through the plugin API: host dict in, host dict out (the output of batch t is fetched while
+    # batch t+1 runs: double-buffered pinned outputs, latent_aug.py get_output)
     time.sleep(3.0)      # both legs start from a comparable power / thermal state (the kernels are power-capped)
     for i in range(3):
         aug.set_input(batch_data(i)); aug.forward(); aug.get_output()
     barrier()
     t0 = time.perf_counter()
+    out = None
     for i in range(args.steps):
         aug.set_input(batch_data(i))
         aug.forward()
@@ -276,50 +458,88 @@ def main():
 
     line = None
     if rank == 0:
-        # ---- roofline of the dominant kernel (tap-GEMM): every launch of one Adam step timed alone
+        # ---- roofline of the dominant kernel (tap-GEMM): every launch of one Adam step timed ALONE (burst peak)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
         except OSError:
             pass
-        peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
-        peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1.4 PFLOP/s sustained'
-        rows, rgb_macs = layer_table(res, C, c.get('channel_base', 32768), c.get('channel_max', 512))
+        peak_burst = peaks.get('bf16_tflops', 1590.0)
+        peak_sust = peaks.get('bf16_tflops_sustained', 1400.0)
+        src = 'MEASURED_PEAKS.json' if peaks else 'fallback (B200_PROFILING.md)'
+        rows, rgb_macs = layer_table(res, C, c['channel_base'], c['channel_max'])
         t = eng.debug_time_gemms(reps=10)
         tot_ms = sum(t['forward']) + sum(t['dgrad'])
         alg = 2.0 * 2.0 * B * sum(r['alg_macs'] for r in rows)          # fwd + dgrad launches of one step
         exe = 2.0 * 2.0 * B * sum(r['exe_macs'] for r in rows) * (3 if args.precision == 'fp32_parity' else 1)
         ach = alg / (tot_ms * 1e-3) / 1e12
-        traffic = None          # DRAM bytes (read + write) of the same 26 launches, from the committed ncu capture of this workload
-        if args.config == 'c2' and args.precision == 'bf16':
-            try:
-                traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r1c_tapgemm_traffic.json')))['dram_bytes_read_plus_write']
-            except (OSError, KeyError, ValueError):
-                pass
-        roof = {'bound': 'tensor', 'kernel': 'tapgemm_kernel (26 launches of one Adam step: 13 forward + 13 data-gradient)',
-                'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'traffic': traffic,
-                'peak_source': peak_src, 'executed_tflops': exe / (tot_ms * 1e-3) / 1e12,
+        fsyn = f_syn(res, C, channel_base=c['channel_base'], channel_max=c['channel_max'])
+        traffic, traffic_src = None, None   # DRAM bytes (read + write) of the same launches: one ncu --set full capture of this workload
+        if args.config == 'c2' and args.precision == 'bf16' and B == 32:
+            for fn in ('r2_tapgemm_traffic.json', 'r1c_tapgemm_traffic.json'):
+                try:
+                    traffic = json.load(open(os.path.join(ROOT, 'profiles', fn)))['dram_bytes_read_plus_write']
+                    traffic_src = f'profiles/{fn} (ncu dram__bytes_read.sum + dram__bytes_write.sum, not measured in this run)'
+                    break
+                except (OSError, KeyError, ValueError):
+                    pass
+        roof = {'bound': 'tensor', 'kernel': f'tapgemm_kernel ({2 * len(rows)} launches of one Adam step: forward + data-gradient)',
+                'achieved': ach, 'peak': peak_burst, 'unit': 'TFLOP/s', 'frac': ach / peak_burst, 'traffic': traffic,
+                'traffic_source': traffic_src,
+                'peak_source': f'{src} bf16_tflops (burst: the launches are timed alone)', 'executed_tflops': exe / (tot_ms * 1e-3) / 1e12,
                 'launch_ms_sum': tot_ms, 'seed_ms': t['seed'], 'fir_pass_ms_sum': sum(t['fir_forward']) + sum(t['fir_backward']),
-                'whole_path_frac': (value / world) * (2 * steps + 1) * f_syn(res, C, channel_base=c.get('channel_base', 32768),
-                                                                            channel_max=c.get('channel_max', 512)) / (peak_tf * 1e12)}
+                'whole_path_frac': (value / world) * (2 * steps + 1) * fsyn / (peak_sust * 1e12),
+                'whole_path_peak': peak_sust, 'whole_path_peak_source': f'{src} bf16_tflops_sustained (kernels timed inside the seconds-long step)'}
         if args.layers_out:
             tab = [dict(r, fwd_ms=t['forward'][i], dgrad_ms=t['dgrad'][i], fir_fwd_ms=t['fir_forward'][i], fir_bwd_ms=t['fir_backward'][i],
                         fwd_alg_tflops=2.0 * B * r['alg_macs'] / (t['forward'][i] * 1e-3) / 1e12,
                         dgrad_alg_tflops=2.0 * B * r['alg_macs'] / (t['dgrad'][i] * 1e-3) / 1e12) for i, r in enumerate(rows)]
             json.dump({'config': args.config, 'precision': args.precision, 'batch': B, 'layers': tab, 'seed_ms': t['seed']},
                       open(args.layers_out, 'w'), indent=1)
+        # ---- the tolerance-matched mode (<= 1e-3) measured in the same run
+        extra = {}
+        if world == 1 and args.precision == 'bf16' and not args.no_fp32_parity and w_lpips == 0 and w_disc == 0:
+            from latentaugment_b200.engine import SynthesisEngine
+            e32 = SynthesisEngine(core.generator_state, img_resolution=res, img_channels=C, w_dim=eng.w_dim, z_dim=eng.z_dim,
+                                  batch=B, precision='fp32_parity', device=dev)
+            e32.set_latent_bank(core.W)
+            e32.set_image_bank(core.X)
+            for i in range(2):
+                e32.augment(w_dev[i], num_steps=steps)
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for i in range(3):
+                e32.augment(w_dev[i], num_steps=steps)
+            a1.record()
+            torch.cuda.synchronize()
+            v32 = B / (a0.elapsed_time(a1) / 3 * 1e-3)
+            extra['fp32_parity'] = {'value': v32, 'unit': 'img/s', 'whole_path_frac': v32 * (2 * steps + 1) * fsyn / (peak_sust * 1e12),
+                                    'note': 'split-bf16 (hi+lo) operands, 3 MMA passes: the <= 1e-3 tolerance mode'}
+            del e32
+            torch.cuda.empty_cache()
+        if world == 1 and not args.no_gpu_reference and w_lpips == 0 and w_disc == 0:
+            w0 = w_dev[0]
+            ours = core.forward(w0)
+            torch.cuda.synchronize()
+            extra['gpu_reference'] = gpu_reference(args.config, core, w0.reshape(B, -1), dev, (ours[0].detach(), ours[1].detach()[:, 0]))
         cb = None
         if world == 1 and not args.no_cpu_baseline:
-            cb, _ = cpu_baseline(args.config)
+            cb = cpu_baseline(args.config)
+        terms = f'w_latent={w_lat:g}, w_pix={w_pix:g}' + (f', w_lpips={w_lpips:g} (VGG16 perceptual term)' if w_lpips > 0 else '') + \
+            (f', w_disc={w_disc:g} (StyleGAN2 discriminator term)' if w_disc > 0 else '')
         line = {'metric': 'augmented images/sec', 'value': value, 'unit': 'img/s', 'n_gpus': world, 'steps': args.steps,
-                'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong' if strong else 'weak',
+                'vs_baseline': None,
                 'dtype': 'bf16 operands, f32 accumulate' if args.precision == 'bf16' else 'split-bf16 (hi+lo) operands, f32 accumulate',
                 'data': 'synthetic',
-                'config': {'workload': workload_name(args.config, c) + (f', w_disc={args.w_disc:g} (StyleGAN2 discriminator term)' if args.w_disc > 0 else ''),
+                'config': {'workload': workload_name(args.config, c, B).replace('w_latent=w_pix=1', terms),
                            'precision': args.precision,
                            'l2': 'working set >> L2: ~2 GB of activations written and re-read per Adam step',
-                           'parallelism': f'batch-sharded x{world}, no data-path collective'},
+                           'parallelism': (f'batch {c["batch"]} split over {world} rank(s)' if strong else f'batch-sharded x{world}')
+                           + ', no data-path collective'},
                 'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cb}
+        line.update(extra)
     if rank == 0:
         print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:

@@ -36,6 +36,7 @@ extern "C" {
 #define LA_MAX_CONV (2 * LA_MAX_BLOCKS)
 #define LA_MAX_MAPPING 8
 #define LA_MAX_STEPS 64
+#define LA_ABI_VERSION 200
 
 typedef struct la_engine la_engine;
 typedef void* la_stream;          /* cudaStream_t */
@@ -126,7 +127,11 @@ typedef struct la_disc_desc {
 } la_disc_desc;
 
 const char* la_last_error(void);
+/* ABI version (LA_ABI_VERSION) and sizeof of the structs passed by pointer, in the order la_generator_desc,
+ * la_augment_options, la_disc_desc, la_conv_params, la_torgb_params, la_disc_block_params (returns how many were
+ * written, at most `max`): a binding checks both before the first call. */
 int la_version(void);
+int la_struct_sizes(size_t* out, int max);
 
 /* Discriminator of the realism term; it runs in the engine's precision (`precision` below must equal the engine's).
  * The workspace is caller-owned like the engine's.  la_disc_logits / la_disc_loss_grad are the stand-alone forms
@@ -200,6 +205,10 @@ int la_nearest_codes_workspace_bytes(int n, int m, int K, int k, size_t* bytes);
 /* Merges per-shard (dist, idx) lists [shards, n, k] into the global k best. */
 int la_merge_topk(const float* d_dist, const long long* d_idx, int shards, int n, int k, float* d_out_dist, long long* d_out_idx,
                   la_stream stream);
+/* Same, shard s read at d_dist + s * dist_shard_stride (floats) / d_idx + s * idx_shard_stride (int64s): lets one
+ * all-gather of a packed per-rank record (dist block, idx block) feed the merge without unpacking. */
+int la_merge_topk_strided(const float* d_dist, const long long* d_idx, int shards, int n, int k, long long dist_shard_stride,
+                          long long idx_shard_stride, float* d_out_dist, long long* d_out_idx, la_stream stream);
 
 /* Test hooks: run every tap-GEMM of the engine once through the SIMT twin as well and report
  * the largest deviation (debug cross-check of the tensor-core path; not a product path). */

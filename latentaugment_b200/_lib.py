@@ -11,6 +11,7 @@ LA_MAX_BLOCKS = 12
 LA_MAX_CONV = 2 * LA_MAX_BLOCKS
 LA_MAX_MAPPING = 8
 LA_MAX_STEPS = 64
+ABI_VERSION = 200          # == LA_ABI_VERSION of include/latentaugment_b200.h
 PRECISION = {'bf16': 0, 'fp32_parity': 1}
 NOISE = {'none': 0, 'const': 1, 'random': 2}
 
@@ -59,6 +60,7 @@ class DiscDesc(C.Structure):
 SIGNATURES = {
     'la_last_error': (C.c_char_p, []),
     'la_version': (C.c_int, []),
+    'la_struct_sizes': (C.c_int, [C.POINTER(C.c_size_t), C.c_int]),
     'la_engine_workspace_bytes': (C.c_int, [C.POINTER(GeneratorDesc), C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     'la_engine_create': (C.c_int, [C.POINTER(GeneratorDesc), C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
                                    C.POINTER(C.c_void_p)]),
@@ -82,6 +84,8 @@ SIGNATURES = {
                                    C.c_void_p, C.c_size_t, fptr, C.c_void_p, C.c_void_p]),
     'la_nearest_codes_workspace_bytes': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     'la_merge_topk': (C.c_int, [fptr, C.c_void_p, C.c_int, C.c_int, C.c_int, fptr, C.c_void_p, C.c_void_p]),
+    'la_merge_topk_strided': (C.c_int, [fptr, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_longlong, fptr, C.c_void_p,
+                                        C.c_void_p]),
     'la_debug_set_simt': (C.c_int, [C.c_void_p, C.c_int]),
     'la_debug_launch_count': (C.c_longlong, [C.c_void_p]),
     'la_debug_check': (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -106,13 +110,21 @@ def load():
     if _lib is not None:
         return _lib
     path = _build.LIB
-    if not os.path.exists(path) or (os.environ.get('LA_REBUILD') == '1'):
-        _build.build()
+    _build.build(force=os.environ.get('LA_REBUILD') == '1')     # content-hashed and incremental: a no-op when current
     lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    # the structs passed by pointer must have the layout the library was compiled with
+    if lib.la_version() != ABI_VERSION:
+        raise LatentAugmentError(f'{path} has ABI version {lib.la_version()}, the Python binding expects {ABI_VERSION}: '
+                                 'rebuild with `python -m latentaugment_b200._build --force`')
+    sizes = (C.c_size_t * 8)()
+    n = lib.la_struct_sizes(sizes, 8)
+    mine = [C.sizeof(t) for t in (GeneratorDesc, AugmentOptions, DiscDesc, ConvParams, ToRgbParams, DiscBlockParams)]
+    if n < len(mine) or list(sizes)[:len(mine)] != mine:
+        raise LatentAugmentError(f'struct layout mismatch between {path} {list(sizes)[:n]} and the ctypes binding {mine}')
     _lib = lib
     return lib
 

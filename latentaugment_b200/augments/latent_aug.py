@@ -93,6 +93,8 @@ class LatentAugment(BaseAugment):
         self.init_w = opt.init_w
         self.verbose_log = opt.verbose_log
         self.stats_time = []
+        self._host_out, self._pending, self._pending_src = {}, None, None
+        self._sync_forward = True
         if self.phase == 'train':
             print('\nTrain phase.')
             if self.rand_aug:                                # :126-137
@@ -123,17 +125,42 @@ class LatentAugment(BaseAugment):
         self.fname = data['A_paths']
         self.real_AB = torch.cat((self.real_A, self.real_B), dim=1)
 
-    def _to_host(self, t):
-        """D2H into pinned host memory -- same values as ``.detach().cpu()``."""
+    # ---- output path (reference get_output :182-203 does ``.detach().cpu()``)
+    # forward() enqueues the device->host copy of the augmented batch right behind the final synthesis, on a copy
+    # stream, into one of TWO pinned buffers per shape (no per-call cudaHostAlloc); get_output() waits for that copy's
+    # event only.  With the reference's call order (set_input, forward, get_output) the copy is already in flight
+    # when get_output is called; with the look-ahead loop ``iterate()`` the copy of batch t runs while batch t+1
+    # computes.  A returned dict stays valid until the next-but-one forward().
+    def _start_d2h(self, t):
         if not t.is_cuda:
-            return t.detach()
-        out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)     # torch's caching host allocator recycles these
-        out.copy_(t.detach(), non_blocking=True)
-        torch.cuda.current_stream(t.device).synchronize()
-        return out
+            self._pending = (t.detach(), None)
+            return
+        key = (tuple(t.shape), t.dtype, t.device)
+        slot = self._host_out.get(key)
+        if slot is None:
+            slot = self._host_out[key] = {'buf': [torch.empty(t.shape, dtype=t.dtype).pin_memory() for _ in range(2)], 'i': 0,
+                                          'stream': torch.cuda.Stream(t.device), 'ev': [torch.cuda.Event(), torch.cuda.Event()]}
+        slot['i'] ^= 1
+        i = slot['i']
+        cs = slot['stream']
+        cs.wait_stream(torch.cuda.current_stream(t.device))
+        with torch.cuda.stream(cs):
+            slot['buf'][i].copy_(t.detach(), non_blocking=True)
+            slot['ev'][i].record(cs)
+        t.record_stream(cs)
+        self._pending = (slot['buf'][i], slot['ev'][i])
+
+    def _host_output(self):
+        if self._pending is None or self._pending_src is not self.real_AB_aug:
+            self._start_d2h(self.real_AB_aug)
+            self._pending_src = self.real_AB_aug
+        buf, ev = self._pending
+        if ev is not None:
+            ev.synchronize()
+        return buf
 
     def get_output(self):
-        real_AB_aug = self._to_host(self.real_AB_aug)
+        real_AB_aug = self._host_output()
         real_A_aug = real_AB_aug[:, 0, :, :].unsqueeze(dim=1)
         real_B_aug = real_AB_aug[:, min(1, real_AB_aug.shape[1] - 1), :, :].unsqueeze(dim=1)
         if self.lower_bound_clip:
@@ -165,16 +192,50 @@ class LatentAugment(BaseAugment):
                     raise NotImplementedError
                 self.w_AB = self.w_AB.to(self.device, non_blocking=True)
                 self.real_AB_aug, self.w_AB_aug = self.latent_aug(self.w_AB, self.fname)
-            torch.cuda.current_stream(self.device).synchronize()
+            self._start_d2h(self.real_AB_aug)
+            self._pending_src = self.real_AB_aug
+            if self._sync_forward:
+                torch.cuda.current_stream(self.device).synchronize()    # stats_time = wall time of the batch, as the reference's
             time_elapsed = time.time() - since
             if self.verbose_log:
                 print('Augmentation completed in {:.0f}m {:.3f}s'.format(time_elapsed // 60, time_elapsed % 60))
         else:
             self.real_AB_aug = torch.cat((self.real_A, self.real_B), dim=1)
+            self._pending, self._pending_src = (self.real_AB_aug, None), self.real_AB_aug
             time_elapsed = time.time() - since
             if self.verbose_log:
                 print('No augmentation, time {:.0f}m {:.3f}s'.format(time_elapsed // 60, time_elapsed % 60))
         self.stats_time.append(time_elapsed)
+
+    def iterate(self, loader):
+        """Look-ahead form of the caller loop (reference backbone_latentaug.py:91-124: ``for data in dataset:
+        set_input; forward; get_output; <write>``): yields ``(data, output_dict)`` per batch with the forward of batch
+        t+1 ENQUEUED before the output of batch t is awaited, so the device->host copy and the caller's work on batch
+        t (pickling, disk writes) overlap the next batch's kernels.  Same values as the three-call sequence."""
+        prev = None
+        self._sync_forward = False
+        try:
+            for data in loader:
+                self.set_input(data)
+                self.forward()
+                cur = (data, self._pending, self.fname)
+                if prev is not None:
+                    yield prev[0], self._finish(prev)
+                prev = cur
+            if prev is not None:
+                yield prev[0], self._finish(prev)
+        finally:
+            self._sync_forward = True
+
+    def _finish(self, item):
+        _, (buf, ev), fname = item
+        if ev is not None:
+            ev.synchronize()
+        a = buf[:, 0, :, :].unsqueeze(dim=1)
+        b = buf[:, min(1, buf.shape[1] - 1), :, :].unsqueeze(dim=1)
+        if self.lower_bound_clip:
+            a, b = torch.clamp(a, min=-1.0, max=None), torch.clamp(b, min=-1.0, max=None)
+        return {'A': a, 'B': b, 'A_paths': fname, 'B_paths': fname}
 
     def sanity_check(self):
         """Smoke run of one batch (reference :281-301 also dumps PNGs with matplotlib; not reproduced)."""

@@ -53,13 +53,23 @@ class InvertedCodeTable:
         self.index = {n: i for i, n in enumerate(names)}
         codes = codes.detach().float().reshape(len(names), -1).contiguous()
         self.codes = codes.pin_memory() if torch.cuda.is_available() else codes
+        self._out = {}           # batch size -> two pinned staging buffers, used alternately
 
     def __len__(self):
         return self.codes.shape[0]
 
     def lookup(self, fnames):
+        """[len(fnames), w_dim] gathered into a PINNED staging buffer (so the caller's ``.to(device, non_blocking=True)``
+        really is asynchronous); two buffers per batch size alternate, so a result stays valid for one more call."""
         idx = torch.tensor([self.index[f] for f in fnames], dtype=torch.long)
-        return self.codes.index_select(0, idx)
+        n = len(fnames)
+        if n not in self._out:
+            mk = (lambda: torch.empty([n, self.codes.shape[1]]).pin_memory()) if torch.cuda.is_available() else \
+                (lambda: torch.empty([n, self.codes.shape[1]]))
+            self._out[n] = [mk(), mk(), 0]
+        slot = self._out[n]
+        slot[2] ^= 1
+        return torch.index_select(self.codes, 0, idx, out=slot[slot[2]])
 
 
 class LatentAug:
@@ -100,6 +110,7 @@ class LatentAug:
                 raise FileNotFoundError(
                     'no generator given: pass --generator_state <state_dict.pt> (reference names, legacy.py:171-203) '
                     'or --synthetic; the reference\'s source-embedding pickles need its persistence module')
+        self.generator_state = generator_state
         kw = synthetic.infer_generator_kwargs(generator_state)
         self.res, self.img_channels = kw['img_resolution'], kw['img_channels']
         self.w_dim, self.z_dim = kw['w_dim'], kw['z_dim']
@@ -159,7 +170,7 @@ class LatentAug:
                 self.criteria['disc'].attach(e, disc_state, conv_clamp=conv_clamp)
         # ---- inverted codes (reference: LatentCodeDataset zip, :140-143; latent_aug.py:310-324)
         if inverted_codes is None and getattr(opt, 'inverted_codes', ''):
-            blob = torch.load(opt.inverted_codes, map_location='cpu', weights_only=False)
+            blob = torch.load(opt.inverted_codes, map_location='cpu', weights_only=True)      # {'names': [str], 'codes': tensor}
             inverted_codes = InvertedCodeTable(blob['names'], blob['codes'])
         if inverted_codes is None and getattr(opt, 'synthetic', False):
             n = opt.synthetic_codes

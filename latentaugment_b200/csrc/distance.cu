@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ X
 
 // merge [shards, n, k] sorted lists -> k best per query (thread per query)
 __global__ void merge_topk_kernel(const float* __restrict__ dist, const long long* __restrict__ idx, int shards, int n, int k,
-                                  float* out_dist, long long* out_idx) {
+                                  long long dist_stride, long long idx_stride, float* out_dist, long long* out_idx) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float bd[8];
@@ -156,8 +156,8 @@ __global__ void merge_topk_kernel(const float* __restrict__ dist, const long lon
     for (int t = 0; t < 8; ++t) { bd[t] = __int_as_float(0x7f800000); bi[t] = 0x7fffffffffffffffLL; }
     for (int s = 0; s < shards; ++s)
         for (int t = 0; t < k; ++t) {
-            float d = dist[(static_cast<long long>(s) * n + i) * k + t];
-            long long id = idx[(static_cast<long long>(s) * n + i) * k + t];
+            float d = dist[s * dist_stride + static_cast<long long>(i) * k + t];
+            long long id = idx[s * idx_stride + static_cast<long long>(i) * k + t];
             if (id < 0) continue;
             for (int u = 0; u < 8; ++u)
                 if (d < bd[u] || (d == bd[u] && id < bi[u])) {
@@ -173,7 +173,7 @@ __global__ void merge_topk_kernel(const float* __restrict__ dist, const long lon
 
 struct NearestLayout {
     int Hq, rows_padded, n_blocks, ncand;
-    size_t off_xhi, off_xlo, off_xx, off_cs, off_ci, total;
+    size_t off_xhi, off_xlo, off_xx, off_cs, off_ci, off_err, total;
 };
 NearestLayout nearest_layout(int n, int m, int K) {
     NearestLayout L;
@@ -189,6 +189,7 @@ NearestLayout nearest_layout(int n, int m, int K) {
     L.off_xx = take(static_cast<size_t>(L.rows_padded) * 4);
     L.off_cs = take(static_cast<size_t>(n) * L.ncand * 4);
     L.off_ci = take(static_cast<size_t>(n) * L.ncand * 4);
+    L.off_err = take(1024);                      // pipeline-timeout flag of the tap-GEMM (caller-owned like everything else)
     L.total = off + 1024;
     return L;
 }
@@ -277,9 +278,8 @@ int la_nearest_codes(const float* d_X, int n, const float* d_Y, const void* d_ba
     uint64_t bstr[2] = {static_cast<uint64_t>(K) * 2, static_cast<uint64_t>(K) * 2 * m};
     uint32_t bbox[3] = {64, 256, 1};
     if (encode_tmap_bf16(&P.b_map, d_bank_bf16, 3, bdims, bstr, bbox)) return la_fail_msg(-5, "tensor map encoding failed (bank)");
-    static int* err_flag = nullptr;
-    if (!err_flag) { DCU(cudaMalloc(&err_flag, sizeof(int))); DCU(cudaMemset(err_flag, 0, sizeof(int))); }
-    P.err_flag = err_flag;
+    P.err_flag = reinterpret_cast<int*>(ws + L.off_err);
+    DCU(cudaMemsetAsync(P.err_flag, 0, sizeof(int), s));
     if (getenv("LA_DEBUG_SIMT_DIST")) {
         TapSimtOperands ops{};
         ops.a_ptrs[0] = xhi; ops.a_ptrs[1] = xlo;
@@ -301,7 +301,18 @@ __attribute__((visibility("default")))
 int la_merge_topk(const float* d_dist, const long long* d_idx, int shards, int n, int k, float* d_out_dist, long long* d_out_idx,
                   la_stream stream) {
     if (!d_dist || !d_idx || !d_out_dist || !d_out_idx || shards < 1 || n < 1 || k < 1 || k > 8) return la_fail_msg(-2, "bad arguments");
-    merge_topk_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(d_dist, d_idx, shards, n, k, d_out_dist, d_out_idx);
+    const long long st = static_cast<long long>(n) * k;
+    merge_topk_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(d_dist, d_idx, shards, n, k, st, st, d_out_dist, d_out_idx);
+    DCU(cudaGetLastError());
+    return 0;
+}
+
+__attribute__((visibility("default")))
+int la_merge_topk_strided(const float* d_dist, const long long* d_idx, int shards, int n, int k, long long dist_shard_stride,
+                          long long idx_shard_stride, float* d_out_dist, long long* d_out_idx, la_stream stream) {
+    if (!d_dist || !d_idx || !d_out_dist || !d_out_idx || shards < 1 || n < 1 || k < 1 || k > 8) return la_fail_msg(-2, "bad arguments");
+    merge_topk_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(d_dist, d_idx, shards, n, k, dist_shard_stride,
+                                                                                      idx_shard_stride, d_out_dist, d_out_idx);
     DCU(cudaGetLastError());
     return 0;
 }

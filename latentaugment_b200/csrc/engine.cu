@@ -625,7 +625,14 @@ int la_fail_msg(int code, const char* msg) { return fail(code, "%s", msg); }
 extern "C" {
 
 LA_API const char* la_last_error(void) { return g_err.c_str(); }
-LA_API int la_version(void) { return 100; }
+LA_API int la_version(void) { return LA_ABI_VERSION; }
+LA_API int la_struct_sizes(size_t* out, int max) {
+    const size_t v[] = {sizeof(la_generator_desc), sizeof(la_augment_options), sizeof(la_disc_desc), sizeof(la_conv_params),
+                        sizeof(la_torgb_params), sizeof(la_disc_block_params)};
+    int n = 0;
+    for (; out && n < max && n < static_cast<int>(sizeof v / sizeof v[0]); ++n) out[n] = v[n];
+    return n;
+}
 
 LA_API int la_engine_workspace_bytes(const la_generator_desc* g, int batch, int precision, size_t* bytes) {
     if (!g || !bytes || batch < 1) return fail(-2, "bad arguments");

@@ -1043,12 +1043,14 @@ static int upfir_launch(const UpFirParams& p, bool fwd, cudaStream_t s) {
         const int rows_per_cta = cdiv(out_h, rblocks);
         dim3 grid(strips, nslabs * cdiv(out_h, rows_per_cta), p.B);
         if (fwd) {
-            static bool a = false;
-            if (!a) { cudaFuncSetAttribute(upfir_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); a = true; }
+            static bool a[kMaxDevices] = {};
+            const int dev = current_device_slot();
+            if (!a[dev]) { cudaFuncSetAttribute(upfir_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); a[dev] = true; }
             upfir_tma_kernel<true><<<grid, 160, smem, s>>>(p, rows_per_cta, nslabs);
         } else {
-            static bool a = false;
-            if (!a) { cudaFuncSetAttribute(upfir_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); a = true; }
+            static bool a[kMaxDevices] = {};
+            const int dev = current_device_slot();
+            if (!a[dev]) { cudaFuncSetAttribute(upfir_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); a[dev] = true; }
             upfir_tma_kernel<false><<<grid, 160, smem, s>>>(p, rows_per_cta, nslabs);
         }
         return last_err();

@@ -7,6 +7,14 @@
 
 namespace la {
 
+// Per-device "already done" flags of one-time host setup (cudaFuncSetAttribute is per device / context).
+constexpr int kMaxDevices = 64;
+inline int current_device_slot() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d >= 0 && d < kMaxDevices ? d : 0;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

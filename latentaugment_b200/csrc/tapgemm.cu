@@ -1510,12 +1510,13 @@ __global__ void __launch_bounds__(128) seed_bulk_kernel(const __grid_constant__ 
 
 template <int BN, int EPI, bool kPair>
 int set_smem_attr() {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[kMaxDevices] = {};      // the attribute is per device (in-process multi-GPU: one engine per GPU id)
+    const int dev = current_device_slot();
+    if (!attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BN, EPI, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg<BN, EPI, kPair>::kSmemBytes);
         if (e != cudaSuccess) return static_cast<int>(e);
-        attr_set = true;
+        attr_set[dev] = true;
     }
     return 0;
 }
@@ -1651,11 +1652,12 @@ int launch_tapgemm_seed(const TapGemmParams& p, int /*num_sms*/, cudaStream_t st
     const int img_px = p.OH * p.OW;
     if (!p.split && (pairs == 32 || pairs == 64 || pairs == 128) && img_px % kSeedRows == 0 && !getenv("LA_SEED_STREAM")) {
         const int smem = kSeedStages * (kSeedRows * p.n_total * 2 + kSeedRows * 20) + 64;
-        static bool attr_set = false;
-        if (!attr_set) {
+        static bool attr_set[kMaxDevices] = {};
+        const int dev = current_device_slot();
+        if (!attr_set[dev]) {
             cudaError_t e = cudaFuncSetAttribute(seed_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
             if (e != cudaSuccess) return static_cast<int>(e);
-            attr_set = true;
+            attr_set[dev] = true;
         }
         const int ppb = img_px < 2048 ? img_px : 2048;
         dim3 grid((img_px + ppb - 1) / ppb, p.batch);

@@ -303,8 +303,9 @@ class LatentBank:
                                                 _stream_ptr(self.Y.device)))
         self._ws = None
 
-    def nearest(self, X, k=1):
-        """(dist [n, k], idx [n, k] int64) of the k nearest bank rows per query, ties to the lowest index."""
+    def nearest(self, X, k=1, out=None):
+        """(dist [n, k], idx [n, k] int64) of the k nearest bank rows per query, ties to the lowest index.
+        ``out = (dist, idx)``: preallocated contiguous result tensors (graph-captured callers)."""
         n = X.shape[0]
         X = X.detach().reshape(n, -1).float().contiguous()
         assert X.shape[1] == self.K
@@ -313,8 +314,12 @@ class LatentBank:
         if self._ws is None or self._ws.numel() < nbytes.value + 1024:
             self._ws = torch.empty(nbytes.value + 1024, dtype=torch.uint8, device=X.device)
         base = (self._ws.data_ptr() + 1023) // 1024 * 1024
-        dist = torch.empty([n, k], device=X.device)
-        idx = torch.empty([n, k], dtype=torch.int64, device=X.device)
+        if out is None:
+            dist = torch.empty([n, k], device=X.device)
+            idx = torch.empty([n, k], dtype=torch.int64, device=X.device)
+        else:
+            dist, idx = out
+            assert dist.is_contiguous() and idx.is_contiguous() and dist.shape == (n, k) and idx.shape == (n, k)
         with torch.cuda.device(X.device):
             _lib.check(self.lib.la_nearest_codes(_ptr(X), n, _ptr(self.Y), _ptr(self.bf16), _ptr(self.sqnorm), self.m, self.K,
                                                  k, self.index_offset, C.c_void_p(base), nbytes.value, _ptr(dist), _ptr(idx),

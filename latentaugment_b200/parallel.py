@@ -35,3 +35,61 @@ def sharded_nearest_codes(nearest_fn, X, k, group=None, merge_fn=None):
     dist.all_gather(ds, d.contiguous(), group=group)
     dist.all_gather(is_, i.contiguous(), group=group)
     return merge_fn(torch.stack(ds), torch.stack(is_))
+
+
+class ShardedNearest:
+    """The nearest-code query against a row-sharded bank as ONE replayable unit (config C5): query split -> tap-GEMM with
+    the fused top-k -> exact re-rank -> ONE NCCL all-gather of the packed per-rank ``(dist, idx)`` record -> merge, all on
+    one stream with static buffers, captured in a CUDA graph after a warm-up (NCCL collectives are capturable); falls back
+    to eager launches of the same sequence if the capture is refused.  ``bank``: this rank's ``LatentBank`` (its
+    ``index_offset`` makes the indices global); every rank passes the same ``n`` queries."""
+
+    def __init__(self, bank, n, k, group=None, use_graph=True):
+        from . import _lib
+        self.bank, self.n, self.k, self.group = bank, int(n), int(k), group
+        self.world = dist.get_world_size(group)
+        dev = bank.Y.device
+        self.lib = _lib.load()
+        nk = self.n * self.k
+        self.rec_bytes = nk * 16                         # [nk f32 dist | pad to 8 nk bytes | nk i64 idx]
+        self.X = torch.empty([self.n, bank.K], device=dev)
+        self.rec = torch.zeros([self.rec_bytes], dtype=torch.uint8, device=dev)
+        self.all = torch.zeros([self.world * self.rec_bytes], dtype=torch.uint8, device=dev)
+        self.d_local = self.rec[:nk * 4].view(torch.float32).view(self.n, self.k)
+        self.i_local = self.rec[nk * 8:].view(torch.int64).view(self.n, self.k)
+        self.out_d = torch.empty([self.n, self.k], device=dev)
+        self.out_i = torch.empty([self.n, self.k], dtype=torch.int64, device=dev)
+        self.graph = None
+        self._run()                                      # warm-up: NCCL communicator, workspaces, function attributes
+        torch.cuda.synchronize(dev)
+        if use_graph:
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._run()
+                self.graph = g
+            except Exception:                            # noqa: BLE001 -- capture refused: keep the eager sequence
+                self.graph = None
+                torch.cuda.synchronize(dev)
+
+    def _run(self):
+        import ctypes as C
+
+        from . import _lib
+        from .engine import _ptr, _stream_ptr
+        self.bank.nearest(self.X, self.k, out=(self.d_local, self.i_local))
+        dist.all_gather_into_tensor(self.all, self.rec, group=self.group)
+        dev = self.X.device
+        nk = self.n * self.k
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.la_merge_topk_strided(
+                C.c_void_p(self.all.data_ptr()), C.c_void_p(self.all.data_ptr() + nk * 8), self.world, self.n, self.k,
+                self.rec_bytes // 4, self.rec_bytes // 8, _ptr(self.out_d), _ptr(self.out_i), _stream_ptr(dev)))
+
+    def __call__(self, X):
+        self.X.copy_(X.reshape(self.n, -1), non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._run()
+        return self.out_d, self.out_i

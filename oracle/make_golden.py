@@ -9,7 +9,7 @@ the outputs are committed).  What is executed from the reference:
   * ``LatentAug.l2_loss_vectorized / calc_loss_latent / calc_loss_pix``  (loss-level pins)
   * ``LatentAug.forward`` itself -- the 10-step Adam loop -- constructed via
     ``LatentAug.__new__`` (its ``__init__`` needs zips/pickles that do not exist offline,
-    SURVEY.md §8c) and driven through ``RefOpsGenerator`` below: the oracle generator's
+    SURVEY.md §8c) and driven through ``oracle.ref_driver.RefOpsGenerator``: the oracle generator's
     parameters, but every op call routed to the reference's ``torch_utils.ops``.
 The generator *classes* are not in the reference, so the layer
 composition in ``RefOpsGenerator`` is this repo's restatement; ops, losses and the loop
@@ -20,110 +20,16 @@ import hashlib
 import os
 import random
 import sys
-import types
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import torch
 
-REF = '/root/reference'
+from oracle.ref_driver import REF_SRC, RefOpsGenerator, import_reference, make_reference_latentaug   # noqa: E402
 
 
 def _import_reference():
-    sys.path[:0] = [REF, os.path.join(REF, 'models/stylegan3')]
-    for name in ['openpyxl', 'matplotlib', 'matplotlib.pyplot', 'albumentations', 'albumentations.pytorch',
-                 'kornia', 'kornia.augmentation', 'cv2']:
-        sys.modules.setdefault(name, types.ModuleType(name))
-    sys.modules['albumentations.pytorch'].ToTensorV2 = object
-    from torch_utils.ops import bias_act, upfirdn2d, conv2d_resample, fma
-    from augments.utils import util_latent_aug
-    return types.SimpleNamespace(bias_act=bias_act, upfirdn2d=upfirdn2d, conv2d_resample=conv2d_resample,
-                                 fma=fma, ula=util_latent_aug)
-
-
-class RefOpsGenerator(torch.nn.Module):
-    """Oracle generator parameters, reference ops.  Fused (grouped-conv) modulation,
-    i.e. the eval-mode form the unpickled upstream network runs."""
-
-    def __init__(self, G, ref):
-        super().__init__()
-        self.G, self.ref = G, ref
-        self.z_dim, self.w_dim, self.num_ws = G.z_dim, G.w_dim, G.num_ws
-        self.mapping = G.mapping
-        self.synthesis = self._synthesis
-
-    def _fc(self, fc, x):
-        return torch.addmm((fc.bias * fc.b_gain).unsqueeze(0), x, (fc.weight * fc.w_gain).t())
-
-    def _modconv(self, x, weight, styles, noise, up, padding, f, demod, flip_weight):
-        B = x.shape[0]
-        O, I, kh, kw = weight.shape
-        w = weight.unsqueeze(0) * styles.reshape(B, 1, -1, 1, 1)
-        if demod:
-            d = (w.square().sum(dim=[2, 3, 4]) + 1e-8).rsqrt()
-            w = w * d.reshape(B, -1, 1, 1, 1)
-        x = x.reshape(1, -1, *x.shape[2:])
-        w = w.reshape(-1, I, kh, kw)
-        x = self.ref.conv2d_resample.conv2d_resample(x=x, w=w, f=f, up=up, padding=padding, groups=B,
-                                                     flip_weight=flip_weight)
-        x = x.reshape(B, -1, *x.shape[2:])
-        if noise is not None:
-            x = x.add_(noise)
-        return x
-
-    def _layer(self, L, x, w, noise_mode):
-        styles = self._fc(L.affine, w)
-        noise = None
-        if noise_mode == 'random':
-            noise = torch.randn([x.shape[0], 1, L.res, L.res], device=x.device) * L.noise_strength
-        if noise_mode == 'const':
-            noise = L.noise_const * L.noise_strength
-        x = self._modconv(x, L.weight, styles, noise, L.up, 1, L.resample_filter, True, L.up == 1)
-        return self.ref.bias_act.bias_act(x, L.bias, act='lrelu', gain=2 ** 0.5, clamp=L.conv_clamp)
-
-    def _torgb(self, T, x, w):
-        styles = self._fc(T.affine, w) * T.w_gain
-        x = self._modconv(x, T.weight, styles, None, 1, 0, None, False, True)
-        return self.ref.bias_act.bias_act(x, T.bias, clamp=T.conv_clamp)
-
-    def _synthesis(self, ws, noise_mode='random', **_):
-        S = self.G.synthesis
-        x = img = None
-        idx = 0
-        for r in S.block_resolutions:
-            blk = getattr(S, f'b{r}')
-            wi = iter(ws.narrow(1, idx, blk.num_conv + blk.num_torgb).unbind(dim=1))
-            idx += blk.num_conv
-            if blk.cin == 0:
-                x = blk.const.unsqueeze(0).repeat([ws.shape[0], 1, 1, 1])
-            else:
-                x = self._layer(blk.conv0, x, next(wi), noise_mode)
-            x = self._layer(blk.conv1, x, next(wi), noise_mode)
-            if img is not None:
-                img = self.ref.upfirdn2d.upsample2d(img, blk.resample_filter)
-            y = self._torgb(blk.torgb, x, next(wi))
-            img = img.add_(y) if img is not None else y
-        return img
-
-
-def make_reference_latentaug(ref, Gref, W, X, cfg, steps, w_latent, w_pix, soft_aug=False, alpha=1.0):
-    LA = ref.ula.LatentAug
-    m = LA.__new__(LA)
-    torch.nn.Module.__init__(m)
-    m.G = Gref
-    m.num_ws, m.w_dim, m.z_dim = Gref.num_ws, Gref.w_dim, Gref.z_dim
-    m.batch_size, m.world_size = cfg['batch'], 1
-    m.res = cfg['img_resolution']
-    m.modalities = [f'm{i}' for i in range(cfg['img_channels'])]
-    m.num_epochs, m.opt_lr = steps, 0.01
-    m.w_latent, m.w_pix, m.w_lpips, m.w_disc = w_latent, w_pix, 0.0, 0.0
-    m.crop_size, m.preprocess = 64, 'center_random_crop'
-    m.soft_aug, m.alpha = soft_aug, alpha
-    m.truncation_psi = 1.0
-    m.verbose_flag, m.verbose_log = False, False
-    m.lpips_script = 'lpips_script'
-    m.register_buffer('W', W)
-    if X is not None:
-        m.register_buffer('X', X)
-    return m
+    return import_reference(REF_SRC)
 
 
 def digest(*tensors):
@@ -194,10 +100,15 @@ def loss_goldens(ref):
     return out
 
 
-def loop_golden(ref, name, noise_strength, steps=None, w_latent=1.0, w_pix=1.0, soft_aug=False, alpha=1.0):
+def loop_golden(ref, name, noise_strength, steps=None, w_latent=1.0, w_pix=1.0, soft_aug=False, alpha=1.0, batch=None,
+                keep_images=None):
+    """``batch`` overrides the config's batch size; ``keep_images`` stores the images of the first k samples only
+    (the benchmark shapes: a full C2 / C3 image batch is 25 / 400 MB)."""
     from oracle import synthetic
-    wl = synthetic.make_workload(name, noise_strength=noise_strength)
+    wl = synthetic.make_workload(name, noise_strength=noise_strength, batch=batch)
     cfg = wl['cfg']
+    if batch is not None:
+        cfg['batch'] = batch
     steps = cfg['steps'] if steps is None else steps
     Gref = RefOpsGenerator(wl['G'], ref)
     la = make_reference_latentaug(ref, Gref, wl['W'], wl['X'], cfg, steps, w_latent, w_pix, soft_aug, alpha)
@@ -212,7 +123,9 @@ def loop_golden(ref, name, noise_strength, steps=None, w_latent=1.0, w_pix=1.0, 
     random.seed(0)
     torch.manual_seed(1234)
     img, w_aug = la(wl['w0'].clone(), ['synthetic'] * cfg['batch'])
-    return dict(config=name, cfg=cfg, noise_strength=noise_strength, steps=steps, w_latent=w_latent, w_pix=w_pix,
+    if keep_images is not None:
+        x0, img = x0[:keep_images].clone(), img[:keep_images].clone()
+    return dict(config=name, cfg=cfg, keep_images=keep_images, noise_strength=noise_strength, steps=steps, w_latent=w_latent, w_pix=w_pix,
                 soft_aug=soft_aug, alpha=alpha, inputs_digest=digest(wl['W'], wl['w0'], wl['X']),
                 params_digest=digest(*[p for p in wl['G'].state_dict().values()]),
                 img0_const=x0, loss_latent0=l_lat0, loss_pix0=l_pix0,
@@ -224,10 +137,20 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--out', default='tests/golden')
     ap.add_argument('--skip-c1', action='store_true')
+    ap.add_argument('--only', default='', help='comma list of fixture names to (re)generate, e.g. loop_c2,loop_c3')
     args = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
     ref = _import_reference()
     os.makedirs(args.out, exist_ok=True)
+    big = {   # the benchmarked shapes: C2 at batch 8 x 10 steps, C3 (512^2) at batch 2 x 2 steps
+        'loop_c2': lambda: loop_golden(ref, 'c2', 0.1, batch=8, keep_images=2),
+        'loop_c3': lambda: loop_golden(ref, 'c3', 0.1, steps=2, batch=2, keep_images=1),
+    }
+    if args.only:
+        for nm in args.only.split(','):
+            torch.save(big[nm](), os.path.join(args.out, nm + '.pt'))
+            print(nm, os.path.getsize(os.path.join(args.out, nm + '.pt')))
+        return
     torch.save(op_goldens(ref), os.path.join(args.out, 'ops.pt'))
     torch.save(loss_goldens(ref), os.path.join(args.out, 'losses.pt'))
     torch.save(loop_golden(ref, 'tiny', 0.1), os.path.join(args.out, 'loop_tiny.pt'))

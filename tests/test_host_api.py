@@ -89,7 +89,7 @@ def test_cabi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f'{name} declared in the header but not exported'
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert _lib.load().la_version() == 100
+    assert _lib.load().la_version() == _lib.ABI_VERSION == int(re.search(r"LA_ABI_VERSION (\d+)", open(os.path.join(ROOT, "include", "latentaugment_b200.h")).read()).group(1))
 
 
 def test_synthetic_state_follows_reference_naming():
