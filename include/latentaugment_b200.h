@@ -35,8 +35,9 @@ extern "C" {
 #define LA_MAX_BLOCKS 12          /* resolutions 4 .. 8192 */
 #define LA_MAX_CONV (2 * LA_MAX_BLOCKS)
 #define LA_MAX_MAPPING 8
-#define LA_MAX_STEPS 64
-#define LA_ABI_VERSION 200
+#define LA_MAX_STEPS 64            /* steps whose loss values are logged (the loop itself is not capped) */
+#define LA_LOSS_COLS 5             /* loss-log row: latent, pixel, total, discriminator, perceptual */
+#define LA_ABI_VERSION 201
 
 typedef struct la_engine la_engine;
 typedef void* la_stream;          /* cudaStream_t */
@@ -90,12 +91,15 @@ typedef struct la_generator_desc {
 typedef struct la_augment_options {
     int num_steps;                 /* opt_num_epochs */
     float lr;                      /* opt_lr */
-    float w_latent, w_pix;         /* criteria weights (the perceptual term is not part of this boundary) */
+    float w_latent, w_pix;         /* criteria weights */
     int soft_aug;                  /* 0: hard_aug, 1: smooth_aug */
     float alpha;
     int final_noise_mode;          /* la_noise_mode of the last synthesis (reference default: random) */
     int n_modalities;              /* number of leading image channels the pixel criterion covers */
     float w_disc;                  /* weight of the discriminator realism term; > 0 needs la_set_discriminator */
+    float w_lpips;                 /* weight of the perceptual term; > 0 needs la_set_lpips + la_set_feature_bank */
+    int lpips_crop_x, lpips_crop_y;/* crop window of this call inside the centre crop (util_dataset.py:284-296: drawn once per forward) */
+    int lpips_norm_mode;           /* 0: lpips_script form (pair mean), 1: forward_tr form (pair sum / bank size) */
 } la_augment_options;
 
 /* One residual block of the StyleGAN2 'resnet' discriminator at resolution res (names per legacy.py:267-287). */
@@ -126,9 +130,23 @@ typedef struct la_disc_desc {
     const float* d_b4_out_bias;    /* [1] */
 } la_disc_desc;
 
+/* VGG16 feature extractor + LPIPS linear layers of the perceptual term (reference augments/criteria/lpips/networks.py:87-97,
+ * 22-32; torchvision vgg16.features parameter order).  Taps are the ReLU outputs relu1_2, relu2_2, relu3_3, relu4_3, relu5_3
+ * (1-based layer indices 4, 9, 16, 23, 30 of BaseNet.forward, networks.py:52-64); a tap is used iff its lin weight is given.
+ * The in-tree LPIPS uses taps 16/23/30 (networks.py:94), the NVIDIA TorchScript model of the lpips_script path all five. */
+#define LA_VGG_CONVS 13
+#define LA_VGG_TAPS 5
+typedef struct la_vgg_desc {
+    const float* d_conv_weight[LA_VGG_CONVS];  /* [cout, cin, 3, 3]: 3-64-64 | 128-128 | 256-256-256 | 512-512-512 | 512-512-512 */
+    const float* d_conv_bias[LA_VGG_CONVS];    /* [cout] */
+    const float* d_lin_weight[LA_VGG_TAPS];    /* [C_tap] (the 1x1 conv C -> 1 without bias), or null = tap not used */
+    float mean[3], std[3];                     /* z-score of the replicated grey crop (networks.py:41-50) */
+    int crop_size;                             /* crop_size_aug: 64 (power of two >= 64) */
+} la_vgg_desc;
+
 const char* la_last_error(void);
 /* ABI version (LA_ABI_VERSION) and sizeof of the structs passed by pointer, in the order la_generator_desc,
- * la_augment_options, la_disc_desc, la_conv_params, la_torgb_params, la_disc_block_params (returns how many were
+ * la_augment_options, la_disc_desc, la_conv_params, la_torgb_params, la_disc_block_params, la_vgg_desc (returns how many were
  * written, at most `max`): a binding checks both before the first call. */
 int la_version(void);
 int la_struct_sizes(size_t* out, int max);
@@ -142,6 +160,22 @@ int la_set_discriminator(la_engine* e, const la_disc_desc* d, void* d_workspace,
 int la_disc_logits(la_engine* e, const float* d_img, float* d_logits, la_stream stream);
 /* loss = w_disc * mean softplus(-D(img)) -> d_loss [1];  d loss / d img -> d_grad [batch, img_channels, res, res] */
 int la_disc_loss_grad(la_engine* e, const float* d_img, float w_disc, float* d_loss, float* d_grad, la_stream stream);
+
+/* Perceptual term (reference calc_loss_lpips_torchscript / calc_loss_lpips_tr, util_latent_aug.py:387-424, + LPIPS.forward,
+ * criteria/lpips/lpips.py:44-56).  la_set_lpips installs the network (caller-owned workspace, engine precision);
+ * la_set_feature_bank takes the real crops [M, img_channels, crop, crop] fp32 in [-1, 1] (the reference builds its feature
+ * bank from one random window per real image, util_latent_aug.py:564-579) and keeps only the bank moments;
+ * la_lpips_loss_grad is the stand-alone form of what la_augment does every step when w_lpips > 0:
+ * crop window at (crop_x, crop_y) inside the centre crop, loss [1] = w_lpips * mean over modalities of the normalised pair
+ * distance (norm_mode 0: / (n * m), 1: / m), grad [batch, C, res, res] = d loss / d img. */
+int la_lpips_workspace_bytes(const la_vgg_desc* v, int batch, int img_channels, int precision, size_t* bytes);
+int la_set_lpips(la_engine* e, const la_vgg_desc* v, void* d_workspace, size_t workspace_bytes, la_stream stream);
+int la_set_feature_bank(la_engine* e, const float* d_crops, int M, la_stream stream);
+int la_lpips_loss_grad(la_engine* e, const float* d_img, int crop_x, int crop_y, float w_lpips, int norm_mode, float* d_loss,
+                       float* d_grad, la_stream stream);
+/* Test hook: normalised activations of used tap k (0-based among the used taps) from the last la_lpips_loss_grad /
+ * la_augment step: fp32 [batch * img_channels, h, w, C] (NHWC); *count receives the element count (d_out may be null). */
+int la_lpips_tap(la_engine* e, int k, float* d_out, size_t* count, la_stream stream);
 
 /* filtered_lrelu (reference torch_utils/ops/filtered_lrelu.py:56-153; the StyleGAN3 synthesis-layer op):
  * y = decimate_down( FIR_fd( clamp( lrelu( FIR_fu( pad( zero_insert_up( x + b ) ) ) * up^2 ) * gain ) ) ).
@@ -184,8 +218,8 @@ int la_synthesis(la_engine* e, const float* d_ws, long long stride_n, long long 
 size_t la_noise_floats(const la_engine* e);
 
 /* The hot path.  d_w0 [batch, w_dim] initial codes; outputs: d_img [batch, C, res, res],
- * d_w_aug [batch, w_dim] (one row per sample), d_loss_log [num_steps, 4] = (latent, pixel, total, 0)
- * or NULL.  d_final_noise as in la_synthesis (may be NULL unless final_noise_mode == RANDOM). */
+ * d_w_aug [batch, w_dim] (one row per sample), d_loss_log [min(num_steps, LA_MAX_STEPS), LA_LOSS_COLS] =
+ * (latent, pixel, total, discriminator, perceptual) or NULL.  d_final_noise as in la_synthesis (may be NULL unless final_noise_mode == RANDOM). */
 int la_augment(la_engine* e, const float* d_w0, const la_augment_options* opt, const float* d_final_noise, float* d_img,
                float* d_w_aug, float* d_loss_log, la_stream stream);
 

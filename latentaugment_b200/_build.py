@@ -12,6 +12,7 @@ shuffled) rebuilds nothing.
 import hashlib
 import json
 import os
+import re
 import subprocess
 import sys
 
@@ -20,8 +21,8 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, 'csrc')
 LIB = os.path.join(PKG, 'liblatentaugment_b200.so')
 STAMP = LIB + '.srchash'
-SOURCES = ['tapgemm.cu', 'kernels.cu', 'distance.cu', 'engine.cu', 'disc.cu', 'filtered_lrelu.cu']
-HEADERS = ['tapgemm.cuh', 'kernels.cuh', 'sm100.cuh', 'plan.cuh', 'disc.cuh',
+SOURCES = ['tapgemm.cu', 'kernels.cu', 'distance.cu', 'engine.cu', 'disc.cu', 'filtered_lrelu.cu', 'lpips.cu']
+HEADERS = ['tapgemm.cuh', 'kernels.cuh', 'sm100.cuh', 'plan.cuh', 'disc.cuh', 'lpips.cuh',
            os.path.join(ROOT, 'include', 'latentaugment_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden']
@@ -46,10 +47,28 @@ def _header_paths():
     return [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS]
 
 
+def _deps(path, seen=None):
+    """The file plus every project header it includes with quotes, transitively."""
+    seen = seen if seen is not None else []
+    path = os.path.normpath(path)
+    if path in seen or not os.path.exists(path):
+        return seen
+    seen.append(path)
+    for m in re.finditer(r'^\s*#\s*include\s+"([^"]+)"', open(path).read(), re.M):
+        _deps(os.path.join(os.path.dirname(path), m.group(1)), seen)
+    return seen
+
+
 def source_hashes():
-    """{source: hash of (that source, every header, the flags)} for the sources that exist."""
-    hdr = _sha(_header_paths(), ' '.join(NVCC_FLAGS))
-    return {s: _sha([os.path.join(CSRC, s)], hdr) for s in SOURCES}
+    """{source: hash of (that source, the headers it includes, the flags)}."""
+    known = set(os.path.normpath(h) for h in _header_paths())
+    out = {}
+    for s in SOURCES:
+        deps = _deps(os.path.join(CSRC, s))
+        missing = [d for d in deps[1:] if d not in known]
+        assert not missing, f'{s} includes headers that HEADERS does not list: {missing}'
+        out[s] = _sha(deps, ' '.join(NVCC_FLAGS))
+    return out
 
 
 def _stored():

@@ -11,7 +11,9 @@ LA_MAX_BLOCKS = 12
 LA_MAX_CONV = 2 * LA_MAX_BLOCKS
 LA_MAX_MAPPING = 8
 LA_MAX_STEPS = 64
-ABI_VERSION = 200          # == LA_ABI_VERSION of include/latentaugment_b200.h
+LA_LOSS_COLS = 5
+LA_VGG_CONVS, LA_VGG_TAPS = 13, 5
+ABI_VERSION = 201          # == LA_ABI_VERSION of include/latentaugment_b200.h
 PRECISION = {'bf16': 0, 'fp32_parity': 1}
 NOISE = {'none': 0, 'const': 1, 'random': 2}
 
@@ -40,7 +42,13 @@ class GeneratorDesc(C.Structure):
 class AugmentOptions(C.Structure):
     _fields_ = [('num_steps', C.c_int), ('lr', C.c_float), ('w_latent', C.c_float), ('w_pix', C.c_float),
                 ('soft_aug', C.c_int), ('alpha', C.c_float), ('final_noise_mode', C.c_int), ('n_modalities', C.c_int),
-                ('w_disc', C.c_float)]
+                ('w_disc', C.c_float), ('w_lpips', C.c_float), ('lpips_crop_x', C.c_int), ('lpips_crop_y', C.c_int),
+                ('lpips_norm_mode', C.c_int)]
+
+
+class VggDesc(C.Structure):
+    _fields_ = [('d_conv_weight', fptr * LA_VGG_CONVS), ('d_conv_bias', fptr * LA_VGG_CONVS), ('d_lin_weight', fptr * LA_VGG_TAPS),
+                ('mean', C.c_float * 3), ('std', C.c_float * 3), ('crop_size', C.c_int)]
 
 
 class DiscBlockParams(C.Structure):
@@ -75,6 +83,11 @@ SIGNATURES = {
     'la_set_discriminator': (C.c_int, [C.c_void_p, C.POINTER(DiscDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
     'la_disc_logits': (C.c_int, [C.c_void_p, fptr, fptr, C.c_void_p]),
     'la_disc_loss_grad': (C.c_int, [C.c_void_p, fptr, C.c_float, fptr, fptr, C.c_void_p]),
+    'la_lpips_workspace_bytes': (C.c_int, [C.POINTER(VggDesc), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    'la_set_lpips': (C.c_int, [C.c_void_p, C.POINTER(VggDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
+    'la_set_feature_bank': (C.c_int, [C.c_void_p, fptr, C.c_int, C.c_void_p]),
+    'la_lpips_loss_grad': (C.c_int, [C.c_void_p, fptr, C.c_int, C.c_int, C.c_float, C.c_int, fptr, fptr, C.c_void_p]),
+    'la_lpips_tap': (C.c_int, [C.c_void_p, C.c_int, fptr, C.POINTER(C.c_size_t), C.c_void_p]),
     'la_filtered_lrelu': (C.c_int, [fptr, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float), C.c_int,
                                     fptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, fptr, C.c_void_p]),
@@ -122,7 +135,7 @@ def load():
                                  'rebuild with `python -m latentaugment_b200._build --force`')
     sizes = (C.c_size_t * 8)()
     n = lib.la_struct_sizes(sizes, 8)
-    mine = [C.sizeof(t) for t in (GeneratorDesc, AugmentOptions, DiscDesc, ConvParams, ToRgbParams, DiscBlockParams)]
+    mine = [C.sizeof(t) for t in (GeneratorDesc, AugmentOptions, DiscDesc, ConvParams, ToRgbParams, DiscBlockParams, VggDesc)]
     if n < len(mine) or list(sizes)[:len(mine)] != mine:
         raise LatentAugmentError(f'struct layout mismatch between {path} {list(sizes)[:n]} and the ctypes binding {mine}')
     _lib = lib

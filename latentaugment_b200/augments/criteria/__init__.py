@@ -6,16 +6,16 @@ under ``augments/criteria/<name>/``.  Here each term is a plugin class with the 
 handled by the loop exactly as ``loss = -latent - pix - lpips + disc`` (:270).
 
 Inside the captured CUDA loop the latent and pixel terms run fused (bank-moment form,
-csrc/kernels.cu) and so does the discriminator term (csrc/disc.cu); the plugin objects configure the engine and evaluate the same quantity
+csrc/kernels.cu) and so do the discriminator term (csrc/disc.cu) and the perceptual term (csrc/lpips.cu); the plugin objects configure the engine and evaluate the same quantity
 stand-alone through the pairwise-distance kernel (the reference's ``l2_loss_vectorized``).
 """
 from .disc import DiscriminatorCriterion
 from .latent import LatentCriterion
+from .lpips import PerceptualCriterion
 from .pix import PixelCriterion
 
-REGISTRY = {'latent': LatentCriterion, 'pix': PixelCriterion, 'disc': DiscriminatorCriterion}
-# terms whose networks / weights cannot exist offline (SURVEY.md §8c, §8f rank 2)
-UNAVAILABLE = {'lpips': 'perceptual term needs the NVIDIA vgg16.pt / LPIPS weights (SURVEY.md §8f rank 2)'}
+REGISTRY = {'latent': LatentCriterion, 'pix': PixelCriterion, 'lpips': PerceptualCriterion, 'disc': DiscriminatorCriterion}
+UNAVAILABLE = {}
 
 
 def find_criterion_using_name(name):
@@ -27,7 +27,7 @@ def find_criterion_using_name(name):
 
 
 def create_criteria(opt):
-    """{name: instance} for every term with a positive weight; raises for the unavailable ones."""
+    """{name: instance} for every term with a positive weight."""
     out = {}
     for name in ('latent', 'pix', 'lpips', 'disc'):
         w = float(getattr(opt, 'w_' + name, 0.0))

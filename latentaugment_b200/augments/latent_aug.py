@@ -69,6 +69,7 @@ class LatentAugment(BaseAugment):
                             help='tensor-core operand precision (fp32_parity = split-bf16, rel-L2 1e-3; bf16 = 1e-2)')
         parser.add_argument('--generator_state', type=str, default='', help='torch state_dict file with the reference parameter names')
         parser.add_argument('--discriminator_state', type=str, default='', help='torch state_dict file of the StyleGAN2 discriminator (needed when w_disc > 0)')
+        parser.add_argument('--vgg_state', type=str, default='', help='torch state_dict file of VGG16 (torchvision features.* names) + LPIPS lin layers lin.{k}.weight (needed when w_lpips > 0)')
         parser.add_argument('--latent_bank', type=str, default='', help='tensor file [M, num_ws, w_dim] or [M, w_dim]')
         parser.add_argument('--image_bank', type=str, default='', help='tensor file [M, C, res, res] in [-1, 1]')
         parser.add_argument('--inverted_codes', type=str, default='', help="file with {'names': [...], 'codes': [N, w_dim]}")

@@ -43,6 +43,20 @@ def get_crop_params(load_size, crop_size, preprocess='center_random_crop'):
     return {'crop_pos': (x, y)}
 
 
+def feature_bank_crops(X, res, crop_size, preprocess='center_random_crop'):
+    """The windows the reference feeds to VGG when it builds ``fea_{mode}`` (compute_stats(manifold='features_*') ->
+    extract_features_mode*, :564-598): for every modality, for every bank image, a FRESH ``get_params`` draw (two python
+    ``random.randint`` calls) inside the centre crop.  X [M, C, res, res] -> [M, C, crop, crop]."""
+    M, C = X.shape[0], X.shape[1]
+    off = center_crop_bounds(res)[0] if preprocess == 'center_random_crop' else 0
+    out = torch.empty([M, C, crop_size, crop_size], dtype=X.dtype)
+    for c in range(C):
+        for m in range(M):
+            x, y = get_crop_params(res, crop_size, preprocess)['crop_pos']
+            out[m, c] = X[m, c, off + y:off + y + crop_size, off + x:off + x + crop_size]
+    return out
+
+
 class InvertedCodeTable:
     """Preloaded table of inverted codes keyed by sample file name: replaces the reference's
     per-sample zip read + unpickle in ``sample_from_inversion`` (latent_aug.py:310-324;
@@ -94,7 +108,8 @@ class LatentAug:
         self.crop_size, self.preprocess = opt.crop_size_aug, opt.preprocess_aug
         self.verbose_flag = bool(getattr(opt, 'verbose_log', False))
         self.precision = getattr(opt, 'precision', 'fp32_parity')
-        self.criteria = create_criteria(opt)           # raises NotImplementedError for a positive lpips weight
+        self.lpips_script = getattr(opt, 'lpips_script', 'lpips_script')
+        self.criteria = create_criteria(opt)
         self.stats_loss, self.stats_time = {}, {}
         self.module = self
 
@@ -133,7 +148,7 @@ class LatentAug:
             latent_bank = self.engines[0].mapping(z)[:, :1].cpu()
         if image_bank is None and getattr(opt, 'image_bank', ''):
             image_bank = torch.load(opt.image_bank, map_location='cpu', weights_only=True)
-        if image_bank is None and getattr(opt, 'synthetic', False) and self.w_pix > 0:
+        if image_bank is None and getattr(opt, 'synthetic', False) and (self.w_pix > 0 or self.w_lpips > 0):
             image_bank = torch.rand([opt.synthetic_img_bank, self.img_channels, self.res, self.res],
                                     generator=torch.Generator().manual_seed(3)) * 2 - 1
         self.W = self.X = None
@@ -168,6 +183,23 @@ class LatentAug:
                                         '(reference names, legacy.py:267-287) or --synthetic')
             for e in self.engines:
                 self.criteria['disc'].attach(e, disc_state, conv_clamp=conv_clamp)
+        # ---- perceptual term (reference: self.vgg16 / self.lpips + register_buffer('fea_{mode}'), :125-131,160-181)
+        if self.w_lpips > 0:
+            vgg_state = None
+            if getattr(opt, 'vgg_state', ''):
+                vgg_state = torch.load(opt.vgg_state, map_location='cpu', weights_only=True)
+            elif getattr(opt, 'synthetic', False):
+                from ..criteria.lpips import taps_and_norm
+                vgg_state = synthetic.random_vgg_state(seed=7, taps=taps_and_norm(self.lpips_script)[0])
+            if vgg_state is None:
+                raise FileNotFoundError('w_lpips > 0 needs the VGG16 + LPIPS parameters: --vgg_state <state_dict.pt> (torchvision '
+                                        'features.* names + lin.{k}.weight) or --synthetic')
+            if image_bank is None:
+                raise FileNotFoundError('w_lpips > 0 needs an image bank (--image_bank or --synthetic)')
+            self.X = image_bank.float() if self.X is None else self.X
+            crops = feature_bank_crops(self.X, self.res, self.crop_size, self.preprocess)
+            for e in self.engines:
+                self.criteria['lpips'].attach(e, vgg_state, crops, lpips_script=self.lpips_script, crop_size=self.crop_size)
         # ---- inverted codes (reference: LatentCodeDataset zip, :140-143; latent_aug.py:310-324)
         if inverted_codes is None and getattr(opt, 'inverted_codes', ''):
             blob = torch.load(opt.inverted_codes, map_location='cpu', weights_only=True)      # {'names': [str], 'codes': tensor}
@@ -194,6 +226,10 @@ class LatentAug:
 
     def calc_loss_pix(self, x, x_bank):
         return self.criteria['pix'](x, x_bank)
+
+    def calc_loss_lpips(self, x, crop_pos):
+        """:387-424 (x is one engine's batch shard, uncropped; ``crop_pos`` from ``get_crop_params``)."""
+        return self.criteria['lpips'](x, crop_pos)
 
     def calc_loss_disc(self, x):
         """:363-371 (x is one engine's batch shard)."""
@@ -222,11 +258,13 @@ class LatentAug:
         if w.ndim == 2:
             w = self.z_to_w(w)
         assert w.shape[0] == self.batch_size
-        get_crop_params(self.res, self.crop_size, self.preprocess)      # :216 (RNG draws; the crop feeds lpips only)
+        crop_pos = get_crop_params(self.res, self.crop_size, self.preprocess)['crop_pos']      # :216 (one window per call, feeds lpips)
+        lpips_norm = self.criteria['lpips'].norm_mode if self.w_lpips > 0 else 0
         imgs, ws_out, self.last_losses = [], [], []
         for e, wsh in zip(self.engines, self._shards(w)):
             out = e.augment(wsh, num_steps=self.num_epochs, lr=self.opt_lr, w_latent=self.w_latent, w_pix=self.w_pix,
-                            w_disc=self.w_disc, soft_aug=self.soft_aug, alpha=self.alpha, final_noise_mode='random',
+                            w_disc=self.w_disc, w_lpips=self.w_lpips, lpips_crop=crop_pos, lpips_norm_mode=lpips_norm,
+                            soft_aug=self.soft_aug, alpha=self.alpha, final_noise_mode='random',
                             return_losses=self.verbose_flag)
             imgs.append(out[0])
             ws_out.append(out[1])
@@ -235,10 +273,26 @@ class LatentAug:
         img = torch.cat([i.to(self.device, non_blocking=True) for i in imgs]) if self.world_size > 1 else imgs[0]
         w_aug = torch.cat([x.to(self.device, non_blocking=True) for x in ws_out]) if self.world_size > 1 else ws_out[0]
         if self.verbose_flag:
-            for rank, ll in enumerate(self.last_losses):
-                for t, row in enumerate(ll.cpu().tolist()):
-                    print(f'[rank {rank}] epoch {t}: loss_latent {row[0]:.6f} loss_pix {row[1]:.6f} loss_disc {row[3]:.6f} loss {row[2]:.6f}')
+            self._log_first_call()
         return img, self.broadcasting(w_aug.unsqueeze(1))
+
+    def _log_first_call(self):
+        """Per-epoch loss values of the FIRST call only, as the reference logs them (:278-300: ``stats_loss[f'epoch_{t}']``,
+        ``losses.jsonl`` in save_dir, then ``verbose_flag = False``); the matplotlib plots are not reproduced."""
+        import json
+        import os
+        rows = torch.stack([ll.cpu() for ll in self.last_losses]).mean(0).tolist()       # replicas averaged
+        for t, row in enumerate(rows):
+            self.stats_loss[f'epoch_{t}'] = {'loss_latent': row[0], 'loss_pix': row[1], 'loss_lpips': row[4], 'loss_disc': row[3], 'loss': row[2]}
+            print(f'epoch {t + 1:>4d}/{self.num_epochs}, ' + ' '.join(f'{k} {v:<4.2f}' for k, v in self.stats_loss[f'epoch_{t}'].items()))
+        if self.save_dir:
+            try:
+                os.makedirs(self.save_dir, exist_ok=True)
+                with open(os.path.join(self.save_dir, 'losses.jsonl'), 'w') as f:
+                    f.write(json.dumps(self.stats_loss, indent=2) + '\n')
+            except OSError:
+                pass
+        self.verbose_flag = False
 
     __call__ = forward
 

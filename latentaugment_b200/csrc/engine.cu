@@ -15,6 +15,7 @@
 #include "tapgemm.cuh"
 #include "plan.cuh"
 #include "disc.cuh"
+#include "lpips.cuh"
 
 using namespace la;
 
@@ -110,6 +111,9 @@ struct la_engine {
     float cur_w_pix = -1.f, cur_w_disc = -1.f;
     la_disc* disc = nullptr;          // realism-term discriminator (optional)
     float* disc_loss = nullptr;
+    la_lpips* lp = nullptr;           // perceptual term (optional)
+    float* lpips_loss = nullptr;
+    float cur_w_lpips = -1.f;
 };
 
 namespace {
@@ -232,11 +236,12 @@ int plan(la_engine* e, char* ws, size_t* bytes_out) {
     e->step = bp.take<int>(1);
     e->err_flag = bp.take<int>(1);
     e->disc_loss = bp.take<float>(1);
+    e->lpips_loss = bp.take<float>(1);
     e->dbg_clock = bp.take<unsigned long long>(64);
     const size_t wn = static_cast<size_t>(B) * g.w_dim;
     e->w_opt = bp.take<float>(wn); e->m = bp.take<float>(wn); e->v = bp.take<float>(wn);
     e->w0 = bp.take<float>(wn); e->w_aug = bp.take<float>(wn);
-    e->loss_log = bp.take<float>(LA_MAX_STEPS * 4);
+    e->loss_log = bp.take<float>(LA_MAX_STEPS * LA_LOSS_COLS);
     const size_t mapn = static_cast<size_t>(B) * (g.w_dim > g.z_dim ? g.w_dim : g.z_dim);
     e->map_a = bp.take<float>(mapn); e->map_b = bp.take<float>(mapn);
     bp.take<char>(1024);
@@ -575,6 +580,10 @@ int run_backward(la_engine* e, const la_augment_options& opt, cudaStream_t s) {
         if (disc_forward(e->disc, top.img, s, &e->launches) || disc_backward(e->disc, opt.w_disc, top.g_img, 1, e->disc_loss, s, &e->launches))
             return fail(-6, "discriminator: %s", disc_last_error());
     }
+    if (opt.w_lpips > 0.f) {         // perceptual term (util_latent_aug.py:387-424): - w_lpips * pair-normalised LPIPS distance to the bank
+        if (lpips_forward(e->lp, top.img, s, &e->launches) || lpips_backward(e->lp, top.g_img, 1, e->lpips_loss, s, &e->launches))
+            return fail(-7, "lpips: %s", lpips_last_error());
+    }
     for (int b = g.num_blocks - 1; b >= 0; --b) {
         Rgb& r = e->rgb[b];
         LA(rgb_backward(r.g_img, r.parts, r.nparts, r.p.d_bias, g.img_channels, g.conv_clamp, B, r.res, r.g_rgb,
@@ -595,7 +604,7 @@ int run_backward(la_engine* e, const la_augment_options& opt, cudaStream_t s) {
 int run_step(la_engine* e, const la_augment_options& opt, cudaStream_t s) {
     const la_generator_desc& g = e->g;
     const int B = e->batch;
-    const bool synth = opt.w_pix > 0.f || opt.w_disc > 0.f;
+    const bool synth = opt.w_pix > 0.f || opt.w_disc > 0.f || opt.w_lpips > 0.f;
     if (synth) {
         CU(cudaMemsetAsync(e->red_all, 0, e->red_bytes, s));
         LA(run_forward(e, e->w_opt, g.w_dim, 0, LA_NOISE_CONST, nullptr, nullptr, s));
@@ -603,7 +612,7 @@ int run_step(la_engine* e, const la_augment_options& opt, cudaStream_t s) {
     }
     LA(adam_step(e->partial, e->nchunks, synth ? 1 : 0, e->w_sum, e->lat_m2, e->consts, e->step, e->w_opt, e->m, e->v, B, g.w_dim,
                  e->loss_parts, synth ? e->n_loss_parts : 0, e->bank_m2, opt.n_modalities, e->crop_size, e->loss_log, LA_MAX_STEPS,
-                 opt.w_disc > 0.f ? e->disc_loss : nullptr, s));
+                 opt.w_disc > 0.f ? e->disc_loss : nullptr, opt.w_lpips > 0.f ? e->lpips_loss : nullptr, s));
     e->launches += 3;
     return 0;
 }
@@ -627,8 +636,9 @@ extern "C" {
 LA_API const char* la_last_error(void) { return g_err.c_str(); }
 LA_API int la_version(void) { return LA_ABI_VERSION; }
 LA_API int la_struct_sizes(size_t* out, int max) {
+    static_assert(kLossCols == LA_LOSS_COLS, "loss-log row width");
     const size_t v[] = {sizeof(la_generator_desc), sizeof(la_augment_options), sizeof(la_disc_desc), sizeof(la_conv_params),
-                        sizeof(la_torgb_params), sizeof(la_disc_block_params)};
+                        sizeof(la_torgb_params), sizeof(la_disc_block_params), sizeof(la_vgg_desc)};
     int n = 0;
     for (; out && n < max && n < static_cast<int>(sizeof v / sizeof v[0]); ++n) out[n] = v[n];
     return n;
@@ -683,6 +693,7 @@ LA_API int la_engine_create(const la_generator_desc* g, int batch, int precision
 LA_API void la_engine_destroy(la_engine* e) {
     if (!e) return;
     if (e->disc) disc_destroy(e->disc);
+    if (e->lp) lpips_destroy(e->lp);
     if (e->step_graph) cudaGraphExecDestroy(e->step_graph);
     if (e->ev_in) cudaEventDestroy(e->ev_in);
     if (e->ev_out) cudaEventDestroy(e->ev_out);
@@ -756,12 +767,13 @@ LA_API int la_synthesis(la_engine* e, const float* d_ws, long long stride_n, lon
 LA_API int la_augment(la_engine* e, const float* d_w0, const la_augment_options* opt, const float* d_final_noise, float* d_img, float* d_w_aug,
                float* d_loss_log, la_stream stream) {
     if (!e || !d_w0 || !opt || !d_img || !d_w_aug) return fail(-2, "bad arguments");
-    if (opt->num_steps < 0 || opt->num_steps > LA_MAX_STEPS) return fail(-2, "num_steps must be in [0, %d]", LA_MAX_STEPS);
+    if (opt->num_steps < 0) return fail(-2, "num_steps must be >= 0");      // (only the first LA_MAX_STEPS loss rows are logged)
     if (opt->w_pix > 0.f && !e->has_img_bank) return fail(-2, "w_pix > 0 needs la_set_image_bank");
     if (opt->w_latent > 0.f && !e->has_lat_bank) return fail(-2, "w_latent > 0 needs la_set_latent_bank");
     if (opt->final_noise_mode == LA_NOISE_RANDOM && !d_final_noise) return fail(-2, "final_noise_mode random needs d_final_noise");
     if (opt->n_modalities != e->g.img_channels) return fail(-2, "n_modalities must equal img_channels");
     if (opt->w_disc > 0.f && !e->disc) return fail(-2, "w_disc > 0 needs la_set_discriminator");
+    if (opt->w_lpips > 0.f && (!e->lp || !lpips_has_bank(e->lp))) return fail(-2, "w_lpips > 0 needs la_set_lpips and la_set_feature_bank");
     const la_generator_desc& g = e->g;
     const int B = e->batch;
     const size_t wbytes = sizeof(float) * B * g.w_dim;
@@ -775,15 +787,21 @@ LA_API int la_augment(la_engine* e, const float* d_w0, const la_augment_options*
     CU(cudaMemsetAsync(e->m, 0, wbytes, w));
     CU(cudaMemsetAsync(e->v, 0, wbytes, w));
     CU(cudaMemsetAsync(e->step, 0, sizeof(int), w));
-    CU(cudaMemsetAsync(e->loss_log, 0, sizeof(float) * 4 * LA_MAX_STEPS, w));
-    if ((e->cur_w_pix != opt->w_pix || e->cur_w_disc != opt->w_disc) && e->step_graph) {   // baked into the criterion launches
+    CU(cudaMemsetAsync(e->loss_log, 0, sizeof(float) * LA_LOSS_COLS * LA_MAX_STEPS, w));
+    if (opt->w_lpips > 0.f) {        // crop window inside the centre crop (util_dataset.py:304-309,325-332): absolute origin
+        if (lpips_set_call(e->lp, e->crop_off + opt->lpips_crop_x, e->crop_off + opt->lpips_crop_y, opt->w_lpips, opt->lpips_norm_mode, w))
+            return fail(-7, "lpips: %s", lpips_last_error());
+    }
+    if ((e->cur_w_pix != opt->w_pix || e->cur_w_disc != opt->w_disc || (e->cur_w_lpips > 0.f) != (opt->w_lpips > 0.f)) &&
+        e->step_graph) {   // baked into the criterion launches
         cudaGraphExecDestroy(e->step_graph);
         e->step_graph = nullptr;
     }
     e->cur_w_pix = opt->w_pix;
     e->cur_w_disc = opt->w_disc;
+    e->cur_w_lpips = opt->w_lpips;
     for (int it = 0; it < opt->num_steps; ++it) {
-        const bool synth = opt->w_pix > 0.f || opt->w_disc > 0.f;
+        const bool synth = opt->w_pix > 0.f || opt->w_disc > 0.f || opt->w_lpips > 0.f;
         if (!synth || e->graph_disabled || !e->warmed) {
             LA(run_step(e, *opt, w));
             e->warmed = true;
@@ -811,7 +829,8 @@ LA_API int la_augment(la_engine* e, const float* d_w0, const la_augment_options*
     LA(run_forward(e, e->w_aug, g.w_dim, 0, opt->final_noise_mode, d_final_noise, d_img, w));
     CU(cudaMemcpyAsync(d_w_aug, e->w_aug, wbytes, cudaMemcpyDeviceToDevice, w));
     if (d_loss_log && opt->num_steps > 0)
-        CU(cudaMemcpyAsync(d_loss_log, e->loss_log, sizeof(float) * 4 * opt->num_steps, cudaMemcpyDeviceToDevice, w));
+        CU(cudaMemcpyAsync(d_loss_log, e->loss_log, sizeof(float) * LA_LOSS_COLS * (opt->num_steps < LA_MAX_STEPS ? opt->num_steps : LA_MAX_STEPS),
+                           cudaMemcpyDeviceToDevice, w));
     LA(bridge_out(e, s));
     return 0;
 }
@@ -857,6 +876,58 @@ LA_API int la_disc_loss_grad(la_engine* e, const float* d_img, float w_disc, flo
     LA(f4_to_nchw(top.g_img, e->batch, e->g.img_channels, e->g.img_resolution, d_grad, e->work));
     CU(cudaMemcpyAsync(d_loss, e->disc_loss, sizeof(float), cudaMemcpyDeviceToDevice, e->work));
     LA(bridge_out(e, s));
+    return 0;
+}
+
+LA_API int la_lpips_workspace_bytes(const la_vgg_desc* v, int batch, int img_channels, int precision, size_t* bytes) {
+    if (!v || !bytes || batch < 1) return fail(-2, "bad arguments");
+    if (lpips_workspace_bytes(*v, batch, img_channels, precision == LA_PRECISION_FP32_PARITY, bytes)) return fail(-2, "%s", lpips_last_error());
+    return 0;
+}
+
+LA_API int la_set_lpips(la_engine* e, const la_vgg_desc* v, void* d_workspace, size_t workspace_bytes, la_stream stream) {
+    if (!e || !v || !d_workspace) return fail(-2, "bad arguments");
+    if (e->lp) { lpips_destroy(e->lp); e->lp = nullptr; }
+    if (e->step_graph) { cudaGraphExecDestroy(e->step_graph); e->step_graph = nullptr; }
+    if (lpips_create(*v, e->batch, e->g.img_channels, e->g.img_resolution, e->split, e->num_sms, d_workspace, workspace_bytes,
+                     static_cast<cudaStream_t>(stream), &e->lp))
+        return fail(-7, "lpips: %s", lpips_last_error());
+    return 0;
+}
+
+LA_API int la_set_feature_bank(la_engine* e, const float* d_crops, int M, la_stream stream) {
+    if (!e || !e->lp || !d_crops || M < 1) return fail(-2, "bad arguments (la_set_lpips first)");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    LA(bridge_in(e, s));
+    if (lpips_set_bank(e->lp, d_crops, M, e->work, &e->launches)) return fail(-7, "lpips: %s", lpips_last_error());
+    LA(bridge_out(e, s));
+    return 0;
+}
+
+LA_API int la_lpips_loss_grad(la_engine* e, const float* d_img, int crop_x, int crop_y, float w_lpips, int norm_mode, float* d_loss,
+                              float* d_grad, la_stream stream) {
+    if (!e || !e->lp || !d_img || !d_loss || !d_grad) return fail(-2, "bad arguments (la_set_lpips first)");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    Rgb& top = e->rgb.back();
+    LA(bridge_in(e, s));
+    LA(nchw_to_f4(d_img, e->batch, e->g.img_channels, e->g.img_resolution, top.img, e->work));
+    // (the term enters the objective with a minus sign; the stand-alone call returns d loss / d img, hence -w)
+    if (lpips_set_call(e->lp, e->crop_off + crop_x, e->crop_off + crop_y, -w_lpips, norm_mode, e->work) ||
+        lpips_forward(e->lp, top.img, e->work, &e->launches) || lpips_backward(e->lp, top.g_img, 0, e->lpips_loss, e->work, &e->launches))
+        return fail(-7, "lpips: %s", lpips_last_error());
+    LA(f4_to_nchw(top.g_img, e->batch, e->g.img_channels, e->g.img_resolution, d_grad, e->work));
+    LA(prep_scale(e->lpips_loss, -1.f, e->lpips_loss, 1, e->work));
+    CU(cudaMemcpyAsync(d_loss, e->lpips_loss, sizeof(float), cudaMemcpyDeviceToDevice, e->work));
+    LA(bridge_out(e, s));
+    return 0;
+}
+
+LA_API int la_lpips_tap(la_engine* e, int k, float* d_out, size_t* count, la_stream stream) {
+    if (!e || !e->lp) return fail(-2, "bad arguments (la_set_lpips first)");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (d_out) LA(bridge_in(e, s));
+    if (lpips_copy_tap(e->lp, k, d_out, count, e->work)) return fail(-7, "lpips: %s", lpips_last_error());
+    if (d_out) LA(bridge_out(e, s));
     return 0;
 }
 

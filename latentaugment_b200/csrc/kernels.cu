@@ -813,7 +813,7 @@ __global__ void gw_partial_kernel(const float* __restrict__ g_s, const float* __
 __global__ void loss_value_kernel(const float* __restrict__ w, const float* __restrict__ w_sum_bank, const float* __restrict__ lat_m2, const AdamConsts* C,
                                   const int* step_counter, int batch, int w_dim, const float* __restrict__ pix_parts,
                                   int n_pix_parts, const float* __restrict__ bank_m2, int img_c, int crop_size, float* loss_log,
-                                  int max_steps, const float* __restrict__ disc_loss) {
+                                  int max_steps, const float* __restrict__ disc_loss, const float* __restrict__ lpips_loss) {
     double sq = 0.0, dot = 0.0, px = 0.0;
     for (int e = threadIdx.x; e < batch * w_dim; e += blockDim.x) {
         const double v = w[e];
@@ -839,11 +839,13 @@ __global__ void loss_value_kernel(const float* __restrict__ w, const float* __re
                 const double hw = static_cast<double>(crop_size) * crop_size;
                 l_pix = C->w_pix * (px / (batch * hw) + m2 / hw) / img_c;
             }
-            loss_log[4 * t + 0] = static_cast<float>(l_lat);
-            loss_log[4 * t + 1] = static_cast<float>(l_pix);
+            loss_log[kLossCols * t + 0] = static_cast<float>(l_lat);
+            loss_log[kLossCols * t + 1] = static_cast<float>(l_pix);
             const double l_disc = disc_loss ? disc_loss[0] : 0.0;
-            loss_log[4 * t + 2] = static_cast<float>(-l_lat - l_pix + l_disc);      // util_latent_aug.py:270
-            loss_log[4 * t + 3] = static_cast<float>(l_disc);
+            const double l_lpips = lpips_loss ? lpips_loss[0] : 0.0;
+            loss_log[kLossCols * t + 2] = static_cast<float>(-l_lat - l_pix - l_lpips + l_disc);      // util_latent_aug.py:270
+            loss_log[kLossCols * t + 3] = static_cast<float>(l_disc);
+            loss_log[kLossCols * t + 4] = static_cast<float>(l_lpips);
         }
     }
 }
@@ -1145,9 +1147,9 @@ int gw_partial(const float* g_s, const float* a_cat, const int* chunk_soff, cons
 }
 int adam_step(const float* partial, int nchunks, int use_partial, const float* w_sum_bank, const float* lat_m2, const AdamConsts* consts, int* step_counter,
               float* w, float* m, float* v, int batch, int w_dim, const float* pix_parts, int n_pix_parts, const float* bank_m2,
-              int img_c, int crop_size, float* loss_log, int max_steps, const float* disc_loss, cudaStream_t s) {
+              int img_c, int crop_size, float* loss_log, int max_steps, const float* disc_loss, const float* lpips_loss, cudaStream_t s) {
     loss_value_kernel<<<1, 512, 0, s>>>(w, w_sum_bank, lat_m2, consts, step_counter, batch, w_dim, pix_parts, n_pix_parts, bank_m2, img_c,
-                                        crop_size, loss_log, max_steps, disc_loss);
+                                        crop_size, loss_log, max_steps, disc_loss, lpips_loss);
     adam_kernel<<<cdiv(batch * w_dim, 256), 256, 0, s>>>(partial, nchunks, use_partial, w_sum_bank, consts, step_counter, w, m, v, batch, w_dim);
     step_inc_kernel<<<1, 1, 0, s>>>(step_counter);
     return last_err();

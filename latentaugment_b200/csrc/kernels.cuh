@@ -91,7 +91,9 @@ struct AdamConsts {      // device-resident so one captured graph serves every o
 };
 int adam_step(const float* partial, int nchunks, int use_partial, const float* w_sum_bank, const float* lat_m2, const AdamConsts* consts, int* step_counter,
               float* w, float* m, float* v, int batch, int w_dim, const float* pix_parts, int n_pix_parts, const float* bank_m2,
-              int img_c, int crop_size, float* loss_log, int max_steps, const float* disc_loss /*or null*/, cudaStream_t s);
+              int img_c, int crop_size, float* loss_log, int max_steps, const float* disc_loss /*or null*/, const float* lpips_loss /*or null*/,
+              cudaStream_t s);
+constexpr int kLossCols = 5;      // loss-log row: latent, pixel, total, discriminator, perceptual (== LA_LOSS_COLS)
 int finalize_w(const float* w_opt, const float* w0, float alpha, int soft, int batch, int w_dim, float* w_aug, cudaStream_t s);
 
 // ---- banks

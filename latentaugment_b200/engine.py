@@ -199,6 +199,75 @@ class SynthesisEngine:
             _lib.check(self.lib.la_disc_loss_grad(self.handle, _ptr(img), float(w_disc), _ptr(loss), _ptr(grad), _stream_ptr(self.device)))
         return loss[0], grad
 
+    # ---- perceptual term (reference self.vgg16 / self.lpips + the feature banks fea_{mode}, util_latent_aug.py:125-131,160-181)
+    VGG_CONV_IDX = (0, 2, 5, 7, 10, 12, 14, 17, 19, 21, 24, 26, 28)      # torchvision vgg16.features indices of the 13 convs
+    VGG_TAP_LAYERS = (4, 9, 16, 23, 30)                                  # 1-based layer indices of networks.py:52-64
+    VGG_TAP_CHANNELS = (64, 128, 256, 512, 512)
+
+    def set_lpips(self, state, taps=(16, 23, 30), crop_size=64, mean=(-.030, -.088, -.188), std=(.458, .448, .450)):
+        """``state``: torchvision names ``features.{i}.{weight,bias}`` + LPIPS lin layers ``lin.{k}.weight`` ([1, C, 1, 1] or
+        [C]; k counts the used ``taps`` in order; criteria/lpips/networks.py:22-32).  ``taps``: 1-based layer indices as in
+        ``VGG16.target_layers`` (networks.py:94)."""
+        keep = self._lpips_keep = []
+
+        def dev(t):
+            t = torch.as_tensor(t).detach().to(self.device, torch.float32).contiguous()
+            keep.append(t)
+            return t
+        d = _lib.VggDesc()
+        for j, i in enumerate(self.VGG_CONV_IDX):
+            d.d_conv_weight[j] = _ptr(dev(state[f'features.{i}.weight']))
+            d.d_conv_bias[j] = _ptr(dev(state[f'features.{i}.bias']))
+        for k, t in enumerate(taps):
+            slot = self.VGG_TAP_LAYERS.index(t)
+            w = dev(state[f'lin.{k}.weight']).reshape(-1)
+            assert w.numel() == self.VGG_TAP_CHANNELS[slot], (t, w.shape)
+            keep.append(w)
+            d.d_lin_weight[slot] = _ptr(w)
+        for k in range(3):
+            d.mean[k], d.std[k] = float(mean[k]), float(std[k])
+        d.crop_size = int(crop_size)
+        nbytes = C.c_size_t(0)
+        _lib.check(self.lib.la_lpips_workspace_bytes(C.byref(d), self.batch, self.img_channels, _lib.PRECISION[self.precision], C.byref(nbytes)))
+        self.lpips_workspace = torch.empty(nbytes.value + 1024, dtype=torch.uint8, device=self.device)
+        base = (self.lpips_workspace.data_ptr() + 1023) // 1024 * 1024
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.la_set_lpips(self.handle, C.byref(d), C.c_void_p(base), nbytes.value, _stream_ptr(self.device)))
+        torch.cuda.current_stream(self.device).synchronize()
+        self.lpips_taps, self.lpips_crop = tuple(taps), int(crop_size)
+
+    def set_feature_bank(self, crops):
+        """Real crops [M, C, crop, crop] in [-1, 1] (one window per real image, util_latent_aug.py:564-579): the engine keeps the
+        bank moments of their normalised VGG activations."""
+        crops = crops.detach().to(self.device, torch.float32).contiguous()
+        assert crops.shape[1:] == (self.img_channels, self.lpips_crop, self.lpips_crop), crops.shape
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.la_set_feature_bank(self.handle, _ptr(crops), crops.shape[0], _stream_ptr(self.device)))
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def lpips_loss_grad(self, img, crop_pos, w_lpips=1.0, norm_mode=0):
+        """(loss, d loss / d img) of the perceptual term alone -- reference calc_loss_lpips_* + autograd.  ``crop_pos`` =
+        ``(x, y)`` inside the centre crop (util_dataset.get_params)."""
+        img = img.detach().to(self.device, torch.float32).contiguous()
+        loss = torch.empty([1], device=self.device)
+        grad = torch.empty_like(img)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.la_lpips_loss_grad(self.handle, _ptr(img), int(crop_pos[0]), int(crop_pos[1]), float(w_lpips), int(norm_mode),
+                                                   _ptr(loss), _ptr(grad), _stream_ptr(self.device)))
+        return loss[0], grad
+
+    def lpips_tap(self, k):
+        """Normalised activations of used tap k from the last perceptual-term evaluation: [batch * C, h, w, C_tap] (NHWC)."""
+        n = C.c_size_t(0)
+        _lib.check(self.lib.la_lpips_tap(self.handle, k, C.c_void_p(0), C.byref(n), _stream_ptr(self.device)))
+        out = torch.empty([n.value], device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.la_lpips_tap(self.handle, k, _ptr(out), C.byref(n), _stream_ptr(self.device)))
+        slot = self.VGG_TAP_LAYERS.index(self.lpips_taps[k])
+        ch = self.VGG_TAP_CHANNELS[slot]
+        hw = int(round((n.value // (self.batch * self.img_channels * ch)) ** 0.5))
+        return out.reshape(self.batch * self.img_channels, hw, hw, ch)
+
     # ---- network
     def mapping(self, z, truncation_psi=1.0):
         """[n, z_dim] -> [n, num_ws, w_dim] (broadcast rows), reference G.mapping(z, None, truncation_psi)."""
@@ -234,21 +303,22 @@ class SynthesisEngine:
                                              _lib.NOISE[noise_mode], _ptr(nz), _ptr(img), _stream_ptr(self.device)))
         return img
 
-    def augment(self, w0, *, num_steps=10, lr=0.01, w_latent=1.0, w_pix=1.0, w_disc=0.0, soft_aug=False, alpha=1.0,
-                final_noise_mode='random', final_noise=None, return_losses=False):
+    def augment(self, w0, *, num_steps=10, lr=0.01, w_latent=1.0, w_pix=1.0, w_disc=0.0, w_lpips=0.0, lpips_crop=(0, 0),
+                lpips_norm_mode=0, soft_aug=False, alpha=1.0, final_noise_mode='random', final_noise=None, return_losses=False):
         """The hot path (reference LatentAug.forward).  w0 [batch, w_dim] or [batch, 1, w_dim]."""
         w0 = w0.detach().to(self.device, torch.float32).reshape(self.batch, self.w_dim).contiguous()
         nz = self._noise(final_noise_mode, final_noise)
         img = torch.empty([self.batch, self.img_channels, self.img_resolution, self.img_resolution], device=self.device)
         w_aug = torch.empty([self.batch, self.w_dim], device=self.device)
-        losses = torch.zeros([max(num_steps, 1), 4], device=self.device) if return_losses else None
+        nlog = min(max(num_steps, 1), _lib.LA_MAX_STEPS)
+        losses = torch.zeros([nlog, _lib.LA_LOSS_COLS], device=self.device) if return_losses else None
         opt = _lib.AugmentOptions(num_steps, lr, w_latent, w_pix, int(bool(soft_aug)), alpha, _lib.NOISE[final_noise_mode],
-                                  self.img_channels, w_disc)
+                                  self.img_channels, w_disc, w_lpips, int(lpips_crop[0]), int(lpips_crop[1]), int(lpips_norm_mode))
         with torch.cuda.device(self.device):
             _lib.check(self.lib.la_augment(self.handle, _ptr(w0), C.byref(opt), _ptr(nz), _ptr(img), _ptr(w_aug), _ptr(losses),
                                            _stream_ptr(self.device)))
         if return_losses:
-            return img, w_aug, losses[:num_steps]
+            return img, w_aug, losses[:min(num_steps, nlog)]      # columns: latent, pixel, total, discriminator, perceptual
         return img, w_aug
 
     # ---- debug hooks (tests)

@@ -99,3 +99,31 @@ def random_discriminator_state(img_resolution=256, img_channels=3, channel_base=
     sd['b4.out.weight'] = randn(1, c4)
     sd['b4.out.bias'] = torch.zeros(1, device=device)
     return sd
+
+
+# ---- perceptual term: VGG16 + LPIPS linear layers (reference criteria/lpips/networks.py:22-32,87-97)
+VGG_CFG = [64, 64, 'M', 128, 128, 'M', 256, 256, 256, 'M', 512, 512, 512, 'M', 512, 512, 512]
+VGG_CONV_IDX = [0, 2, 5, 7, 10, 12, 14, 17, 19, 21, 24, 26, 28]
+VGG_TAP_LAYERS = (4, 9, 16, 23, 30)
+VGG_TAP_CHANNELS = (64, 128, 256, 512, 512)
+
+
+def random_vgg_state(seed=7, taps=(16, 23, 30)):
+    """Seeded random VGG16 / LPIPS-lin parameters with torchvision's names (``features.{i}.weight/bias``) and
+    ``lin.{k}.weight`` [1, C, 1, 1] for the used ``taps`` in order -- for throughput runs and users without the
+    pretrained files (they cannot be downloaded offline).  He-scaled so activations stay O(1); positive lin weights."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    cin, ci = 3, 0
+    for v in VGG_CFG:
+        if v == 'M':
+            continue
+        i = VGG_CONV_IDX[ci]
+        sd[f'features.{i}.weight'] = torch.randn([v, cin, 3, 3], generator=g) * math.sqrt(2.0 / (9 * cin))
+        sd[f'features.{i}.bias'] = torch.randn([v], generator=g) * 0.05
+        cin = v
+        ci += 1
+    for k, t in enumerate(taps):
+        c = VGG_TAP_CHANNELS[VGG_TAP_LAYERS.index(t)]
+        sd[f'lin.{k}.weight'] = torch.rand([1, c, 1, 1], generator=g) * 0.5 + 0.05
+    return sd

@@ -79,16 +79,17 @@ class LatentAugOracle:
     """The N-step Adam loop on w (ULA:207-310) with the latent and pixel criteria.
 
     ``G`` exposes ``.synthesis(ws, noise_mode=...)``, ``.mapping``, ``num_ws``,
-    ``w_dim``; ``D`` (optional) is the realism-term discriminator (oracle/sg2_disc.py).  The LPIPS
-    term needs weights that are not available offline and must have zero weight.
+    ``w_dim``; ``D`` (optional) is the realism-term discriminator (oracle/sg2_disc.py); ``lpips`` (optional) =
+    dict(state, taps, script, bank_feats) configures the perceptual term (oracle/lpips.py).
     """
 
     def __init__(self, G, W=None, X=None, *, num_epochs=10, opt_lr=0.01, w_latent=1.0, w_pix=1.0,
                  w_lpips=0.0, w_disc=0.0, soft_aug=False, alpha=1.0, truncation_psi=1.0,
-                 n_modalities=None, res=None, crop_size=64, preprocess='center_random_crop', fused=True, D=None):
-        assert w_lpips == 0.0, 'oracle covers the latent, pixel and discriminator criteria'
+                 n_modalities=None, res=None, crop_size=64, preprocess='center_random_crop', fused=True, D=None, lpips=None):
+        assert w_lpips == 0.0 or lpips is not None, 'w_lpips > 0 needs the VGG / bank-feature configuration'
         assert w_disc == 0.0 or D is not None, 'w_disc > 0 needs a discriminator'
         self.G, self.W, self.X, self.D, self.w_disc = G, W, X, D, w_disc
+        self.w_lpips, self.lpips = w_lpips, lpips
         self.num_ws, self.w_dim = G.num_ws, G.w_dim
         self.num_epochs, self.opt_lr = num_epochs, opt_lr
         self.w_latent, self.w_pix = w_latent, w_pix
@@ -110,7 +111,7 @@ class LatentAugOracle:
             w = self.z_to_w(w)
         w_opt = w.detach().clone().to(torch.float32).requires_grad_(True)     # ULA:212
         optim = torch.optim.Adam([w_opt], betas=(0.9, 0.999), lr=self.opt_lr)  # ULA:213
-        get_crop_params(self.res, self.crop_size, self.preprocess)             # ULA:216 (RNG draws only)
+        crop_pos = get_crop_params(self.res, self.crop_size, self.preprocess)  # ULA:216-217 (one window per call)
         self.loss_log = []
         for _ in range(self.num_epochs):                                       # ULA:220
             ws = self.broadcasting(w_opt)
@@ -123,8 +124,14 @@ class LatentAugOracle:
             l_disc = 0.0
             if self.w_disc > 0:                                                # ULA:363-371
                 l_disc = torch.nn.functional.softplus(-self.D(x, c=None)).mean() * self.w_disc
-            loss = -l_lat - l_pix + l_disc                                     # ULA:270
-            self.loss_log.append(tuple(float(torch.as_tensor(v).detach()) for v in (l_lat, l_pix, loss, l_disc)))
+            l_lpips = 0.0
+            if self.w_lpips > 0:                                               # ULA:258-266,387-424
+                from . import lpips as olp
+                xc = olp.crop(center_crop(x, self.res) if self.preprocess == 'center_random_crop' else x, crop_pos, self.crop_size)
+                l_lpips = olp.calc_loss_lpips(self.lpips['state'], xc, self.lpips['bank_feats'], self.w_lpips, self.lpips['taps'],
+                                              self.lpips['script'])
+            loss = -l_lat - l_pix - l_lpips + l_disc                           # ULA:270
+            self.loss_log.append(tuple(float(torch.as_tensor(v).detach()) for v in (l_lat, l_pix, loss, l_disc, l_lpips)))
             optim.zero_grad()
             loss.backward()
             optim.step()

@@ -1,0 +1,125 @@
+"""GPU parity of the perceptual (LPIPS) term: CUDA path (through the C ABI) against
+  * tests/golden/lpips.pt -- losses, image gradients and tap activations produced by the REFERENCE's own
+    ``BaseNet`` / ``LinLayers`` / ``LPIPS.forward`` / crop pipeline (oracle/make_golden_lpips.py), and
+  * the CPU oracle loop with all four criteria (author's weights, backbone_latentaug.py:46-49).
+Tolerances (relative L2): fp32_parity 1e-3, bf16 1e-2 on loop outputs; the stand-alone gradient in bf16 is compared by
+cosine (bf16 rounding flips near-zero ReLU pre-activations, as for the discriminator term).
+"""
+import random
+
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine_for(res, C, batch, precision):
+    from latentaugment_b200.engine import SynthesisEngine
+    from latentaugment_b200.utils import synthetic
+    cb = 64 * res                      # every resolution gets 64 channels
+    sd = synthetic.random_generator_state(img_resolution=res, img_channels=C, channel_base=cb, channel_max=64)
+    return SynthesisEngine(sd, img_resolution=res, img_channels=C, batch=batch, precision=precision)
+
+
+@pytest.mark.parametrize('case', ['intree3', 'script5'])
+@pytest.mark.parametrize('precision', ['fp32_parity', 'bf16'])
+def test_lpips_loss_and_gradient_match_reference_golden(golden, case, precision):
+    from oracle import lpips as olp
+    g = golden('lpips.pt')[case]
+    st = olp.random_vgg_state(7, g['taps'])
+    n, C, res = g['img'].shape[0], g['img'].shape[1], g['res']
+    eng = _engine_for(res, C, n, precision)
+    eng.set_lpips(st, taps=g['taps'], crop_size=g['crop_size'])
+    eng.set_feature_bank(g['bank_crops'])
+    loss, grad = eng.lpips_loss_grad(g['img'], g['crop_pos'], g['w_lpips'], norm_mode=0 if g['script'] else 1)
+    eng.debug_check()
+    el = abs(float(loss) - g['loss']) / abs(g['loss'])
+    eg = rel_l2(grad.cpu(), g['grad'])
+    cos = float(torch.nn.functional.cosine_similarity(grad.cpu().flatten().double(), g['grad'].flatten().double(), dim=0))
+    print(f'\n[lpips {case} {precision}] loss ours={float(loss):.7f} ref={g["loss"]:.7f} rel={el:.2e}  grad rel_l2={eg:.3e} cos={cos:.6f}')
+    # gradient is confined to the crop window
+    off = (res - int((res * res / 2) ** 0.5) + 1) // 2
+    if precision == 'fp32_parity':
+        assert el < 1e-4 and eg < 1e-3
+        if case == 'intree3':
+            taps = [eng.lpips_tap(k).cpu() for k in range(len(g['taps']))]
+            for k, ref in enumerate(g['feats']):
+                e = rel_l2(taps[k][0].permute(2, 0, 1), ref[0])
+                print(f'   tap {k}: normalised activations rel_l2={e:.3e}')
+                assert e < 1e-4
+    else:
+        assert el < 2e-2 and cos > 0.98
+
+
+def test_lpips_golden_matches_product_random_state():
+    """The product-side seeded VGG parameters equal the oracle's (the goldens were made with the latter)."""
+    from latentaugment_b200.utils import synthetic
+    from oracle import lpips as olp
+    for taps in (olp.TAPS_INTREE, olp.TAPS_SCRIPT):
+        a, b = synthetic.random_vgg_state(7, taps), olp.random_vgg_state(7, taps)
+        assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+
+
+@pytest.mark.parametrize('precision', ['fp32_parity', 'bf16'])
+@pytest.mark.parametrize('script', [True, False])
+def test_augment_loop_with_all_four_terms(precision, script):
+    """latent + pixel + perceptual + discriminator with the author's weights (w_lpips 10, w_pix 0.1, w_latent 0.001,
+    w_disc 0.01) against the oracle loop; 128x128 so the 64x64 window fits the 90x90 centre crop."""
+    from oracle import latent_aug as ola
+    from oracle import lpips as olp
+    from oracle import sg2_disc, synthetic
+    cfg = dict(img_resolution=128, img_channels=2, channel_base=8192, channel_max=64, batch=4, steps=3, bank=32, img_bank=6)
+    wl = synthetic.make_workload(cfg, noise_strength=0.1)
+    G = wl['G']
+    from latentaugment_b200.engine import SynthesisEngine
+    eng = SynthesisEngine(dict(G.state_dict()), img_resolution=128, img_channels=2, batch=4, precision=precision)
+    eng.set_latent_bank(wl['W'])
+    eng.set_image_bank(wl['X'])
+    D = sg2_disc.make_discriminator(img_resolution=128, img_channels=2, channel_base=8192, channel_max=64)
+    eng.set_discriminator(dict(D.state_dict()))
+    taps = olp.TAPS_SCRIPT if script else olp.TAPS_INTREE
+    st = olp.random_vgg_state(7, taps)
+    random.seed(11)
+    from latentaugment_b200.augments.utils.util_latent_aug import feature_bank_crops
+    crops = feature_bank_crops(wl['X'], 128, 64)
+    eng.set_lpips(st, taps=taps, crop_size=64)
+    eng.set_feature_bank(crops)
+    lp = dict(state=st, taps=taps, script=script, bank_feats=olp.bank_features(st, crops, taps))
+    kw = dict(w_latent=0.001, w_pix=0.1, w_disc=0.01)
+    orc = ola.LatentAugOracle(G, wl['W'], wl['X'], num_epochs=3, w_lpips=10.0, D=D, lpips=lp, fused=True, **kw)
+    random.seed(0)
+    _, w_ref = orc.forward(wl['w0'].clone())
+    with torch.no_grad():
+        img_ref = G.synthesis(w_ref, noise_mode='const')
+    random.seed(0)
+    pos = ola.get_crop_params(128, 64)
+    img, w_aug, losses = eng.augment(wl['w0'], num_steps=3, lr=0.01, w_lpips=10.0, lpips_crop=pos, lpips_norm_mode=0 if script else 1,
+                                     final_noise_mode='const', return_losses=True, **kw)
+    eng.debug_check()
+    ew, ei = rel_l2(w_aug.cpu(), w_ref[:, 0]), rel_l2(img.cpu(), img_ref)
+    l0 = losses[0].cpu()
+    print(f'\n[4-term loop script={script} {precision}] rel_w={ew:.3e} rel_img={ei:.3e} loss0 ours: lat {l0[0]:.6f} pix {l0[1]:.6f} disc {l0[3]:.6f} '
+          f'lpips {l0[4]:.6f} total {l0[2]:.6f} | oracle {orc.loss_log[0]}')
+    tol = 1e-3 if precision == 'fp32_parity' else 1e-2
+    assert abs(float(l0[4]) - orc.loss_log[0][4]) <= (1e-3 if precision == 'fp32_parity' else 3e-2) * abs(orc.loss_log[0][4])
+    assert abs(float(l0[2]) - orc.loss_log[0][2]) <= (1e-3 if precision == 'fp32_parity' else 3e-2) * abs(orc.loss_log[0][2])
+    assert ew < tol and ei < tol
+
+
+def test_plugin_runs_with_reference_default_weights():
+    """create_augment(opt) with the reference's DEFAULT criteria weights (w_pix = w_lpips = w_latent = w_disc = 1) no longer raises."""
+    from latentaugment_b200.augments import create_augment
+    from latentaugment_b200.options.aug_options import AugOptions
+    argv = ['--aug', 'latent', '--synthetic', '--batch_size', '4', '--img_resolution', '128', '--synthetic_channels', '2',
+            '--synthetic_channel_base', '8192', '--synthetic_channel_max', '64', '--synthetic_bank', '64', '--synthetic_img_bank', '8',
+            '--synthetic_codes', '16', '--opt_num_epochs', '2', '--no_log', '--precision', 'bf16']
+    opt = AugOptions().parse(args={'p_thres': 0.0, 'init_w': 'inv'}, argv=argv)
+    assert opt.w_lpips == 1.0 and opt.w_disc == 1.0
+    aug = create_augment(opt)
+    names = list(aug.stats_dataset_w.index)[:4]
+    aug.set_input({'A': torch.zeros(4, 1, 128, 128), 'B': torch.zeros(4, 1, 128, 128), 'A_paths': names, 'B_paths': names})
+    aug.forward()
+    out = aug.get_output()
+    assert out['A'].shape == (4, 1, 128, 128) and bool(torch.isfinite(out['A']).all())

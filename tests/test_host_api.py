@@ -53,8 +53,8 @@ def test_criteria_registry():
     opt = _opts(args={'w_lpips': 0.0, 'w_disc': 0.0})
     c = criteria.create_criteria(opt)
     assert sorted(c) == ['latent', 'pix'] and c['latent'].sign == -1.0 and c['pix'].weight == 1.0
-    with pytest.raises(NotImplementedError):
-        criteria.create_criteria(_opts())                      # default w_lpips = w_disc = 1 need unavailable networks
+    full = criteria.create_criteria(_opts())                   # reference defaults: all four weights are 1
+    assert sorted(full) == ['disc', 'latent', 'lpips', 'pix'] and full['lpips'].sign == -1.0 and full['disc'].sign == 1.0
 
 
 def test_no_cpu_fallback():
@@ -160,3 +160,34 @@ def test_shard_range_covers_everything():
         for world in (1, 2, 3, 8):
             r = [shard_range(n, k, world) for k in range(world)]
             assert r[0][0] == 0 and r[-1][1] == n and all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+
+
+def test_feature_bank_crops_follow_reference_draw_order():
+    """One fresh get_params draw (two random.randint calls) per (modality, bank image), modality-major -- the order in
+    which the reference builds fea_{mode} (util_latent_aug.py:160-169,564-579)."""
+    import random
+
+    import torch
+
+    from latentaugment_b200.augments.criteria.pix import center_crop_bounds
+    from latentaugment_b200.augments.utils.util_latent_aug import feature_bank_crops
+    X = torch.arange(3 * 2 * 128 * 128, dtype=torch.float32).reshape(3, 2, 128, 128)
+    random.seed(4)
+    crops = feature_bank_crops(X, 128, 64)
+    random.seed(4)
+    off, size = center_crop_bounds(128)
+    for c in range(2):
+        for m in range(3):
+            x = random.randint(0, size - 64)
+            y = random.randint(0, size - 64)
+            assert torch.equal(crops[m, c], X[m, c, off + y:off + y + 64, off + x:off + x + 64])
+
+
+def test_lpips_flag_selects_taps_and_normaliser():
+    from latentaugment_b200.augments.criteria import REGISTRY, create_criteria
+    from latentaugment_b200.augments.criteria.lpips import taps_and_norm
+    assert taps_and_norm('lpips_script') == ((4, 9, 16, 23, 30), 0)
+    assert taps_and_norm('lpips') == ((16, 23, 30), 1)
+    import types
+    crit = create_criteria(types.SimpleNamespace(w_latent=1.0, w_pix=0.0, w_lpips=1.0, w_disc=0.0))
+    assert set(crit) == {'latent', 'lpips'} and isinstance(crit['lpips'], REGISTRY['lpips'])

@@ -120,3 +120,27 @@ def test_loop_matches_reference(golden, name):
         assert rel_l2(w_aug[:, 0], g['w_aug']) < tol_w, (fused, rel_l2(w_aug[:, 0], g['w_aug']))
         assert rel_l2(img, g['img']) < tol_img, (fused, rel_l2(img, g['img']))
         assert torch.equal(w_aug[:, 0], w_aug[:, -1])
+
+
+def test_lpips_oracle_matches_reference_golden(golden):
+    """oracle/lpips.py against losses / image gradients / tap activations produced by the reference's own
+    BaseNet + LinLayers + LPIPS.forward + crop pipeline (oracle/make_golden_lpips.py)."""
+    from oracle import latent_aug as ola
+    from oracle import lpips as olp
+    G = golden('lpips.pt')
+    for name, g in G.items():
+        st = olp.random_vgg_state(7, g['taps'])
+        img = g['img'].clone().requires_grad_(True)
+        off, size = ola.center_crop_bounds(g['res'])
+        xc = olp.crop(img[:, :, off:off + size, off:off + size], g['crop_pos'], g['crop_size'])
+        bf = olp.bank_features(st, g['bank_crops'], g['taps'])
+        loss = olp.calc_loss_lpips(st, xc, bf, g['w_lpips'], g['taps'], g['script'])
+        (gr,) = torch.autograd.grad(loss, img)
+        assert abs(float(loss) - g['loss']) < 1e-5 * abs(g['loss']), name
+        assert rel_l2(gr, g['grad']) < 5e-4, name
+        assert float(gr[:, :, :off].abs().max()) == 0.0          # nothing outside the centre crop
+        for c in range(img.shape[1]):
+            f = olp.vgg_features(st, xc[:, c:c + 1].repeat(1, 3, 1, 1).detach(), g['taps'])
+            for k, t in enumerate(f):
+                s, a = g['feat_sums'][c][k]
+                assert abs(float(t.sum()) - s) < 1e-3 * a and abs(float(t.abs().sum()) - a) < 1e-4 * a
