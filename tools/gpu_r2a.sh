@@ -9,4 +9,7 @@ tail -3 gpurun_out/r2a_bench_c3.err
 python bench.py --config c5 > gpurun_out/r2a_bench_c5.json 2> gpurun_out/r2a_bench_c5.err
 tail -3 gpurun_out/r2a_bench_c5.err
 cat gpurun_out/r2a_bench_c5.json
+python bench.py --author-weights --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/r2a_bench_c2_author.json 2> gpurun_out/r2a_bench_c2_author.err
+tail -3 gpurun_out/r2a_bench_c2_author.err
+cat gpurun_out/r2a_bench_c2_author.json
 tail -40 gpurun_out/r2a_pytest.log
