@@ -9,11 +9,13 @@ way and enqueues the replicas' loops asynchronously on their own devices -- same
 no per-call replication.  For multi-process runs (one process per GPU, ``torchrun``) each
 rank simply builds its own ``LatentAug`` over its batch shard (bench.py).
 """
+import os
 import random
 
 import torch
 
 from ... import engine as _engine
+from . import util_dataset
 from ...utils import synthetic
 from ..criteria import create_criteria
 from ..criteria.pix import center_crop_bounds
@@ -141,6 +143,14 @@ class LatentAug:
 
         # ---- banks (reference: compute_stats -> register_buffer('W' / 'X'), :140-158)
         gen = torch.Generator().manual_seed(1)
+        if (latent_bank is None and image_bank is None and inverted_codes is None and getattr(opt, 'interim_dir', '')
+                and not getattr(opt, 'latent_bank', '') and not getattr(opt, 'image_bank', '') and not getattr(opt, 'inverted_codes', '')):
+            # the reference's own zips: {interim_dir}/{dataset_aug}/{dataset_w_name|dataset_name_aug}.zip (util_dataset.py)
+            zpath = os.path.join(opt.interim_dir, opt.dataset_aug, opt.dataset_w_name + '.zip')
+            if os.path.isfile(zpath):
+                ds_w, latent_bank, image_bank = util_dataset.banks_from_reference_layout(
+                    opt, phase, self.w_dim, self.num_ws, need_latent=self.w_latent > 0, need_img=self.w_pix > 0 or self.w_lpips > 0)
+                inverted_codes = ds_w.to_table()
         if latent_bank is None and getattr(opt, 'latent_bank', ''):
             latent_bank = torch.load(opt.latent_bank, map_location='cpu', weights_only=True)
         if latent_bank is None and getattr(opt, 'synthetic', False):
