@@ -228,9 +228,11 @@ int la_augment(la_engine* e, const float* d_w0, const la_augment_options* opt, c
 int la_pairwise_sqdist(const float* d_X, int n, const float* d_Y, int m, int K, float* d_D, la_stream stream);
 
 /* k nearest bank rows per query under that distance, ties to the lowest index.  Candidates are
- * selected by a bf16 tensor-core GEMM with a fused per-tile top-k and re-ranked in exact fp32.
- * d_bank_bf16 / d_bank_sqnorm come from la_bank_prepare.  index_offset is added to the returned
- * indices (bank shards).  Outputs: d_dist [n, k] fp32, d_idx [n, k] int64. */
+ * selected by ONE bf16 tensor-core GEMM pass with a fused per-tile top-k and re-ranked exactly (fp64 dot, one
+ * rounding, the reference's association order); the re-rank margin bounds the bf16 error and tiles whose candidate
+ * list may be incomplete are rescanned, so the result equals the exhaustive search for any data.
+ * la_bank_prepare fills d_bank_bf16 [m, K] bf16 and d_bank_sqnorm [m + 1] fp32 (the squared norms followed by their
+ * maximum).  index_offset is added to the returned indices (bank shards).  Outputs: d_dist [n, k] fp32, d_idx [n, k] int64. */
 int la_bank_prepare(const float* d_Y, int m, int K, void* d_bank_bf16, float* d_bank_sqnorm, la_stream stream);
 int la_nearest_codes(const float* d_X, int n, const float* d_Y, const void* d_bank_bf16, const float* d_bank_sqnorm, int m, int K,
                      int k, long long index_offset, void* d_workspace, size_t workspace_bytes, float* d_dist, long long* d_idx,

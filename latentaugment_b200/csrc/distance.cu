@@ -1,7 +1,8 @@
 // Distance-to-bank: exact pairwise squared L2 (reference l2_loss_vectorized, compute_mean=False,
 // augments/utils/util_latent_aug.py:315-361) and the nearest-code / top-k extension
-// (SURVEY.md F3): tensor-core candidate selection (tap-GEMM with the fused top-k epilogue,
-// split-bf16 operands) followed by an exact fp32 re-rank in the reference's association order.
+// (SURVEY.md F3): tensor-core candidate selection (tap-GEMM with the fused top-k epilogue, one
+// bf16 pass) followed by an exact re-rank in the reference's association order whose margins
+// make the result equal to the exhaustive search for any data (rerank_kernel).
 #include <cuda_bf16.h>
 #include <math.h>
 #include <string.h>
@@ -26,7 +27,7 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
-// rows -> bf16 hi / lo planes + |row|^2 (fp64 accumulate, rounded once to fp32).  Warp per row.
+// rows -> bf16 (hi [, lo] planes) + |row|^2 (fp64 accumulate, rounded once to fp32).  Warp per row.
 __global__ void split_rows_kernel(const float* __restrict__ src, int rows, int rows_padded, int K, bf16* hi, bf16* lo, float* sqnorm) {
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -36,7 +37,7 @@ __global__ void split_rows_kernel(const float* __restrict__ src, int rows, int r
         const float v = r < rows ? src[static_cast<long long>(r) * K + k] : 0.f;
         const bf16 h = __float2bfloat16_rn(v);
         hi[static_cast<long long>(r) * K + k] = h;
-        lo[static_cast<long long>(r) * K + k] = __float2bfloat16_rn(v - __bfloat162float(h));
+        if (lo) lo[static_cast<long long>(r) * K + k] = __float2bfloat16_rn(v - __bfloat162float(h));
         acc += static_cast<double>(v) * v;
     }
     acc = warp_sum_d(acc);
@@ -60,36 +61,47 @@ __global__ void pairwise_kernel(const float* __restrict__ X, int n, const float*
     if (lane == 0) D[pair] = (static_cast<float>(yy) + static_cast<float>(xx)) - 2.f * static_cast<float>(yx);
 }
 
-// Exact re-rank, warp per query.  The tap-GEMM left n_blocks * 2 * kCand candidates with approximate
-// scores |y|^2 - 2<x,y> (split-bf16 operands, fp32 accumulate: relative error ~1e-5).  Stage 1: every
-// lane keeps the 8 best of its strided share by approximate score (the union holds the global 8 best);
-// the warp's 8th best plus a 2e-3 relative margin -- two orders of magnitude above the GEMM error --
-// bounds what can still be among the exact k best.  Stage 2: the surviving candidates are recomputed
-// exactly (fp64 dot, one rounding, the reference's association (YY + XX) - 2 YX) and the k smallest
-// (distance, index) pairs are kept, ties to the lowest index.
+// Exact re-rank, warp per query.  The tap-GEMM (ONE bf16 pass) left, per (query, 128-code half tile = "group"), the 8
+// smallest approximate scores s^ = |y|^2 - 2 <bf16(x), bf16(y)> in ascending order.  With eps = 2^-6 |x| max_j|y_j|
+// (>= the error of s^: two bf16 roundings of relative size 2^-9 each on every product, doubled by the factor -2, plus
+// the fp32 accumulation error, Cauchy-Schwarz on sum |x_k y_k|) the exact k best are found as follows:
+//   1. thr = the warp-wide 8th smallest s^ over all candidates.  The k-th smallest EXACT score T satisfies T <= thr + eps
+//      and every exact top-k member has s^ <= T + eps, hence s^ <= cut = thr + 2 eps.
+//   2. A member can be missing from the candidate lists only if 8 others of its group have smaller s^, i.e. only if
+//      that group's 8th kept score is <= cut: such groups ("overflowed") are rescanned exhaustively (their listed
+//      candidates are dropped, the scan covers them); with more than kMaxOvf of them the whole shard is scanned.
+//   3. every surviving candidate (s^ <= cut) and every code of an overflowed group is recomputed exactly -- fp64 dot,
+//      one rounding, the reference's association (YY + XX) - 2 YX -- and the k smallest (distance, index) pairs are
+//      kept, ties to the lowest index.
+// So the result equals the exact search for ANY data, not only in probability; the margins only set the cost.
+constexpr int kMaxOvf = 32;
 __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ X, const float* __restrict__ xx, const float* __restrict__ Y,
-                                                     const float* __restrict__ yy, int n, int K, const float* __restrict__ cand_score,
+                                                     const float* __restrict__ yy, int n, int m, int K, const float* __restrict__ cand_score,
                                                      const int* __restrict__ cand_idx, int ncand, int k, long long index_offset,
                                                      float* out_dist, long long* out_idx) {
     __shared__ int s_list[8][256];
+    __shared__ int s_ovf[8][kMaxOvf];
     const int wib = threadIdx.x >> 5;
     const int i = blockIdx.x * (blockDim.x >> 5) + wib;
     const int lane = threadIdx.x & 31;
     if (i >= n) return;
     const float INF = __int_as_float(0x7f800000);
     float ls[8];
-    int li[8];
+    int li[8], lc[8];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) { ls[t] = INF; li[t] = -1; }
+    for (int t = 0; t < 8; ++t) { ls[t] = INF; li[t] = -1; lc[t] = -1; }
     const float* cs = cand_score + static_cast<long long>(i) * ncand;
     const int* ci = cand_idx + static_cast<long long>(i) * ncand;
     for (int c = lane; c < ncand; c += 32) {
         float sc = cs[c];
-        int id = ci[c];
+        int id = ci[c], pos = c;
         if (id < 0 || !(sc < ls[7])) continue;
 #pragma unroll
         for (int t = 0; t < 8; ++t)
-            if (sc < ls[t]) { const float ts = ls[t]; const int ti = li[t]; ls[t] = sc; li[t] = id; sc = ts; id = ti; }
+            if (sc < ls[t]) {
+                const float ts = ls[t]; const int ti = li[t], tp = lc[t];
+                ls[t] = sc; li[t] = id; lc[t] = pos; sc = ts; id = ti; pos = tp;
+            }
     }
     // the warp's 8th smallest approximate score: pop the minimum of the lane heads 8 times
     int head = 0;
@@ -98,21 +110,39 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ X
         float h = INF;
 #pragma unroll
         for (int t = 0; t < 8; ++t) if (t == head) h = ls[t];
-        float m = h;
+        float mn = h;
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        thr = m;
-        if (m == INF) break;
-        const unsigned who = __ballot_sync(0xffffffffu, h == m);
+        for (int o = 16; o >= 1; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        thr = mn;
+        if (mn == INF) break;
+        const unsigned who = __ballot_sync(0xffffffffu, h == mn);
         if (lane == __ffs(who) - 1) ++head;
     }
     const float xi = xx[i];
-    const float cut = thr == INF ? INF : thr + 2e-3f * (fabsf(thr) + xi + 1e-30f);
-    // compact the survivors into the warp's list
+    const float eps = 0.015625f * sqrtf(xi) * sqrtf(yy[m]) * 1.01f;          // yy[m] = max_j |y_j|^2 (la_bank_prepare)
+    const float cut = thr == INF ? INF : thr + 2.f * eps;
+    // overflowed groups: the 8th (largest) kept score of the group is still within the cut
+    const int ngroups = ncand >> 3;
+    int novf = 0;
+    for (int g0 = 0; g0 < ngroups; g0 += 32) {
+        const int g = g0 + lane;
+        const bool ov = g < ngroups && ci[g * 8 + 7] >= 0 && cs[g * 8 + 7] <= cut;
+        const unsigned bal = __ballot_sync(0xffffffffu, ov);
+        if (ov) {
+            const int slot = novf + __popc(bal & ((1u << lane) - 1));
+            if (slot < kMaxOvf) s_ovf[wib][slot] = g;
+        }
+        novf += __popc(bal);
+    }
+    __syncwarp();
+    const bool scan_all = novf > kMaxOvf || thr == INF;
+    // compact the surviving listed candidates (not those of overflowed groups: the scan covers them)
     int cnt = 0;
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
-        const bool keep = li[t] >= 0 && ls[t] <= cut;
+        bool keep = !scan_all && li[t] >= 0 && ls[t] <= cut;
+        if (keep)
+            for (int o = 0; o < novf; ++o) if (s_ovf[wib][o] == (lc[t] >> 3)) keep = false;
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         if (keep) s_list[wib][cnt + __popc(bal & ((1u << lane) - 1))] = li[t];
         cnt += __popc(bal);
@@ -123,8 +153,7 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ X
 #pragma unroll
     for (int t = 0; t < 8; ++t) { bd[t] = INF; bi[t] = 0x7fffffff; }
     const float* x = X + static_cast<long long>(i) * K;
-    for (int c = 0; c < cnt; ++c) {
-        const int j = s_list[wib][c];
+    auto exact = [&](int j) {
         const float* y = Y + static_cast<long long>(j) * K;
         double dot = 0.0;
         for (int kk = lane; kk < K; kk += 32) dot += static_cast<double>(x[kk]) * y[kk];
@@ -138,12 +167,37 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ X
                 bd[t] = d; bi[t] = id; d = td; id = ti;
             }
         }
+    };
+    if (scan_all) {
+        for (int j = 0; j < m; ++j) exact(j);
+    } else {
+        for (int c = 0; c < cnt; ++c) exact(s_list[wib][c]);
+        for (int o = 0; o < novf; ++o) {
+            const int g = s_ovf[wib][o];
+            const int j0 = (g >> 1) * 256 + (g & 1) * 128;          // group = (256-code tile, 128-column half)
+            for (int j = j0; j < j0 + 128 && j < m; ++j) exact(j);
+        }
     }
     if (lane == 0)
         for (int t = 0; t < k; ++t) {
             out_dist[static_cast<long long>(i) * k + t] = bd[t];
             out_idx[static_cast<long long>(i) * k + t] = bi[t] == 0x7fffffff ? -1 : bi[t] + index_offset;
         }
+}
+
+// max_j |y_j|^2 -> sqnorm[m]   (one block)
+__global__ void max_sqnorm_kernel(float* sqnorm, int m) {
+    float v = 0.f;
+    for (int j = threadIdx.x; j < m; j += blockDim.x) v = fmaxf(v, sqnorm[j]);
+    __shared__ float sm[32];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (blockDim.x >> 5); ++w) v = fmaxf(v, sm[w]);
+        sqnorm[m] = v;
+    }
 }
 
 // merge [shards, n, k] sorted lists -> k best per query (thread per query)
@@ -173,7 +227,7 @@ __global__ void merge_topk_kernel(const float* __restrict__ dist, const long lon
 
 struct NearestLayout {
     int Hq, rows_padded, n_blocks, ncand;
-    size_t off_xhi, off_xlo, off_xx, off_cs, off_ci, off_err, total;
+    size_t off_xhi, off_xx, off_cs, off_ci, off_err, total;
 };
 NearestLayout nearest_layout(int n, int m, int K) {
     NearestLayout L;
@@ -185,7 +239,6 @@ NearestLayout nearest_layout(int n, int m, int K) {
     size_t off = 0;
     auto take = [&](size_t b) { off = (off + 1023) & ~size_t(1023); size_t o = off; off += b; return o; };
     L.off_xhi = take(static_cast<size_t>(L.rows_padded) * K * 2);
-    L.off_xlo = take(static_cast<size_t>(L.rows_padded) * K * 2);
     L.off_xx = take(static_cast<size_t>(L.rows_padded) * 4);
     L.off_cs = take(static_cast<size_t>(n) * L.ncand * 4);
     L.off_ci = take(static_cast<size_t>(n) * L.ncand * 4);
@@ -217,8 +270,9 @@ __attribute__((visibility("default")))
 int la_bank_prepare(const float* d_Y, int m, int K, void* d_bank_bf16, float* d_bank_sqnorm, la_stream stream) {
     if (!d_Y || !d_bank_bf16 || !d_bank_sqnorm || m < 1 || K < 64 || K % 64) return la_fail_msg(-2, "bad arguments (K must be a multiple of 64)");
     bf16* hi = static_cast<bf16*>(d_bank_bf16);
-    bf16* lo = hi + static_cast<size_t>(m) * K;
-    split_rows_kernel<<<(m + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_Y, m, m, K, hi, lo, d_bank_sqnorm);
+    split_rows_kernel<<<(m + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_Y, m, m, K, hi, nullptr, d_bank_sqnorm);
+    DCU(cudaGetLastError());
+    max_sqnorm_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(d_bank_sqnorm, m);
     DCU(cudaGetLastError());
     return 0;
 }
@@ -242,11 +296,10 @@ int la_nearest_codes(const float* d_X, int n, const float* d_Y, const void* d_ba
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     char* ws = static_cast<char*>(d_workspace);
     bf16* xhi = reinterpret_cast<bf16*>(ws + L.off_xhi);
-    bf16* xlo = reinterpret_cast<bf16*>(ws + L.off_xlo);
     float* xx = reinterpret_cast<float*>(ws + L.off_xx);
     float* cs = reinterpret_cast<float*>(ws + L.off_cs);
     int* ci = reinterpret_cast<int*>(ws + L.off_ci);
-    split_rows_kernel<<<(L.rows_padded + 7) / 8, 256, 0, s>>>(d_X, n, L.rows_padded, K, xhi, xlo, xx);
+    split_rows_kernel<<<(L.rows_padded + 7) / 8, 256, 0, s>>>(d_X, n, L.rows_padded, K, xhi, nullptr, xx);
     DCU(cudaGetLastError());
 
     int dev = 0, sms = 0;
@@ -264,17 +317,14 @@ int la_nearest_codes(const float* d_X, int n, const float* d_Y, const void* d_ba
     P.OH = L.Hq; P.OW = 16; P.osy = P.osx = 1;
     P.code_sqnorm = d_bank_sqnorm; P.n_codes = m; P.n_queries = n; P.topk = kCand;
     P.cand_score = cs; P.cand_idx = ci;
-    P.taps[0] = Tap{0, 0, 0, 0};      // x_hi . y_hi
-    P.taps[1] = Tap{0, 0, 0, 1};      // x_lo . y_hi
-    P.taps[2] = Tap{0, 0, 1, 0};      // x_hi . y_lo
-    P.prob[0].tap_begin = 0; P.prob[0].ntaps = 3;
+    P.taps[0] = Tap{0, 0, 0, 0};      // one bf16 pass: bf16(x) . bf16(y); the exact re-rank absorbs its error (rerank_kernel)
+    P.prob[0].tap_begin = 0; P.prob[0].ntaps = 1;
     if (tapgemm_finalize(P)) return la_fail_msg(-5, "tap grouping failed");
     uint64_t adims[4] = {static_cast<uint64_t>(K), 16, static_cast<uint64_t>(L.Hq), 1};
     uint64_t astr[3] = {static_cast<uint64_t>(K) * 2, static_cast<uint64_t>(K) * 32, static_cast<uint64_t>(K) * 32 * L.Hq};
     uint32_t abox[4] = {64, 16, 8, 1};
-    if (encode_tmap_bf16(&P.a_map[0], xhi, 4, adims, astr, abox) || encode_tmap_bf16(&P.a_map[1], xlo, 4, adims, astr, abox))
-        return la_fail_msg(-5, "tensor map encoding failed (queries)");
-    uint64_t bdims[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(m), 2};
+    if (encode_tmap_bf16(&P.a_map[0], xhi, 4, adims, astr, abox)) return la_fail_msg(-5, "tensor map encoding failed (queries)");
+    uint64_t bdims[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(m), 1};
     uint64_t bstr[2] = {static_cast<uint64_t>(K) * 2, static_cast<uint64_t>(K) * 2 * m};
     uint32_t bbox[3] = {64, 256, 1};
     if (encode_tmap_bf16(&P.b_map, d_bank_bf16, 3, bdims, bstr, bbox)) return la_fail_msg(-5, "tensor map encoding failed (bank)");
@@ -282,9 +332,9 @@ int la_nearest_codes(const float* d_X, int n, const float* d_Y, const void* d_ba
     DCU(cudaMemsetAsync(P.err_flag, 0, sizeof(int), s));
     if (getenv("LA_DEBUG_SIMT_DIST")) {
         TapSimtOperands ops{};
-        ops.a_ptrs[0] = xhi; ops.a_ptrs[1] = xlo;
+        ops.a_ptrs[0] = xhi;
         ops.a_sw = K; ops.a_sh = 16LL * K; ops.a_sn = 16LL * K * L.Hq;
-        for (int i = 0; i < 2; ++i) { ops.a_ws[i] = 16; ops.a_hs[i] = L.Hq; }
+        ops.a_ws[0] = 16; ops.a_hs[0] = L.Hq;
         ops.w = d_bank_bf16;
         int r = launch_tapgemm_simt(P, ops, s);
         if (r) return la_fail_msg(r, "launch_tapgemm_simt failed");
@@ -292,7 +342,7 @@ int la_nearest_codes(const float* d_X, int n, const float* d_Y, const void* d_ba
         int r = launch_tapgemm(P, sms, s);
         if (r) return la_fail_msg(r, "launch_tapgemm failed");
     }
-    rerank_kernel<<<(n + 7) / 8, 256, 0, s>>>(d_X, xx, d_Y, d_bank_sqnorm, n, K, cs, ci, L.ncand, k, index_offset, d_dist, d_idx);
+    rerank_kernel<<<(n + 7) / 8, 256, 0, s>>>(d_X, xx, d_Y, d_bank_sqnorm, n, m, K, cs, ci, L.ncand, k, index_offset, d_dist, d_idx);
     DCU(cudaGetLastError());
     return 0;
 }

@@ -366,8 +366,8 @@ class LatentBank:
         self.Y = Y.detach().reshape(m, -1).float().contiguous()
         self.m, self.K = m, self.Y.shape[1]
         self.index_offset = int(index_offset)
-        self.bf16 = torch.empty([2, m, self.K], dtype=torch.bfloat16, device=self.Y.device)
-        self.sqnorm = torch.empty([m], device=self.Y.device)
+        self.bf16 = torch.empty([m, self.K], dtype=torch.bfloat16, device=self.Y.device)
+        self.sqnorm = torch.empty([m + 1], device=self.Y.device)          # |y_j|^2 followed by their maximum
         with torch.cuda.device(self.Y.device):
             _lib.check(self.lib.la_bank_prepare(_ptr(self.Y), m, self.K, _ptr(self.bf16), _ptr(self.sqnorm),
                                                 _stream_ptr(self.Y.device)))

@@ -349,3 +349,38 @@ def test_in_process_two_gpus():
     # what is asserted is that the second device ran at all and produced finite, close results
     assert torch.isfinite(outs[1][0]).all()
     assert rel_l2(outs[1][0], outs[0][0]) < 0.2
+
+
+@pytest.mark.parametrize('kind', ['cluster_in_one_tile', 'all_codes_nearly_equal', 'exact_ties'])
+def test_nearest_codes_exact_on_adversarial_banks(kind):
+    """Banks built to defeat the bf16 candidate pass: more than 8 near-identical codes inside one 128-code group (the
+    group's candidate list overflows -> exhaustive rescan of the group), a bank whose codes differ by less than the bf16
+    rounding (every group overflows -> whole-shard scan), and exact duplicates (ties go to the lowest index)."""
+    from latentaugment_b200.engine import LatentBank
+    from oracle import latent_aug as ola
+    gen = torch.Generator().manual_seed(5)
+    K, m, n = 512, 1500, 24
+    Y = torch.randn([m, K], generator=gen)
+    X = torch.randn([n, K], generator=gen)
+    if kind == 'cluster_in_one_tile':
+        Y[300:340] = X[3] + 1e-3 * torch.randn([40, K], generator=gen)        # 40 codes within bf16 noise of query 3, groups 2 / 3 of tile 1
+        Y[1290:1300] = X[7] + 1e-4 * torch.randn([10, K], generator=gen)
+    elif kind == 'all_codes_nearly_equal':
+        Y = Y[:1].repeat(m, 1) + 1e-3 * torch.randn([m, K], generator=gen)
+    else:
+        Y[500:520] = Y[100]                                                    # 21 identical codes
+        X[0] = Y[100] + 0.01 * torch.randn([K], generator=gen)
+    d_ref, i_ref = ola.nearest_codes(X, Y, k=8)
+    dist, idx = LatentBank(Y.cuda()).nearest(X.cuda(), k=8)
+    same_idx = torch.equal(idx.cpu(), i_ref)
+    # equal distances may legitimately order differently only if the oracle's fp32 einsum and the fp64-dot-rounded-once
+    # distance disagree in the last bit; indices must match wherever the oracle's distances are distinct
+    dr = d_ref
+    distinct = torch.ones_like(dr, dtype=torch.bool)
+    distinct[:, 1:] &= dr[:, 1:] != dr[:, :-1]
+    distinct[:, :-1] &= dr[:, :-1] != dr[:, 1:]
+    print(f'\n[nearest {kind}] indices equal everywhere: {same_idx}; distinct-distance slots: {int(distinct.sum())}/{distinct.numel()}')
+    assert torch.equal(idx.cpu()[distinct], i_ref[distinct])
+    torch.testing.assert_close(dist.cpu(), d_ref, rtol=1e-5, atol=2e-3)
+    if kind == 'exact_ties':
+        assert idx[0, 0].item() == 100 and idx[0, 1].item() == 500             # duplicates: lowest index first
