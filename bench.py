@@ -338,6 +338,7 @@ def main():
     ap.add_argument('--author-weights', action='store_true',
                     help="the author's run configuration (backbone_latentaug.py:46-56): w_lpips 10, w_pix 0.1, w_latent 0.001, w_disc 0.01")
     ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch')
+    ap.add_argument('--micro-batches', type=int, default=1, help='concurrent parts per GPU batch (own stream + graph each)')
     ap.add_argument('--c5-total', action='store_true', help='c5: keep 2^20 codes in total (strong scaling) instead of 2^17 per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-gpu-reference', action='store_true')
@@ -378,7 +379,8 @@ def main():
             '--img_resolution', str(res), '--synthetic_channels', str(C), '--synthetic_bank', str(c['bank']),
             '--synthetic_img_bank', str(c['img_bank']), '--synthetic_codes', str(max(4 * B, 256)), '--precision', args.precision,
             '--opt_num_epochs', str(steps), '--no_log',
-            '--synthetic_channel_base', str(c['channel_base']), '--synthetic_channel_max', str(c['channel_max'])]
+            '--synthetic_channel_base', str(c['channel_base']), '--synthetic_channel_max', str(c['channel_max']),
+            '--micro_batches', str(args.micro_batches)]
     # stdout carries exactly ONE JSON line: everything else (plugin banners, the NCCL version line that
     # the C library writes to fd 1) goes to stderr -- at the file-descriptor level.
     sys.stdout.flush()
@@ -417,14 +419,14 @@ def main():
     clocks = ClockSampler(local_rank)
     barrier()
     mark = clocks.mark()
-    l0 = eng.launch_count
+    l0 = sum(e.launch_count for e in core.engines)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(args.steps):
         core.forward(w_dev[args.warmup + i])
     ev1.record()
     barrier()
-    launches = eng.launch_count - l0
+    launches = sum(e.launch_count for e in core.engines) - l0
     ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
     value = world * B / (ms * 1e-3)
 
@@ -470,8 +472,9 @@ def main():
         rows, rgb_macs = layer_table(res, C, c['channel_base'], c['channel_max'])
         t = eng.debug_time_gemms(reps=10)
         tot_ms = sum(t['forward']) + sum(t['dgrad'])
-        alg = 2.0 * 2.0 * B * sum(r['alg_macs'] for r in rows)          # fwd + dgrad launches of one step
-        exe = 2.0 * 2.0 * B * sum(r['exe_macs'] for r in rows) * (3 if args.precision == 'fp32_parity' else 1)
+        Bm = eng.batch                                                    # (a micro-batch part when --micro-batches > 1)
+        alg = 2.0 * 2.0 * Bm * sum(r['alg_macs'] for r in rows)         # fwd + dgrad launches of one step
+        exe = 2.0 * 2.0 * Bm * sum(r['exe_macs'] for r in rows) * (3 if args.precision == 'fp32_parity' else 1)
         ach = alg / (tot_ms * 1e-3) / 1e12
         fsyn = f_syn(res, C, channel_base=c['channel_base'], channel_max=c['channel_max'])
         traffic, traffic_src = None, None   # DRAM bytes (read + write) of the same launches: one ncu --set full capture of this workload
@@ -492,8 +495,8 @@ def main():
                 'whole_path_peak': peak_sust, 'whole_path_peak_source': f'{src} bf16_tflops_sustained (kernels timed inside the seconds-long step)'}
         if args.layers_out:
             tab = [dict(r, fwd_ms=t['forward'][i], dgrad_ms=t['dgrad'][i], fir_fwd_ms=t['fir_forward'][i], fir_bwd_ms=t['fir_backward'][i],
-                        fwd_alg_tflops=2.0 * B * r['alg_macs'] / (t['forward'][i] * 1e-3) / 1e12,
-                        dgrad_alg_tflops=2.0 * B * r['alg_macs'] / (t['dgrad'][i] * 1e-3) / 1e12) for i, r in enumerate(rows)]
+                        fwd_alg_tflops=2.0 * Bm * r['alg_macs'] / (t['forward'][i] * 1e-3) / 1e12,
+                        dgrad_alg_tflops=2.0 * Bm * r['alg_macs'] / (t['dgrad'][i] * 1e-3) / 1e12) for i, r in enumerate(rows)]
             json.dump({'config': args.config, 'precision': args.precision, 'batch': B, 'layers': tab, 'seed_ms': t['seed']},
                       open(args.layers_out, 'w'), indent=1)
         # ---- the tolerance-matched mode (<= 1e-3) measured in the same run
@@ -537,7 +540,7 @@ def main():
                            'precision': args.precision,
                            'l2': 'working set >> L2: ~2 GB of activations written and re-read per Adam step',
                            'parallelism': (f'batch {c["batch"]} split over {world} rank(s)' if strong else f'batch-sharded x{world}')
-                           + ', no data-path collective'},
+                           + ', no data-path collective' + (f'; {args.micro_batches} concurrent micro-batches per GPU' if args.micro_batches > 1 else '')},
                 'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cb}
         line.update(extra)
     if rank == 0:

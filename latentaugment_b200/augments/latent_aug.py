@@ -67,6 +67,7 @@ class LatentAugment(BaseAugment):
         # ---- additions of this implementation
         parser.add_argument('--precision', type=str, default='fp32_parity', choices=['fp32_parity', 'bf16'],
                             help='tensor-core operand precision (fp32_parity = split-bf16, rel-L2 1e-3; bf16 = 1e-2)')
+        parser.add_argument('--micro_batches', type=int, default=1, help='cut every GPU shard into k concurrently running parts (own stream + graph each)')
         parser.add_argument('--generator_state', type=str, default='', help='torch state_dict file with the reference parameter names')
         parser.add_argument('--discriminator_state', type=str, default='', help='torch state_dict file of the StyleGAN2 discriminator (needed when w_disc > 0)')
         parser.add_argument('--vgg_state', type=str, default='', help='torch state_dict file of VGG16 (torchvision features.* names) + LPIPS lin layers lin.{k}.weight (needed when w_lpips > 0)')

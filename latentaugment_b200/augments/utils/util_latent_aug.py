@@ -102,7 +102,12 @@ class LatentAug:
         self.gpu_ids = list(gpu_ids)
         self.world_size = len(self.gpu_ids)
         self.batch_size = opt.batch_size
-        assert self.batch_size % self.world_size == 0, 'batch_size must divide over gpu_ids_aug'
+        # micro-batches (addition): every GPU's shard is cut into k parts, each with its own engine, stream and captured graph,
+        # all enqueued before any is awaited -- the latency-bound low-resolution launches of one part overlap the
+        # tensor-core-bound launches of another and fill the tails of its persistent kernels.  Per-replica loss normalisers
+        # stay those of the reference (n = batch / world): the term weights handed to a part are scaled by 1 / k.
+        self.micro = max(1, int(getattr(opt, 'micro_batches', 1)))
+        assert self.batch_size % (self.world_size * self.micro) == 0, 'batch_size must divide over gpu_ids_aug x micro_batches'
         self.num_epochs, self.opt_lr = opt.opt_num_epochs, opt.opt_lr
         self.w_pix, self.w_lpips, self.w_latent, self.w_disc = opt.w_pix, opt.w_lpips, opt.w_latent, opt.w_disc
         self.soft_aug, self.alpha = bool(opt.soft_aug), opt.alpha
@@ -134,10 +139,13 @@ class LatentAug:
         self.modalities = list(range(self.img_channels))
         conv_clamp = getattr(opt, 'conv_clamp', 256.0)
         self.engines = []
+        if self.micro > 1 and self.w_disc > 0:
+            raise ValueError('--micro_batches > 1 changes the discriminator\'s minibatch-stddev groups: use 1 with w_disc > 0')
         for gid in self.gpu_ids:
-            self.engines.append(_engine.SynthesisEngine(
-                generator_state, batch=self.batch_size // self.world_size, precision=self.precision,
-                device=f'cuda:{gid}', conv_clamp=conv_clamp, **kw))
+            for _ in range(self.micro):
+                self.engines.append(_engine.SynthesisEngine(
+                    generator_state, batch=self.batch_size // (self.world_size * self.micro), precision=self.precision,
+                    device=f'cuda:{gid}', conv_clamp=conv_clamp, **kw))
         self.num_ws = self.engines[0].num_ws
         self.device = self.engines[0].device
 
@@ -246,8 +254,9 @@ class LatentAug:
         return self.criteria['disc'](x)
 
     def _shards(self, t):
-        n = self.batch_size // self.world_size
-        return [t[i * n:(i + 1) * n] for i in range(self.world_size)]
+        parts = self.world_size * self.micro
+        n = self.batch_size // parts
+        return [t[i * n:(i + 1) * n] for i in range(parts)]
 
     def z_to_w(self, z):
         """:459-464"""
@@ -271,17 +280,19 @@ class LatentAug:
         crop_pos = get_crop_params(self.res, self.crop_size, self.preprocess)['crop_pos']      # :216 (one window per call, feeds lpips)
         lpips_norm = self.criteria['lpips'].norm_mode if self.w_lpips > 0 else 0
         imgs, ws_out, self.last_losses = [], [], []
+        k = 1.0 / self.micro            # a part's means run over batch / (world * micro) samples: rescale to the replica's normaliser
         for e, wsh in zip(self.engines, self._shards(w)):
-            out = e.augment(wsh, num_steps=self.num_epochs, lr=self.opt_lr, w_latent=self.w_latent, w_pix=self.w_pix,
-                            w_disc=self.w_disc, w_lpips=self.w_lpips, lpips_crop=crop_pos, lpips_norm_mode=lpips_norm,
+            out = e.augment(wsh, num_steps=self.num_epochs, lr=self.opt_lr, w_latent=self.w_latent * k, w_pix=self.w_pix * k,
+                            w_disc=self.w_disc, w_lpips=self.w_lpips * (k if lpips_norm == 0 else 1.0), lpips_crop=crop_pos,
+                            lpips_norm_mode=lpips_norm,
                             soft_aug=self.soft_aug, alpha=self.alpha, final_noise_mode='random',
                             return_losses=self.verbose_flag)
             imgs.append(out[0])
             ws_out.append(out[1])
             if self.verbose_flag:
                 self.last_losses.append(out[2])
-        img = torch.cat([i.to(self.device, non_blocking=True) for i in imgs]) if self.world_size > 1 else imgs[0]
-        w_aug = torch.cat([x.to(self.device, non_blocking=True) for x in ws_out]) if self.world_size > 1 else ws_out[0]
+        img = torch.cat([i.to(self.device, non_blocking=True) for i in imgs]) if len(imgs) > 1 else imgs[0]
+        w_aug = torch.cat([x.to(self.device, non_blocking=True) for x in ws_out]) if len(ws_out) > 1 else ws_out[0]
         if self.verbose_flag:
             self._log_first_call()
         return img, self.broadcasting(w_aug.unsqueeze(1))
@@ -291,7 +302,7 @@ class LatentAug:
         ``losses.jsonl`` in save_dir, then ``verbose_flag = False``); the matplotlib plots are not reproduced."""
         import json
         import os
-        rows = torch.stack([ll.cpu() for ll in self.last_losses]).mean(0).tolist()       # replicas averaged
+        rows = (torch.stack([ll.cpu() for ll in self.last_losses]).sum(0) / self.world_size).tolist()   # parts summed, replicas averaged
         for t, row in enumerate(rows):
             self.stats_loss[f'epoch_{t}'] = {'loss_latent': row[0], 'loss_pix': row[1], 'loss_lpips': row[4], 'loss_disc': row[3], 'loss': row[2]}
             print(f'epoch {t + 1:>4d}/{self.num_epochs}, ' + ' '.join(f'{k} {v:<4.2f}' for k, v in self.stats_loss[f'epoch_{t}'].items()))

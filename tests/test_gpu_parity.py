@@ -384,3 +384,44 @@ def test_nearest_codes_exact_on_adversarial_banks(kind):
     torch.testing.assert_close(dist.cpu(), d_ref, rtol=1e-5, atol=2e-3)
     if kind == 'exact_ties':
         assert idx[0, 0].item() == 100 and idx[0, 1].item() == 500             # duplicates: lowest index first
+
+
+def test_micro_batches_and_lookahead_loop_match_plain_calls():
+    """--micro_batches 2 (two concurrent half-batch engines, term weights rescaled to the replica's normaliser) and the
+    look-ahead caller loop iterate() give the same images as the plain set_input / forward / get_output sequence."""
+    import random as pyrandom
+
+    from latentaugment_b200.augments import create_augment
+    from latentaugment_b200.options.aug_options import AugOptions
+    argv = ['--aug', 'latent', '--synthetic', '--batch_size', '4', '--img_resolution', '64', '--synthetic_channels', '2',
+            '--synthetic_channel_base', '8192', '--synthetic_channel_max', '128', '--synthetic_bank', '64', '--synthetic_img_bank', '8',
+            '--synthetic_codes', '16', '--opt_num_epochs', '3', '--no_log']
+    args = {'p_thres': 0.0, 'w_lpips': 0.0, 'w_disc': 0.0, 'init_w': 'inv'}
+    plain = create_augment(AugOptions().parse(args=dict(args), argv=argv))
+    micro = create_augment(AugOptions().parse(args=dict(args), argv=argv + ['--micro_batches', '2']))
+    names = list(plain.stats_dataset_w.index)
+    batches = [{'A': torch.zeros(4, 1, 64, 64), 'B': torch.zeros(4, 1, 64, 64), 'A_paths': names[4 * i:4 * i + 4], 'B_paths': names[4 * i:4 * i + 4]}
+               for i in range(3)]
+    ref = []
+    for data in batches:
+        plain.set_input(data)
+        pyrandom.seed(1)
+        plain.forward()
+        ref.append(plain.get_output()['A'].clone())
+    # micro-batches
+    for data, r in zip(batches, ref):
+        micro.set_input(data)
+        pyrandom.seed(1)
+        micro.forward()
+        e = rel_l2(micro.get_output()['A'], r)
+        print(f'\n[micro-batches] rel_img={e:.3e}')
+        assert e < 1e-3
+    # look-ahead loop: same values, outputs stay valid until the next-but-one batch
+    pyrandom.seed(1)
+    got = []
+    for data, out in plain.iterate(iter(batches)):
+        got.append((data['A_paths'], out['A'].clone(), out['A_paths']))
+    assert len(got) == 3
+    for (paths, img, out_paths), data, r in zip(got, batches, ref):
+        assert paths == data['A_paths'] == out_paths
+        assert rel_l2(img, r) < 1e-5
