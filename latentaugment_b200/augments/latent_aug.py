@@ -125,7 +125,13 @@ class LatentAugment(BaseAugment):
         self.real_A = data['A']
         self.real_B = data['B']
         self.fname = data['A_paths']
-        self.real_AB = torch.cat((self.real_A, self.real_B), dim=1)
+        self._real_AB = None           # (the reference concatenates here, :176; only the pass-through branch reads it -> built on demand)
+
+    @property
+    def real_AB(self):
+        if self._real_AB is None:
+            self._real_AB = torch.cat((self.real_A, self.real_B), dim=1)
+        return self._real_AB
 
     # ---- output path (reference get_output :182-203 does ``.detach().cpu()``)
     # forward() enqueues the device->host copy of the augmented batch right behind the final synthesis, on a copy
