@@ -98,7 +98,7 @@ typedef struct la_augment_options {
     int n_modalities;              /* number of leading image channels the pixel criterion covers */
     float w_disc;                  /* weight of the discriminator realism term; > 0 needs la_set_discriminator */
     float w_lpips;                 /* weight of the perceptual term; > 0 needs la_set_lpips + la_set_feature_bank */
-    int lpips_crop_x, lpips_crop_y;/* crop window of this call inside the centre crop (util_dataset.py:284-296: drawn once per forward) */
+    int lpips_crop_x, lpips_crop_y;/* origin of this call's crop window, absolute image coordinates (util_dataset.py:284-296: one draw per forward) */
     int lpips_norm_mode;           /* 0: lpips_script form (pair mean), 1: forward_tr form (pair sum / bank size) */
 } la_augment_options;
 
@@ -166,7 +166,8 @@ int la_disc_loss_grad(la_engine* e, const float* d_img, float w_disc, float* d_l
  * la_set_feature_bank takes the real crops [M, img_channels, crop, crop] fp32 in [-1, 1] (the reference builds its feature
  * bank from one random window per real image, util_latent_aug.py:564-579) and keeps only the bank moments;
  * la_lpips_loss_grad is the stand-alone form of what la_augment does every step when w_lpips > 0:
- * crop window at (crop_x, crop_y) inside the centre crop, loss [1] = w_lpips * mean over modalities of the normalised pair
+ * crop window with origin (crop_x, crop_y) in absolute image coordinates (the reference draws the position inside the
+ * centre crop, util_dataset.py:284-309: add the centre-crop offset), loss [1] = w_lpips * mean over modalities of the normalised pair
  * distance (norm_mode 0: / (n * m), 1: / m), grad [batch, C, res, res] = d loss / d img. */
 int la_lpips_workspace_bytes(const la_vgg_desc* v, int batch, int img_channels, int precision, size_t* bytes);
 int la_set_lpips(la_engine* e, const la_vgg_desc* v, void* d_workspace, size_t workspace_bytes, la_stream stream);

@@ -284,7 +284,7 @@ class LatentAug:
         for e, wsh in zip(self.engines, self._shards(w)):
             out = e.augment(wsh, num_steps=self.num_epochs, lr=self.opt_lr, w_latent=self.w_latent * k, w_pix=self.w_pix * k,
                             w_disc=self.w_disc, w_lpips=self.w_lpips * (k if lpips_norm == 0 else 1.0), lpips_crop=crop_pos,
-                            lpips_norm_mode=lpips_norm,
+                            lpips_norm_mode=lpips_norm, lpips_centre=self.preprocess == 'center_random_crop',
                             soft_aug=self.soft_aug, alpha=self.alpha, final_noise_mode='random',
                             return_losses=self.verbose_flag)
             imgs.append(out[0])

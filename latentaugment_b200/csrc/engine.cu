@@ -788,8 +788,8 @@ LA_API int la_augment(la_engine* e, const float* d_w0, const la_augment_options*
     CU(cudaMemsetAsync(e->v, 0, wbytes, w));
     CU(cudaMemsetAsync(e->step, 0, sizeof(int), w));
     CU(cudaMemsetAsync(e->loss_log, 0, sizeof(float) * LA_LOSS_COLS * LA_MAX_STEPS, w));
-    if (opt->w_lpips > 0.f) {        // crop window inside the centre crop (util_dataset.py:304-309,325-332): absolute origin
-        if (lpips_set_call(e->lp, e->crop_off + opt->lpips_crop_x, e->crop_off + opt->lpips_crop_y, opt->w_lpips, opt->lpips_norm_mode, w))
+    if (opt->w_lpips > 0.f) {        // crop window of this call (util_dataset.py:284-309,325-332), absolute image coordinates
+        if (lpips_set_call(e->lp, opt->lpips_crop_x, opt->lpips_crop_y, opt->w_lpips, opt->lpips_norm_mode, w))
             return fail(-7, "lpips: %s", lpips_last_error());
     }
     if ((e->cur_w_pix != opt->w_pix || e->cur_w_disc != opt->w_disc || (e->cur_w_lpips > 0.f) != (opt->w_lpips > 0.f)) &&
@@ -912,7 +912,7 @@ LA_API int la_lpips_loss_grad(la_engine* e, const float* d_img, int crop_x, int 
     LA(bridge_in(e, s));
     LA(nchw_to_f4(d_img, e->batch, e->g.img_channels, e->g.img_resolution, top.img, e->work));
     // (the term enters the objective with a minus sign; the stand-alone call returns d loss / d img, hence -w)
-    if (lpips_set_call(e->lp, e->crop_off + crop_x, e->crop_off + crop_y, -w_lpips, norm_mode, e->work) ||
+    if (lpips_set_call(e->lp, crop_x, crop_y, -w_lpips, norm_mode, e->work) ||
         lpips_forward(e->lp, top.img, e->work, &e->launches) || lpips_backward(e->lp, top.g_img, 0, e->lpips_loss, e->work, &e->launches))
         return fail(-7, "lpips: %s", lpips_last_error());
     LA(f4_to_nchw(top.g_img, e->batch, e->g.img_channels, e->g.img_resolution, d_grad, e->work));

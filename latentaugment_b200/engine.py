@@ -245,10 +245,20 @@ class SynthesisEngine:
             _lib.check(self.lib.la_set_feature_bank(self.handle, _ptr(crops), crops.shape[0], _stream_ptr(self.device)))
         torch.cuda.current_stream(self.device).synchronize()
 
-    def lpips_loss_grad(self, img, crop_pos, w_lpips=1.0, norm_mode=0):
+    def _crop_origin(self, crop_pos, centre):
+        """Absolute window origin: ``crop_pos`` is drawn inside the centre crop when ``preprocess == 'center_random_crop'``
+        (util_dataset.py:284-309)."""
+        off = 0
+        if centre:
+            size = int(math.sqrt(self.img_resolution * self.img_resolution / 2))
+            off = int(round((self.img_resolution - size) / 2.0))
+        return int(crop_pos[0]) + off, int(crop_pos[1]) + off
+
+    def lpips_loss_grad(self, img, crop_pos, w_lpips=1.0, norm_mode=0, centre=True):
         """(loss, d loss / d img) of the perceptual term alone -- reference calc_loss_lpips_* + autograd.  ``crop_pos`` =
-        ``(x, y)`` inside the centre crop (util_dataset.get_params)."""
+        ``(x, y)`` from util_dataset.get_params (inside the centre crop when ``centre``)."""
         img = img.detach().to(self.device, torch.float32).contiguous()
+        crop_pos = self._crop_origin(crop_pos, centre)
         loss = torch.empty([1], device=self.device)
         grad = torch.empty_like(img)
         with torch.cuda.device(self.device):
@@ -304,12 +314,14 @@ class SynthesisEngine:
         return img
 
     def augment(self, w0, *, num_steps=10, lr=0.01, w_latent=1.0, w_pix=1.0, w_disc=0.0, w_lpips=0.0, lpips_crop=(0, 0),
-                lpips_norm_mode=0, soft_aug=False, alpha=1.0, final_noise_mode='random', final_noise=None, return_losses=False):
+                lpips_norm_mode=0, lpips_centre=True, soft_aug=False, alpha=1.0, final_noise_mode='random', final_noise=None,
+                return_losses=False):
         """The hot path (reference LatentAug.forward).  w0 [batch, w_dim] or [batch, 1, w_dim]."""
         w0 = w0.detach().to(self.device, torch.float32).reshape(self.batch, self.w_dim).contiguous()
         nz = self._noise(final_noise_mode, final_noise)
         img = torch.empty([self.batch, self.img_channels, self.img_resolution, self.img_resolution], device=self.device)
         w_aug = torch.empty([self.batch, self.w_dim], device=self.device)
+        lpips_crop = self._crop_origin(lpips_crop, lpips_centre) if w_lpips > 0 else (0, 0)
         nlog = min(max(num_steps, 1), _lib.LA_MAX_STEPS)
         losses = torch.zeros([nlog, _lib.LA_LOSS_COLS], device=self.device) if return_losses else None
         opt = _lib.AugmentOptions(num_steps, lr, w_latent, w_pix, int(bool(soft_aug)), alpha, _lib.NOISE[final_noise_mode],
