@@ -256,6 +256,10 @@ int la_debug_check(la_engine* e, la_stream stream);
  * FIR pass backward[0..L) (0 where the layer has none), backward seed.  Synchronous. */
 int la_debug_time_gemms(la_engine* e, int reps, float* h_ms, int* n_layers);   /* synchronises; non-zero if a pipeline wait timed out */
 long long la_debug_launch_count(const la_engine* e);
+/* Copies an internal quantity of the LAST optimisation step to d_out (fp32; null = only report *count): what = 0 style
+ * gradients (layer-blocked [batch * soff_l + n * cin_l + i], conv layers then toRGB layers), 1 styles (same layout),
+ * 2 demodulation coefficients, 3 d loss / d w of the synthesis path [batch, w_dim], 4 the per-layer block offsets. */
+int la_debug_get(la_engine* e, int what, float* d_out, size_t* count, la_stream stream);
 
 #ifdef __cplusplus
 }

@@ -101,6 +101,7 @@ SIGNATURES = {
                                         C.c_void_p]),
     'la_debug_set_simt': (C.c_int, [C.c_void_p, C.c_int]),
     'la_debug_launch_count': (C.c_longlong, [C.c_void_p]),
+    'la_debug_get': (C.c_int, [C.c_void_p, C.c_int, fptr, C.POINTER(C.c_size_t), C.c_void_p]),
     'la_debug_check': (C.c_int, [C.c_void_p, C.c_void_p]),
     'la_debug_time_gemms': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
 }

@@ -1005,6 +1005,38 @@ LA_API int la_debug_time_gemms(la_engine* e, int reps, float* h_ms, int* n_layer
     return 0;
 }
 
+// Test hook: copies an internal per-step quantity of the LAST optimisation step to d_out (fp32) and reports its element count
+// (d_out may be null).  what = 0: style gradients g_s [layer-blocked: batch * soff_l + n * cin_l + i, conv layers then toRGB
+// layers]; 1: styles s (same layout); 2: demodulation coefficients d [batch * doff_l + n * cout_l + o]; 3: d loss / d w of the
+// synthesis path [batch, w_dim] (sum of the per-chunk partials); 4: per-layer block offsets as floats [nconv + nrgb] (soff).
+LA_API int la_debug_get(la_engine* e, int what, float* d_out, size_t* count, la_stream stream) {
+    if (!e || !count) return fail(-2, "bad arguments");
+    const size_t B = e->batch;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (what == 4) {
+        std::vector<float> off;
+        for (const Conv& c : e->conv) off.push_back(static_cast<float>(c.soff));
+        for (const Rgb& r : e->rgb) off.push_back(static_cast<float>(r.soff));
+        *count = off.size();
+        if (d_out) { CU(cudaMemcpyAsync(d_out, off.data(), sizeof(float) * off.size(), cudaMemcpyHostToDevice, s)); CU(cudaStreamSynchronize(s)); }
+        return 0;
+    }
+    const float* src = what == 0 ? e->g_s : (what == 1 ? e->s_cat : (what == 2 ? e->d_cat : nullptr));
+    const size_t n = what == 2 ? B * e->D : (what == 3 ? B * e->g.w_dim : B * e->S);
+    if (what < 0 || what > 3) return fail(-2, "unknown quantity %d", what);
+    *count = n;
+    if (!d_out) return 0;
+    LA(bridge_in(e, s));
+    if (what == 3) {
+        CU(cudaMemsetAsync(d_out, 0, sizeof(float) * n, e->work));
+        for (int c = 0; c < e->nchunks; ++c) LA(prep_axpy(e->partial + static_cast<size_t>(c) * n, 1.f, d_out, static_cast<long long>(n), e->work));
+    } else {
+        CU(cudaMemcpyAsync(d_out, src, sizeof(float) * n, cudaMemcpyDeviceToDevice, e->work));
+    }
+    LA(bridge_out(e, s));
+    return 0;
+}
+
 LA_API int la_debug_check(la_engine* e, la_stream stream) { return e ? check_err_flag(e, static_cast<cudaStream_t>(stream)) : -2; }
 
 }  // extern "C"

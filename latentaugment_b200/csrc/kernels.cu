@@ -1017,6 +1017,14 @@ int prep_affine(const float* aw, const float* ab, int cin, int w_dim, float wsca
     prep_affine_kernel<<<cdiv(static_cast<long long>(cin) * w_dim, 256), 256, 0, s>>>(aw, ab, cin, w_dim, wscale, bscale, a_rows, b_rows);
     return last_err();
 }
+__global__ void prep_axpy_kernel(const float* __restrict__ x, float a, float* y, long long n) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i < n) y[i] = fmaf(a, x[i], y[i]);
+}
+int prep_axpy(const float* x, float a, float* y, long long n, cudaStream_t s) {
+    prep_axpy_kernel<<<cdiv(n, 256), 256, 0, s>>>(x, a, y, n);
+    return last_err();
+}
 int prep_scale(const float* src, float scale, float* dst, long long n, cudaStream_t s) {
     prep_scale_kernel<<<cdiv(n, 256), 256, 0, s>>>(src, scale, dst, n);
     return last_err();

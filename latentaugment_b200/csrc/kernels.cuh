@@ -38,6 +38,7 @@ int prep_conv_weights(const float* w, int cout, int cin, int up, const float* fi
 int prep_affine(const float* aw, const float* ab, int cin, int w_dim, float wscale, float bscale, float* a_cat_rows,
                 float* b_cat_rows, cudaStream_t s);
 int prep_scale(const float* src, float scale, float* dst, long long n, cudaStream_t s);
+int prep_axpy(const float* x, float a, float* y, long long n, cudaStream_t s);      // y += a x
 int prep_const(const float* cst /*[C,4,4]*/, int C, int hw, float* c_f32 /*[hw][C]*/, void* hi, void* lo, cudaStream_t s);
 
 // ---- x2 up-sampling conv, split form: transposed-conv GEMM -> T [(2H+1) x (2W+1)] -> 4x4 FIR (pad 1, gain 4)

@@ -341,6 +341,16 @@ class SynthesisEngine:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.la_debug_check(self.handle, _stream_ptr(self.device)))
 
+    def debug_get(self, what):
+        """Internal quantity of the last optimisation step (``la_debug_get``): 'g_s' | 's' | 'd' | 'grad_w' | 'soff'."""
+        code = {'g_s': 0, 's': 1, 'd': 2, 'grad_w': 3, 'soff': 4}[what]
+        n = C.c_size_t(0)
+        _lib.check(self.lib.la_debug_get(self.handle, code, C.c_void_p(0), C.byref(n), _stream_ptr(self.device)))
+        out = torch.empty([n.value], device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.la_debug_get(self.handle, code, _ptr(out), C.byref(n), _stream_ptr(self.device)))
+        return out
+
     def debug_time_gemms(self, reps=5):
         """Per-launch device time (ms) of every tap-GEMM of one optimisation step, timed alone."""
         n = len(self.conv_res)

@@ -59,6 +59,9 @@ def init_cuda_plugins(ref):
     """JIT-builds the reference's CUDA plugins the SG2 path uses (bias_act, upfirdn2d).  If a build fails (the sources
     target torch 1.9) the ops are switched to their own ``ref`` implementations -- still the reference's torch path,
     cuDNN convolutions included.  Returns a description string."""
+    import glob
+
+    import torch.utils.cpp_extension as ce
     ref.custom_ops.verbosity = 'none'
     status = []
     for mod in (ref.bias_act, ref.upfirdn2d):
@@ -66,9 +69,27 @@ def init_cuda_plugins(ref):
         try:
             mod._init()
             status.append(f'{name}: jit cuda plugin')
+            continue
+        except ModuleNotFoundError:
+            # custom_ops.get_plugin builds with torch.utils.cpp_extension.load(...) and then importlib.import_module()s
+            # the plugin by NAME (custom_ops.py:136-139); torch >= 2 no longer leaves the build directory on sys.path, so
+            # the import of the freshly built .so fails.  Put the directory it was built in on sys.path and ask again
+            # (the second call finds the cached build).  The reference files themselves stay untouched.
+            plug = f'{name}_plugin'
+            hits = glob.glob(os.path.join(ce._get_build_directory(plug, verbose=False), '*', plug + '*.so'))
+            try:
+                if not hits:
+                    raise
+                sys.path.insert(0, os.path.dirname(sorted(hits, key=os.path.getmtime)[-1]))
+                mod._init()
+                status.append(f'{name}: jit cuda plugin')
+                continue
+            except Exception as exc:   # noqa: BLE001
+                err = exc
         except Exception as exc:       # noqa: BLE001  (any build / load failure)
-            mod._init = lambda: False
-            status.append(f'{name}: ref ops (plugin build failed: {type(exc).__name__})')
+            err = exc
+        mod._init = lambda: False
+        status.append(f'{name}: ref ops (plugin build failed: {type(err).__name__})')
     return '; '.join(status)
 
 
