@@ -425,3 +425,29 @@ def test_micro_batches_and_lookahead_loop_match_plain_calls():
     for (paths, img, out_paths), data, r in zip(got, batches, ref):
         assert paths == data['A_paths'] == out_paths
         assert rel_l2(img, r) < 1e-5
+
+
+@pytest.mark.parametrize('precision', ['fp32_parity', 'bf16'])
+def test_bn128_layers_match_oracle(precision):
+    """128-channel layers on a grid with more than 74 M tiles select the BN = 128 kernels (two M tiles per unit sharing each
+    weight tile; CTA-pair four-tile work items in the forward conv) -- the variant the 256x256 layers of config C2 run.
+    64x64 with batch 4 reaches it at a size the oracle finishes in seconds."""
+    from oracle import latent_aug as ola
+    from oracle import synthetic
+    cfg = dict(img_resolution=64, img_channels=3, channel_base=8192, channel_max=128, batch=4, steps=3, bank=32, img_bank=4)
+    wl = synthetic.make_workload(cfg, noise_strength=0.1)
+    G = wl['G']
+    eng = _engine(wl, precision)
+    eng.set_latent_bank(wl['W'])
+    eng.set_image_bank(wl['X'])
+    orc = ola.LatentAugOracle(G, wl['W'], wl['X'], num_epochs=3, fused=True)
+    random.seed(0)
+    _, w_ref = orc.forward(wl['w0'].clone())
+    with torch.no_grad():
+        img_ref = G.synthesis(w_ref, noise_mode='const')
+    img, w_aug = eng.augment(wl['w0'], num_steps=3, final_noise_mode='const')
+    eng.debug_check()
+    d = (w_aug.cpu() - w_ref[:, 0]).abs()
+    ew, ei = rel_l2(w_aug.cpu(), w_ref[:, 0]), rel_l2(img.cpu(), img_ref)
+    print(f'\n[BN=128 layers {precision}] rel_w={ew:.3e} rel_img={ei:.3e} components off by > lr: {int((d > 0.01).sum())}/{d.numel()}')
+    assert ew < TOL[precision] and ei < TOL[precision]
