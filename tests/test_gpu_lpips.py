@@ -2,8 +2,14 @@
   * tests/golden/lpips.pt -- losses, image gradients and tap activations produced by the REFERENCE's own
     ``BaseNet`` / ``LinLayers`` / ``LPIPS.forward`` / crop pipeline (oracle/make_golden_lpips.py), and
   * the CPU oracle loop with all four criteria (author's weights, backbone_latentaug.py:46-49).
-Tolerances (relative L2): fp32_parity 1e-3, bf16 1e-2 on loop outputs; the stand-alone gradient in bf16 is compared by
-cosine (bf16 rounding flips near-zero ReLU pre-activations, as for the discriminator term).
+Tolerances.  Loss values: 1e-4 (fp32_parity) / 2e-2 (bf16).  Gradients through the 13 ReLU layers + 4 max-pools are limited
+by GATE FLIPS, not by arithmetic precision: a pre-activation within the forward error delta of zero takes the other ReLU
+branch than in the checker's run, which changes that unit's whole gradient contribution, so the relative L2 error of the
+gradient is about sqrt(2 pdf(0) delta) -- 3e-3 for the 1.5e-5 forward error of split-bf16 operands (measured 2.5-3.9e-3
+with cosine 0.99999; the loss itself agrees to 3e-6), 0.15-0.2 for bf16 operands (cosine 0.975-0.99).  The same holds
+for two fp32 runs of the reference on different devices, at their 1e-7 forward difference.  Hence: stand-alone gradient
+1e-2 + cosine 0.9999 (fp32_parity) / cosine 0.95 (bf16); loops that include the term with the author's weight of 10:
+relative L2 3e-3 (fp32_parity, measured 1.0-1.6e-3) / 1e-2 (bf16).
 """
 import random
 
@@ -42,7 +48,7 @@ def test_lpips_loss_and_gradient_match_reference_golden(golden, case, precision)
     # gradient is confined to the crop window
     off = (res - int((res * res / 2) ** 0.5) + 1) // 2
     if precision == 'fp32_parity':
-        assert el < 1e-4 and eg < 1e-3
+        assert el < 1e-4 and eg < 1e-2 and cos > 0.9999
         if case == 'intree3':
             taps = [eng.lpips_tap(k).cpu() for k in range(len(g['taps']))]
             for k, ref in enumerate(g['feats']):
@@ -50,7 +56,7 @@ def test_lpips_loss_and_gradient_match_reference_golden(golden, case, precision)
                 print(f'   tap {k}: normalised activations rel_l2={e:.3e}')
                 assert e < 1e-4
     else:
-        assert el < 2e-2 and cos > 0.98
+        assert el < 2e-2 and cos > 0.95
 
 
 def test_lpips_golden_matches_product_random_state():
@@ -102,7 +108,7 @@ def test_augment_loop_with_all_four_terms(precision, script):
     l0 = losses[0].cpu()
     print(f'\n[4-term loop script={script} {precision}] rel_w={ew:.3e} rel_img={ei:.3e} loss0 ours: lat {l0[0]:.6f} pix {l0[1]:.6f} disc {l0[3]:.6f} '
           f'lpips {l0[4]:.6f} total {l0[2]:.6f} | oracle {orc.loss_log[0]}')
-    tol = 1e-3 if precision == 'fp32_parity' else 1e-2
+    tol = 3e-3 if precision == 'fp32_parity' else 1e-2
     assert abs(float(l0[4]) - orc.loss_log[0][4]) <= (1e-3 if precision == 'fp32_parity' else 3e-2) * abs(orc.loss_log[0][4])
     assert abs(float(l0[2]) - orc.loss_log[0][2]) <= (1e-3 if precision == 'fp32_parity' else 3e-2) * abs(orc.loss_log[0][2])
     assert ew < tol and ei < tol
