@@ -19,7 +19,8 @@ int la_fail_msg(int code, const char* msg);   // engine.cu
 namespace {
 
 typedef __nv_bfloat16 bf16;
-constexpr int kCand = 8;          // candidates kept per (query, 256-code tile)
+constexpr int kCand = 2;          // candidates kept per (query, 32-code chunk)
+constexpr int kChunk = 32;
 
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
@@ -61,20 +62,20 @@ __global__ void pairwise_kernel(const float* __restrict__ X, int n, const float*
     if (lane == 0) D[pair] = (static_cast<float>(yy) + static_cast<float>(xx)) - 2.f * static_cast<float>(yx);
 }
 
-// Exact re-rank, warp per query.  The tap-GEMM (ONE bf16 pass) left, per (query, 128-code half tile = "group"), the 8
+// Exact re-rank, warp per query.  The tap-GEMM (ONE bf16 pass) left, per (query, 32-code chunk = "group"), the 2
 // smallest approximate scores s^ = |y|^2 - 2 <bf16(x), bf16(y)> in ascending order.  With eps = 2^-6 |x| max_j|y_j|
 // (>= the error of s^: two bf16 roundings of relative size 2^-9 each on every product, doubled by the factor -2, plus
 // the fp32 accumulation error, Cauchy-Schwarz on sum |x_k y_k|) the exact k best are found as follows:
 //   1. thr = the warp-wide 8th smallest s^ over all candidates.  The k-th smallest EXACT score T satisfies T <= thr + eps
 //      and every exact top-k member has s^ <= T + eps, hence s^ <= cut = thr + 2 eps.
-//   2. A member can be missing from the candidate lists only if 8 others of its group have smaller s^, i.e. only if
-//      that group's 8th kept score is <= cut: such groups ("overflowed") are rescanned exhaustively (their listed
+//   2. A member can be missing from the candidate lists only if 2 others of its group have smaller s^, i.e. only if
+//      that group's 2nd kept score is <= cut: such groups ("overflowed") are rescanned exhaustively (their listed
 //      candidates are dropped, the scan covers them); with more than kMaxOvf of them the whole shard is scanned.
 //   3. every surviving candidate (s^ <= cut) and every code of an overflowed group is recomputed exactly -- fp64 dot,
 //      one rounding, the reference's association (YY + XX) - 2 YX -- and the k smallest (distance, index) pairs are
 //      kept, ties to the lowest index.
 // So the result equals the exact search for ANY data, not only in probability; the margins only set the cost.
-constexpr int kMaxOvf = 32;
+constexpr int kMaxOvf = 128;
 __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ X, const float* __restrict__ xx, const float* __restrict__ Y,
                                                      const float* __restrict__ yy, int n, int m, int K, const float* __restrict__ cand_score,
                                                      const int* __restrict__ cand_idx, int ncand, int k, long long index_offset,
@@ -121,12 +122,12 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ X
     const float xi = xx[i];
     const float eps = 0.015625f * sqrtf(xi) * sqrtf(yy[m]) * 1.01f;          // yy[m] = max_j |y_j|^2 (la_bank_prepare)
     const float cut = thr == INF ? INF : thr + 2.f * eps;
-    // overflowed groups: the 8th (largest) kept score of the group is still within the cut
-    const int ngroups = ncand >> 3;
+    // overflowed groups: the last (largest) kept score of the group is still within the cut
+    const int ngroups = ncand / kCand;
     int novf = 0;
     for (int g0 = 0; g0 < ngroups; g0 += 32) {
         const int g = g0 + lane;
-        const bool ov = g < ngroups && ci[g * 8 + 7] >= 0 && cs[g * 8 + 7] <= cut;
+        const bool ov = g < ngroups && ci[g * kCand + kCand - 1] >= 0 && cs[g * kCand + kCand - 1] <= cut;
         const unsigned bal = __ballot_sync(0xffffffffu, ov);
         if (ov) {
             const int slot = novf + __popc(bal & ((1u << lane) - 1));
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ X
     for (int t = 0; t < 8; ++t) {
         bool keep = !scan_all && li[t] >= 0 && ls[t] <= cut;
         if (keep)
-            for (int o = 0; o < novf; ++o) if (s_ovf[wib][o] == (lc[t] >> 3)) keep = false;
+            for (int o = 0; o < novf; ++o) if (s_ovf[wib][o] == lc[t] / kCand) keep = false;
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         if (keep) s_list[wib][cnt + __popc(bal & ((1u << lane) - 1))] = li[t];
         cnt += __popc(bal);
@@ -174,8 +175,8 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ X
         for (int c = 0; c < cnt; ++c) exact(s_list[wib][c]);
         for (int o = 0; o < novf; ++o) {
             const int g = s_ovf[wib][o];
-            const int j0 = (g >> 1) * 256 + (g & 1) * 128;          // group = (256-code tile, 128-column half)
-            for (int j = j0; j < j0 + 128 && j < m; ++j) exact(j);
+            const int j0 = g * kChunk;
+            for (int j = j0; j < j0 + kChunk && j < m; ++j) exact(j);
         }
     }
     if (lane == 0)
@@ -235,7 +236,7 @@ NearestLayout nearest_layout(int n, int m, int K) {
     L.Hq = (L.Hq + 7) / 8 * 8;                 // whole 8x16 query tiles
     L.rows_padded = L.Hq * 16;
     L.n_blocks = (m + 255) / 256;
-    L.ncand = L.n_blocks * 2 * kCand;        // two epilogue groups per tile
+    L.ncand = L.n_blocks * (256 / kChunk) * kCand;
     size_t off = 0;
     auto take = [&](size_t b) { off = (off + 1023) & ~size_t(1023); size_t o = off; off += b; return o; };
     L.off_xhi = take(static_cast<size_t>(L.rows_padded) * K * 2);

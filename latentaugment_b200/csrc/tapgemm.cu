@@ -303,10 +303,6 @@ __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const
     float nz = 0.f;
     if (EPI == kEpiFwd && rc.valid && P.noise) nz = __ldg(P.noise + rc.n * P.noise_stride_n + rc.px_in_img) * P.noise_scale;
     float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
-    float best_s[8];
-    int best_i[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { best_s[k] = __int_as_float(0x7f800000); best_i[k] = -1; }
     const bool tk_valid = rc.valid && rc.pix < P.n_queries;
     const float clampv = P.act_clamp >= 0.f ? P.act_clamp : __int_as_float(0x7f800000);
     // staged stores: the lane re-reads 16-byte piece (lane & 3) of rows 8j + (lane >> 2), j = 0..3, so that
@@ -413,25 +409,26 @@ __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const
                 }
             }
         } else if constexpr (EPI == kEpiTopK) {
+            // the two smallest scores of this row within the 32-code chunk, branch-free (a per-lane sorted insertion into a
+            // deeper list diverges on almost every column and made this epilogue four times longer than the MMAs of its
+            // tile); ties keep the lower code.  The exact re-rank rescans any chunk whose list may be incomplete.
             if (tk_valid) {
+                const float INF = __int_as_float(0x7f800000);
+                float m1 = INF, m2 = INF;
+                int i1 = -1, i2 = -1;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int code = col0 + j;
-                    if (code < P.n_codes) {
-                        float sc = fmaf(-2.f, acc[j], __ldg(P.code_sqnorm + code));
-                        int id = code;
-                        if (sc < best_s[7]) {
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) {       // sorted insertion, ascending
-                                if (sc < best_s[k]) {
-                                    const float ts = best_s[k]; const int ti = best_i[k];
-                                    best_s[k] = sc; best_i[k] = id;
-                                    sc = ts; id = ti;
-                                }
-                            }
-                        }
-                    }
+                    const float sc = code < P.n_codes ? fmaf(-2.f, acc[j], __ldg(P.code_sqnorm + code)) : INF;
+                    const bool lt1 = sc < m1, lt2 = sc < m2;
+                    m2 = lt1 ? m1 : (lt2 ? sc : m2);
+                    i2 = lt1 ? i1 : (lt2 ? code : i2);
+                    m1 = lt1 ? sc : m1;
+                    i1 = lt1 ? code : i1;
                 }
+                const long long base = (rc.pix * (static_cast<long long>(P.n_blocks) * (BN / 32)) + tc.nblk * (BN / 32) + ch) * 2;
+                *reinterpret_cast<float2*>(P.cand_score + base) = make_float2(m1, m2);
+                *reinterpret_cast<int2*>(P.cand_idx + base) = make_int2(i1, i2);
             }
         } else if constexpr (EPI == kEpiFwd) {
             if (kStaged) {
@@ -502,16 +499,6 @@ __device__ __forceinline__ void rowowner_warp_tile(const TapGemmParams& P, const
                 }
             }
         }
-    }
-    if (EPI == kEpiTopK && tk_valid) {
-        const long long base = ((rc.pix * P.n_blocks + tc.nblk) * 2 + part) * P.topk;
-        const long long other = ((rc.pix * P.n_blocks + tc.nblk) * 2 + (part ^ 1)) * P.topk;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (k < P.topk) {
-                P.cand_score[base + k] = best_s[k]; P.cand_idx[base + k] = best_i[k];
-                if (fill_other) { P.cand_score[other + k] = __int_as_float(0x7f800000); P.cand_idx[other + k] = -1; }
-            }
     }
     if (EPI == kEpiLinear && P.lin_rgb_w && rc.valid) {
         float* g = reinterpret_cast<float*>(P.lin_rgb_g + rc.pix);
@@ -633,8 +620,11 @@ __device__ __forceinline__ void bwd_warp_tile(const TapGemmParams& P, const BwdT
     if (new_key != st.key) {
         bwd_flush<BN, NSTEP>(P, st, lane);
         st.key = new_key;
+        st.nsteps = 0;
     }
-    if (n_ok) st.nsteps = nsteps;
+    // the accumulators of a key live across tiles whose step counts differ (a two-tile unit gives the warp all steps of its
+    // tile, a single-tile unit -- the odd tile at the end of a CTA's range -- only half of them): flush the widest seen
+    if (n_ok && nsteps > st.nsteps) st.nsteps = nsteps;
 
     const float inv_gain = 1.f / P.act_gain, inv_gain_slope = 1.f / (P.act_gain * P.act_slope);
     const float clampv = P.act_clamp >= 0.f ? P.act_clamp : __int_as_float(0x7f800000);

@@ -53,7 +53,7 @@ enum TapEpilogue : int {
     kEpiRawF32 = 0,    // store accumulators as fp32 [pixel][n_total]                  (tests)
     kEpiFwd = 1,       // demod + noise + bias + lrelu*gain + clamp -> x, x*s_next, toRGB partials
     kEpiBwd = 2,       // style-gradient reductions + activation backward of the producer layer -> g_y
-    kEpiTopK = 3,      // rows = queries, columns = bank codes: per-tile k smallest |y|^2 - 2<x,y> per row
+    kEpiTopK = 3,      // rows = queries, columns = bank codes: the 2 smallest |y|^2 - 2<x,y> per row and 32-code chunk
     kEpiStoreBf16 = 4, // store accumulators as bf16 (hi [+ lo]) into x_hi / x_lo [pixel][n_total]
     kEpiLinear = 5,    // plain (unmodulated) layers of the discriminator: r = acc (+ lin_add) -> lin_out;
                        // r * act'(lin_saved) -> lin_gz   (bf16 [pixel][n_total] tensors, each optional)
@@ -137,9 +137,9 @@ struct TapGemmParams {
 
     // ---- kEpiTopK: acc[query, code] = <x, y>
     const float* code_sqnorm;          // [n_codes] |y_j|^2
-    int n_codes, n_queries, topk;      // topk <= 8
-    float* cand_score;                 // [n_queries][n_blocks][2][topk]  (two epilogue groups per tile)
-    int* cand_idx;                     // [n_queries][n_blocks][2][topk]
+    int n_codes, n_queries, topk;      // topk = 2
+    float* cand_score;                 // [n_queries][n_blocks * BN / 32][2]  ascending per 32-code chunk
+    int* cand_idx;                     // [n_queries][n_blocks * BN / 32][2]  (-1 = empty)
 
     int* err_flag;
     unsigned long long* dbg_clock;     // optional [64]: CTA 0 cycles, nanoseconds and MMA-thread timeline stamps (LA_DBG_CLK experiments)
