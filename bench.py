@@ -255,10 +255,10 @@ def run_c5(args):
     shard = torch.randn([per, K], generator=torch.Generator().manual_seed(1 + rank)).to(dev)
     X = torch.randn([nq, K], generator=torch.Generator().manual_seed(7)).to(dev)
     bank = LatentBank(shard, index_offset=rank * per)
-    searcher = parallel.ShardedNearest(bank, nq, k) if world > 1 else None
+    searcher = parallel.ShardedNearest(bank, nq, k)          # search (+ all-gather + merge) captured once, replayed per call
 
     def search():
-        return searcher(X) if searcher is not None else bank.nearest(X, k)
+        return searcher(X)
     for _ in range(max(args.warmup, 3)):
         d, i = search()
     torch.cuda.synchronize()
@@ -291,7 +291,7 @@ def run_c5(args):
     t0 = time.perf_counter()
     for _ in range(20):
         Xd = Xh.to(dev, non_blocking=True)
-        dd, ii = searcher(Xd) if searcher is not None else bank.nearest(Xd, k)
+        dd, ii = searcher(Xd)
         dd.cpu(), ii.cpu()
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) / 20 * 1e3
@@ -314,7 +314,7 @@ def run_c5(args):
                            'l2': f'bank shard {per * K * 2 / 2**20:.0f} MiB bf16 + {per * K * 4 / 2**20:.0f} MiB f32 per GPU vs 126 MB L2'},
                 'clocks': clk, 'indices_bit_exact_vs_pairwise': exact,
                 'e2e': {'value': nq / (e2e_ms * 1e-3), 'unit': 'queries/s', 'h2d_bytes_per_step': nq * K * 4, 'd2h_bytes_per_step': nq * k * 12},
-                'gpu_launches': int(reps * (4 if world > 1 else 3)),
+                'gpu_launches': int(reps * (5 if world > 1 else 4)), 'graph_captured': searcher.graph is not None,
                 'roofline': {'bound': 'tensor', 'kernel': 'tapgemm_kernel<EPI=TopK> (query x bank GEMM + fused per-tile top-k)',
                              'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'traffic': None,
                              'peak_source': 'MEASURED_PEAKS.json bf16_tflops (burst)' if peaks else 'fallback 1.59 PFLOP/s',
@@ -479,7 +479,7 @@ def main():
         fsyn = f_syn(res, C, channel_base=c['channel_base'], channel_max=c['channel_max'])
         traffic, traffic_src = None, None   # DRAM bytes (read + write) of the same launches: one ncu --set full capture of this workload
         if args.config == 'c2' and args.precision == 'bf16' and B == 32:
-            for fn in ('r2_tapgemm_traffic.json', 'r1c_tapgemm_traffic.json'):
+            for fn in ('r2_tapgemm_traffic.json', 'r1c_tapgemm_traffic.json'):       # newest capture first
                 try:
                     traffic = json.load(open(os.path.join(ROOT, 'profiles', fn)))['dram_bytes_read_plus_write']
                     traffic_src = f'profiles/{fn} (ncu dram__bytes_read.sum + dram__bytes_write.sum, not measured in this run)'

@@ -47,7 +47,7 @@ class ShardedNearest:
     def __init__(self, bank, n, k, group=None, use_graph=True):
         from . import _lib
         self.bank, self.n, self.k, self.group = bank, int(n), int(k), group
-        self.world = dist.get_world_size(group)
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         dev = bank.Y.device
         self.lib = _lib.load()
         nk = self.n * self.k
@@ -77,6 +77,9 @@ class ShardedNearest:
 
         from . import _lib
         from .engine import _ptr, _stream_ptr
+        if self.world == 1:              # one shard: the search alone, still replayed as one graph (no per-call host work)
+            self.bank.nearest(self.X, self.k, out=(self.out_d, self.out_i))
+            return
         self.bank.nearest(self.X, self.k, out=(self.d_local, self.i_local))
         dist.all_gather_into_tensor(self.all, self.rec, group=self.group)
         dev = self.X.device
