@@ -237,10 +237,13 @@ __global__ void __launch_bounds__(256) lpips_tap_kernel(const unsigned* __restri
                                                         int C, const float* __restrict__ lin_w, float* bank_mean, const CallConsts* cc, int n_valid_crops,
                                                         float inv_m, double* S, float* m2, int mask, unsigned* out_hi, unsigned* out_lo, float* out_f32) {
     const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
-    const long long pix = blockIdx.x * static_cast<long long>(warps) + (threadIdx.x >> 5);
+    const long long total_px = static_cast<long long>(ncrops) * P;
+    float s_block = 0.f;             // this warp's loss partial over all its pixels (grid-stride walk: few, long-lived blocks, so
+                                     // the loss needs one double atomic per block instead of one per 8 pixels)
+    for (long long pix = blockIdx.x * static_cast<long long>(warps) + (threadIdx.x >> 5); pix < total_px;
+         pix += static_cast<long long>(gridDim.x) * warps) {
     float s_acc = 0.f;
-    const bool live = pix < static_cast<long long>(ncrops) * P;
-    if (live) {
+    {
         const int crop = static_cast<int>(pix / P), p = static_cast<int>(pix - static_cast<long long>(crop) * P);
         const int mod = crop % imgc;
         const int hc = C >> 1, npair = C >> 6;           // pairs per lane
@@ -302,11 +305,13 @@ __global__ void __launch_bounds__(256) lpips_tap_kernel(const unsigned* __restri
                     st_sp2(out_hi, out_lo, pix * hc + j * 32 + lane, o0, o1);
                 }
             s_acc = warp_sum(s_acc) / P;
+            s_block += s_acc;
         }
+    }
     }
     if (MODE == 0) {       // one double atomic per block
         __shared__ float sm[8];
-        if (lane == 0) sm[threadIdx.x >> 5] = live ? s_acc : 0.f;
+        if (lane == 0) sm[threadIdx.x >> 5] = s_block;
         __syncthreads();
         if (threadIdx.x == 0) {
             double t = 0.0;
@@ -367,6 +372,11 @@ struct la_lpips {
 namespace {
 
 int choose_bn(int n, long long m_tiles) { return n % 128 ? 64 : pick_bn(n, m_tiles); }
+// blocks of 8 warps, a warp per pixel, grid-stride: at most 8 resident blocks per SM
+inline int tap_grid(long long pixels, int num_sms) {
+    const long long want = (pixels + 7) / 8, cap = static_cast<long long>(num_sms > 0 ? num_sms : 148) * 8;
+    return static_cast<int>(want < cap ? want : cap);
+}
 
 int dense_maps(const la_lpips* L, TapGemmParams& P, const Pl& t, int C, int R) {
     const long long sW = C, sH = static_cast<long long>(R) * C, sN = sH * R;
@@ -594,7 +604,7 @@ int lpips_set_bank(la_lpips* L, const float* d_crops, int M, cudaStream_t s, lon
             if (!T.used) continue;
             const Conv& c = L->conv[T.conv];
             const long long pixels = static_cast<long long>(L->ncrops) * T.R * T.R;
-            lpips_tap_kernel<1><<<cdiv(pixels, 8), 256, 0, s>>>(CU32(c.x.hi), CU32(c.x.lo), L->ncrops, L->imgc, T.R * T.R, T.C, T.lin_w, T.bank_mean, L->cc,
+            lpips_tap_kernel<1><<<tap_grid(pixels, L->num_sms), 256, 0, s>>>(CU32(c.x.hi), CU32(c.x.lo), L->ncrops, L->imgc, T.R * T.R, T.C, T.lin_w, T.bank_mean, L->cc,
                                                               nv * L->imgc, 1.f / M, nullptr, L->m2, 0, nullptr, nullptr, nullptr);
             LCU(cudaGetLastError());
         }
@@ -622,7 +632,7 @@ int lpips_backward(la_lpips* L, float4* g_img, int accumulate, float* d_loss, cu
         const bool last = T.conv == L->last_conv;
         const Pl& out = last ? L->gz[T.conv & 1] : T.tg;
         const long long pixels = static_cast<long long>(L->ncrops) * T.R * T.R;
-        lpips_tap_kernel<0><<<cdiv(pixels, 8), 256, 0, s>>>(CU32(c.x.hi), CU32(c.x.lo), L->ncrops, L->imgc, T.R * T.R, T.C, T.lin_w, T.bank_mean, L->cc,
+        lpips_tap_kernel<0><<<tap_grid(pixels, L->num_sms), 256, 0, s>>>(CU32(c.x.hi), CU32(c.x.lo), L->ncrops, L->imgc, T.R * T.R, T.C, T.lin_w, T.bank_mean, L->cc,
                                                           L->ncrops, 0.f, L->S, nullptr, last ? 1 : 0, U32(out.hi), U32(out.lo), nullptr);
         LCU(cudaGetLastError());
         if (launches) ++*launches;
@@ -665,7 +675,7 @@ int lpips_copy_tap(la_lpips* L, int k, float* d_out, size_t* count, cudaStream_t
         if (!d_out) return 0;
         const Conv& c = L->conv[T.conv];
         const long long pixels = static_cast<long long>(L->ncrops) * T.R * T.R;
-        lpips_tap_kernel<2><<<cdiv(pixels, 8), 256, 0, s>>>(CU32(c.x.hi), CU32(c.x.lo), L->ncrops, L->imgc, T.R * T.R, T.C, T.lin_w, nullptr, L->cc, 0, 0.f,
+        lpips_tap_kernel<2><<<tap_grid(pixels, L->num_sms), 256, 0, s>>>(CU32(c.x.hi), CU32(c.x.lo), L->ncrops, L->imgc, T.R * T.R, T.C, T.lin_w, nullptr, L->cc, 0, 0.f,
                                                           nullptr, nullptr, 0, nullptr, nullptr, d_out);
         LCU(cudaGetLastError());
         return 0;
