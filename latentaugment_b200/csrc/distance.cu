@@ -66,8 +66,8 @@ __global__ void pairwise_kernel(const float* __restrict__ X, int n, const float*
 // smallest approximate scores s^ = |y|^2 - 2 <bf16(x), bf16(y)> in ascending order.  With eps = 2^-6 |x| max_j|y_j|
 // (>= the error of s^: two bf16 roundings of relative size 2^-9 each on every product, doubled by the factor -2, plus
 // the fp32 accumulation error, Cauchy-Schwarz on sum |x_k y_k|) the exact k best are found as follows:
-//   1. thr = the warp-wide 8th smallest s^ over all candidates.  The k-th smallest EXACT score T satisfies T <= thr + eps
-//      and every exact top-k member has s^ <= T + eps, hence s^ <= cut = thr + 2 eps.
+//   1. thr = the 8th smallest of the lanes' two best s^ (8 distinct candidates have s^ <= thr, so the k-th smallest EXACT
+//      score T satisfies T <= thr + eps) and every exact top-k member has s^ <= T + eps, hence s^ <= cut = thr + 2 eps.
 //   2. A member can be missing from the candidate lists only if 2 others of its group have smaller s^, i.e. only if
 //      that group's 2nd kept score is <= cut: such groups ("overflowed") are rescanned exhaustively (their listed
 //      candidates are dropped, the scan covers them); with more than kMaxOvf of them the whole shard is scanned.
@@ -75,42 +75,34 @@ __global__ void pairwise_kernel(const float* __restrict__ X, int n, const float*
 //      one rounding, the reference's association (YY + XX) - 2 YX -- and the k smallest (distance, index) pairs are
 //      kept, ties to the lowest index.
 // So the result equals the exact search for ANY data, not only in probability; the margins only set the cost.
-constexpr int kMaxOvf = 128;
+constexpr int kMaxOvf = 128, kMaxList = 512;
 __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ X, const float* __restrict__ xx, const float* __restrict__ Y,
                                                      const float* __restrict__ yy, int n, int m, int K, const float* __restrict__ cand_score,
                                                      const int* __restrict__ cand_idx, int ncand, int k, long long index_offset,
                                                      float* out_dist, long long* out_idx) {
-    __shared__ int s_list[8][256];
+    __shared__ int s_list[8][kMaxList];
     __shared__ int s_ovf[8][kMaxOvf];
     const int wib = threadIdx.x >> 5;
     const int i = blockIdx.x * (blockDim.x >> 5) + wib;
     const int lane = threadIdx.x & 31;
     if (i >= n) return;
     const float INF = __int_as_float(0x7f800000);
-    float ls[8];
-    int li[8], lc[8];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) { ls[t] = INF; li[t] = -1; lc[t] = -1; }
     const float* cs = cand_score + static_cast<long long>(i) * ncand;
     const int* ci = cand_idx + static_cast<long long>(i) * ncand;
+    // pass 1 (branch-free): the two smallest approximate scores of this lane's strided share.  The 8th smallest of the
+    // 64 lane values bounds the 8th smallest over all candidates from ABOVE, which is all the argument of step 1 needs
+    // (any 8 candidates with s^ <= thr give T <= thr + eps); a looser thr only lets a few more candidates through.
+    float m1 = INF, m2 = INF;
     for (int c = lane; c < ncand; c += 32) {
-        float sc = cs[c];
-        int id = ci[c], pos = c;
-        if (id < 0 || !(sc < ls[7])) continue;
-#pragma unroll
-        for (int t = 0; t < 8; ++t)
-            if (sc < ls[t]) {
-                const float ts = ls[t]; const int ti = li[t], tp = lc[t];
-                ls[t] = sc; li[t] = id; lc[t] = pos; sc = ts; id = ti; pos = tp;
-            }
+        const float sc = ci[c] >= 0 ? cs[c] : INF;
+        const bool lt1 = sc < m1, lt2 = sc < m2;
+        m2 = lt1 ? m1 : (lt2 ? sc : m2);
+        m1 = lt1 ? sc : m1;
     }
-    // the warp's 8th smallest approximate score: pop the minimum of the lane heads 8 times
     int head = 0;
     float thr = INF;
     for (int r = 0; r < 8; ++r) {
-        float h = INF;
-#pragma unroll
-        for (int t = 0; t < 8; ++t) if (t == head) h = ls[t];
+        const float h = head == 0 ? m1 : (head == 1 ? m2 : INF);
         float mn = h;
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
@@ -136,16 +128,17 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ X
         novf += __popc(bal);
     }
     __syncwarp();
-    const bool scan_all = novf > kMaxOvf || thr == INF;
-    // compact the surviving listed candidates (not those of overflowed groups: the scan covers them)
+    bool scan_all = novf > kMaxOvf || thr == INF;
+    // pass 2: compact the listed candidates within the cut (not those of overflowed groups: the scan covers them)
     int cnt = 0;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        bool keep = !scan_all && li[t] >= 0 && ls[t] <= cut;
+    for (int c0 = 0; c0 < ncand && !scan_all; c0 += 32) {
+        const int c = c0 + lane;
+        bool keep = c < ncand && ci[c] >= 0 && cs[c] <= cut;
         if (keep)
-            for (int o = 0; o < novf; ++o) if (s_ovf[wib][o] == lc[t] / kCand) keep = false;
+            for (int o = 0; o < novf; ++o) if (s_ovf[wib][o] == c / kCand) keep = false;
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (keep) s_list[wib][cnt + __popc(bal & ((1u << lane) - 1))] = li[t];
+        if (cnt + __popc(bal) > kMaxList) { scan_all = true; break; }        // (warp-uniform) more survivors than the list holds
+        if (keep) s_list[wib][cnt + __popc(bal & ((1u << lane) - 1))] = ci[c];
         cnt += __popc(bal);
     }
     __syncwarp();
