@@ -189,22 +189,31 @@ __global__ void firdown_fwd_kernel(const unsigned* __restrict__ x, const unsigne
     const int e = blockIdx.x * blockDim.x + threadIdx.x;       // (n, channel pair) of output row m = blockIdx.y, sample blockIdx.z
     if (e >= Ro * hc) return;
     const int cp = e % hc, n = e / hc, m = blockIdx.y, b = blockIdx.z;
-    float a0 = 0.f, a1 = 0.f;
+    // all 16 (x 2 planes) loads are issued before the first FMA: out-of-range taps read a clamped address with weight 0
+    // (a `continue` per tap kept the loads from being batched and left the kernel latency-bound)
+    unsigned u[16], l[16];
+    float wgt[16];
 #pragma unroll
     for (int jy = 0; jy < 4; ++jy) {
         const int y = 2 * m + jy - 1;
-        if (y < 0 || y >= R) continue;
-        const long long roff = (static_cast<long long>(b) * R + y) * R * hc + cp;
+        const bool oky = y >= 0 && y < R;
+        const long long roff = (static_cast<long long>(b) * R + (oky ? y : 0)) * R * hc + cp;
 #pragma unroll
         for (int jx = 0; jx < 4; ++jx) {
             const int xx = 2 * n + jx - 1;
-            if (xx < 0 || xx >= R) continue;
-            const unsigned u = __ldg(x + roff + xx * hc);
-            float v0 = lo_f(u), v1 = hi_f(u);
-            if (x_lo) { const unsigned l = __ldg(x_lo + roff + xx * hc); v0 += lo_f(l); v1 += hi_f(l); }
-            a0 = fmaf(f.k[jy * 4 + jx], v0, a0);
-            a1 = fmaf(f.k[jy * 4 + jx], v1, a1);
+            const bool ok = oky && xx >= 0 && xx < R;
+            const long long off = roff + static_cast<long long>(ok ? xx : 0) * hc;
+            u[jy * 4 + jx] = __ldg(x + off);
+            l[jy * 4 + jx] = x_lo ? __ldg(x_lo + off) : 0u;
+            wgt[jy * 4 + jx] = ok ? f.k[jy * 4 + jx] : 0.f;
         }
+    }
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        const float v0 = lo_f(u[t]) + lo_f(l[t]), v1 = hi_f(u[t]) + hi_f(l[t]);
+        a0 = fmaf(wgt[t], v0, a0);
+        a1 = fmaf(wgt[t], v1, a1);
     }
     st_sp2(ys, ys_lo, ((static_cast<long long>(b) * Ro + m) * Ro) * hc + e, a0, a1);
 }

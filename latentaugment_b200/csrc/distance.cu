@@ -75,13 +75,13 @@ __global__ void pairwise_kernel(const float* __restrict__ X, int n, const float*
 //      one rounding, the reference's association (YY + XX) - 2 YX -- and the k smallest (distance, index) pairs are
 //      kept, ties to the lowest index.
 // So the result equals the exact search for ANY data, not only in probability; the margins only set the cost.
-constexpr int kMaxOvf = 128, kMaxList = 512;
-__global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ X, const float* __restrict__ xx, const float* __restrict__ Y,
+constexpr int kMaxOvf = 128, kMaxList = 512, kRerankWarps = 4;      // 4 warps per block: 1024 queries spread over every SM
+__global__ void __launch_bounds__(32 * kRerankWarps) rerank_kernel(const float* __restrict__ X, const float* __restrict__ xx, const float* __restrict__ Y,
                                                      const float* __restrict__ yy, int n, int m, int K, const float* __restrict__ cand_score,
                                                      const int* __restrict__ cand_idx, int ncand, int k, long long index_offset,
                                                      float* out_dist, long long* out_idx) {
-    __shared__ int s_list[8][kMaxList];
-    __shared__ int s_ovf[8][kMaxOvf];
+    __shared__ int s_list[kRerankWarps][kMaxList];
+    __shared__ int s_ovf[kRerankWarps][kMaxOvf];
     const int wib = threadIdx.x >> 5;
     const int i = blockIdx.x * (blockDim.x >> 5) + wib;
     const int lane = threadIdx.x & 31;
@@ -89,15 +89,25 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ X
     const float INF = __int_as_float(0x7f800000);
     const float* cs = cand_score + static_cast<long long>(i) * ncand;
     const int* ci = cand_idx + static_cast<long long>(i) * ncand;
-    // pass 1 (branch-free): the two smallest approximate scores of this lane's strided share.  The 8th smallest of the
-    // 64 lane values bounds the 8th smallest over all candidates from ABOVE, which is all the argument of step 1 needs
-    // (any 8 candidates with s^ <= thr give T <= thr + eps); a looser thr only lets a few more candidates through.
+    // (the kernel is a chain of memory latencies in one warp per query -- 7 warps per SM at 1024 queries -- so every loop
+    // issues several independent loads per trip: candidate pairs as 8-byte loads, four trips in flight; code rows as
+    // four 16-byte loads per lane)
+    const float2* cs2 = reinterpret_cast<const float2*>(cs);
+    const int2* ci2 = reinterpret_cast<const int2*>(ci);
+    const int ngroups = ncand / kCand;
+    // pass 1 (branch-free): the two smallest approximate scores of this lane's strided share of the groups.  The 8th
+    // smallest of the 64 lane values bounds the 8th smallest over all candidates from ABOVE, which is all the argument
+    // of step 1 needs; a looser thr only lets a few more candidates through.
     float m1 = INF, m2 = INF;
-    for (int c = lane; c < ncand; c += 32) {
-        const float sc = ci[c] >= 0 ? cs[c] : INF;
-        const bool lt1 = sc < m1, lt2 = sc < m2;
-        m2 = lt1 ? m1 : (lt2 ? sc : m2);
-        m1 = lt1 ? sc : m1;
+#pragma unroll 4
+    for (int g = lane; g < ngroups; g += 32) {
+        const float2 sc = __ldg(cs2 + g);
+        const int2 id = __ldg(ci2 + g);
+        const float a = id.x >= 0 ? sc.x : INF, bq = id.y >= 0 ? sc.y : INF;        // a <= bq (ascending per group)
+        const bool a1 = a < m1, a2 = a < m2;
+        m2 = a1 ? m1 : (a2 ? a : m2);
+        m1 = a1 ? a : m1;
+        m2 = bq < m2 ? bq : m2;                                                     // bq >= a: it can only displace m2
     }
     int head = 0;
     float thr = INF;
@@ -114,46 +124,38 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ X
     const float xi = xx[i];
     const float eps = 0.015625f * sqrtf(xi) * sqrtf(yy[m]) * 1.01f;          // yy[m] = max_j |y_j|^2 (la_bank_prepare)
     const float cut = thr == INF ? INF : thr + 2.f * eps;
-    // overflowed groups: the last (largest) kept score of the group is still within the cut
-    const int ngroups = ncand / kCand;
-    int novf = 0;
+    // pass 2, one trip per 32 groups: overflowed groups (the last kept score is still within the cut: the group may hide
+    // more) go to the rescan list, the candidates within the cut of the other groups are compacted into the survivor list
+    int novf = 0, cnt = 0;
+    bool scan_all = thr == INF;
+#pragma unroll 4
     for (int g0 = 0; g0 < ngroups; g0 += 32) {
         const int g = g0 + lane;
-        const bool ov = g < ngroups && ci[g * kCand + kCand - 1] >= 0 && cs[g * kCand + kCand - 1] <= cut;
-        const unsigned bal = __ballot_sync(0xffffffffu, ov);
+        float2 sc = make_float2(INF, INF);
+        int2 id = make_int2(-1, -1);
+        if (g < ngroups) { sc = __ldg(cs2 + g); id = __ldg(ci2 + g); }
+        const bool ov = id.y >= 0 && sc.y <= cut;
+        const bool k0 = !ov && id.x >= 0 && sc.x <= cut;           // (sc.y > cut here, so only the first entry can survive)
+        const unsigned bo = __ballot_sync(0xffffffffu, ov), bk = __ballot_sync(0xffffffffu, k0);
         if (ov) {
-            const int slot = novf + __popc(bal & ((1u << lane) - 1));
+            const int slot = novf + __popc(bo & ((1u << lane) - 1));
             if (slot < kMaxOvf) s_ovf[wib][slot] = g;
         }
-        novf += __popc(bal);
+        if (k0) {
+            const int slot = cnt + __popc(bk & ((1u << lane) - 1));
+            if (slot < kMaxList) s_list[wib][slot] = id.x;
+        }
+        novf += __popc(bo);
+        cnt += __popc(bk);
     }
-    __syncwarp();
-    bool scan_all = novf > kMaxOvf || thr == INF;
-    // pass 2: compact the listed candidates within the cut (not those of overflowed groups: the scan covers them)
-    int cnt = 0;
-    for (int c0 = 0; c0 < ncand && !scan_all; c0 += 32) {
-        const int c = c0 + lane;
-        bool keep = c < ncand && ci[c] >= 0 && cs[c] <= cut;
-        if (keep)
-            for (int o = 0; o < novf; ++o) if (s_ovf[wib][o] == c / kCand) keep = false;
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (cnt + __popc(bal) > kMaxList) { scan_all = true; break; }        // (warp-uniform) more survivors than the list holds
-        if (keep) s_list[wib][cnt + __popc(bal & ((1u << lane) - 1))] = ci[c];
-        cnt += __popc(bal);
-    }
+    if (novf > kMaxOvf || cnt > kMaxList) scan_all = true;
     __syncwarp();
     float bd[8];
     int bi[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) { bd[t] = INF; bi[t] = 0x7fffffff; }
     const float* x = X + static_cast<long long>(i) * K;
-    auto exact = [&](int j) {
-        const float* y = Y + static_cast<long long>(j) * K;
-        double dot = 0.0;
-        for (int kk = lane; kk < K; kk += 32) dot += static_cast<double>(x[kk]) * y[kk];
-        dot = warp_sum_d(dot);
-        float d = (yy[j] + xi) - 2.f * static_cast<float>(dot);
-        int id = j;
+    auto insert = [&](float d, int id) {
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
             if (d < bd[t] || (d == bd[t] && id < bi[t])) {
@@ -162,14 +164,53 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ X
             }
         }
     };
-    if (scan_all) {
-        for (int j = 0; j < m; ++j) exact(j);
+    if ((K & 127) == 0 && K <= 1024) {
+        // query row in registers; a code row = K / 128 independent 16-byte loads per lane
+        float4 xr[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (q * 128 < K) xr[q] = __ldg(reinterpret_cast<const float4*>(x) + q * 32 + lane);
+        auto exact = [&](int j) {
+            const float4* y = reinterpret_cast<const float4*>(Y + static_cast<long long>(j) * K);
+            float4 yr[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (q * 128 < K) yr[q] = __ldg(y + q * 32 + lane);
+            double dot = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (q * 128 < K) {
+                    dot += static_cast<double>(xr[q].x) * yr[q].x; dot += static_cast<double>(xr[q].y) * yr[q].y;
+                    dot += static_cast<double>(xr[q].z) * yr[q].z; dot += static_cast<double>(xr[q].w) * yr[q].w;
+                }
+            dot = warp_sum_d(dot);
+            insert((yy[j] + xi) - 2.f * static_cast<float>(dot), j);
+        };
+        if (scan_all) {
+            for (int j = 0; j < m; ++j) exact(j);
+        } else {
+            for (int c = 0; c < cnt; ++c) exact(s_list[wib][c]);
+            for (int o = 0; o < novf; ++o) {
+                const int j0 = s_ovf[wib][o] * kChunk;
+                for (int j = j0; j < j0 + kChunk && j < m; ++j) exact(j);
+            }
+        }
     } else {
-        for (int c = 0; c < cnt; ++c) exact(s_list[wib][c]);
-        for (int o = 0; o < novf; ++o) {
-            const int g = s_ovf[wib][o];
-            const int j0 = g * kChunk;
-            for (int j = j0; j < j0 + kChunk && j < m; ++j) exact(j);
+        auto exact = [&](int j) {
+            const float* y = Y + static_cast<long long>(j) * K;
+            double dot = 0.0;
+            for (int kk = lane; kk < K; kk += 32) dot += static_cast<double>(x[kk]) * y[kk];
+            dot = warp_sum_d(dot);
+            insert((yy[j] + xi) - 2.f * static_cast<float>(dot), j);
+        };
+        if (scan_all) {
+            for (int j = 0; j < m; ++j) exact(j);
+        } else {
+            for (int c = 0; c < cnt; ++c) exact(s_list[wib][c]);
+            for (int o = 0; o < novf; ++o) {
+                const int j0 = s_ovf[wib][o] * kChunk;
+                for (int j = j0; j < j0 + kChunk && j < m; ++j) exact(j);
+            }
         }
     }
     if (lane == 0)
@@ -336,7 +377,7 @@ int la_nearest_codes(const float* d_X, int n, const float* d_Y, const void* d_ba
         int r = launch_tapgemm(P, sms, s);
         if (r) return la_fail_msg(r, "launch_tapgemm failed");
     }
-    rerank_kernel<<<(n + 7) / 8, 256, 0, s>>>(d_X, xx, d_Y, d_bank_sqnorm, n, m, K, cs, ci, L.ncand, k, index_offset, d_dist, d_idx);
+    rerank_kernel<<<(n + kRerankWarps - 1) / kRerankWarps, 32 * kRerankWarps, 0, s>>>(d_X, xx, d_Y, d_bank_sqnorm, n, m, K, cs, ci, L.ncand, k, index_offset, d_dist, d_idx);
     DCU(cudaGetLastError());
     return 0;
 }
