@@ -25,5 +25,5 @@ def golden():
     import torch
 
     def load(name):
-        return torch.load(os.path.join(GOLDEN, name), weights_only=False)
+        return torch.load(os.path.join(GOLDEN, name), weights_only=True)
     return load

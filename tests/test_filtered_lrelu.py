@@ -16,7 +16,7 @@ GOLDEN = os.path.join(os.path.dirname(__file__), 'golden', 'filtered_lrelu.pt')
 
 
 def _cases():
-    return torch.load(GOLDEN, weights_only=False)
+    return torch.load(GOLDEN, weights_only=True)
 
 
 def test_oracle_matches_reference_golden():

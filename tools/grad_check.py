@@ -17,7 +17,7 @@ import torch
 
 def oracle_grads(wl, cache):
     if cache and os.path.exists(cache):
-        return torch.load(cache, weights_only=False)
+        return torch.load(cache, weights_only=True)
     from oracle import latent_aug as ola
     G = wl['G']
     torch.set_num_threads(os.cpu_count() or 1)
