@@ -75,32 +75,35 @@ __global__ void pairwise_kernel(const float* __restrict__ X, int n, const float*
 //      one rounding, the reference's association (YY + XX) - 2 YX -- and the k smallest (distance, index) pairs are
 //      kept, ties to the lowest index.
 // So the result equals the exact search for ANY data, not only in probability; the margins only set the cost.
-constexpr int kMaxOvf = 128, kMaxList = 512, kRerankWarps = 4;      // 4 warps per block: 1024 queries spread over every SM
+constexpr int kMaxOvf = 128, kMaxList = 512, kRerankWarps = 4;
+// One BLOCK of kRerankWarps warps per query (the kernel is a chain of memory latencies: with a warp per query only 7 warps
+// per SM were in flight at 1024 queries and it took 550 of the 770 us of a search): the warps split the groups of both
+// passes and the exact evaluations, and every loop keeps several independent loads in flight.
 __global__ void __launch_bounds__(32 * kRerankWarps) rerank_kernel(const float* __restrict__ X, const float* __restrict__ xx, const float* __restrict__ Y,
                                                      const float* __restrict__ yy, int n, int m, int K, const float* __restrict__ cand_score,
                                                      const int* __restrict__ cand_idx, int ncand, int k, long long index_offset,
                                                      float* out_dist, long long* out_idx) {
-    __shared__ int s_list[kRerankWarps][kMaxList];
-    __shared__ int s_ovf[kRerankWarps][kMaxOvf];
-    const int wib = threadIdx.x >> 5;
-    const int i = blockIdx.x * (blockDim.x >> 5) + wib;
-    const int lane = threadIdx.x & 31;
+    __shared__ int s_list[kMaxList];
+    __shared__ int s_ovf[kMaxOvf];
+    __shared__ float s_thr[kRerankWarps];
+    __shared__ int s_cnt[2];                       // survivors, overflowed groups
+    __shared__ float s_bd[kRerankWarps][8];
+    __shared__ int s_bi[kRerankWarps][8];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    const int i = blockIdx.x;
     if (i >= n) return;
     const float INF = __int_as_float(0x7f800000);
-    const float* cs = cand_score + static_cast<long long>(i) * ncand;
-    const int* ci = cand_idx + static_cast<long long>(i) * ncand;
-    // (the kernel is a chain of memory latencies in one warp per query -- 7 warps per SM at 1024 queries -- so every loop
-    // issues several independent loads per trip: candidate pairs as 8-byte loads, four trips in flight; code rows as
-    // four 16-byte loads per lane)
-    const float2* cs2 = reinterpret_cast<const float2*>(cs);
-    const int2* ci2 = reinterpret_cast<const int2*>(ci);
+    const float2* cs2 = reinterpret_cast<const float2*>(cand_score + static_cast<long long>(i) * ncand);
+    const int2* ci2 = reinterpret_cast<const int2*>(cand_idx + static_cast<long long>(i) * ncand);
     const int ngroups = ncand / kCand;
-    // pass 1 (branch-free): the two smallest approximate scores of this lane's strided share of the groups.  The 8th
-    // smallest of the 64 lane values bounds the 8th smallest over all candidates from ABOVE, which is all the argument
-    // of step 1 needs; a looser thr only lets a few more candidates through.
+    constexpr int NT = 32 * kRerankWarps;
+    if (tid < 2) s_cnt[tid] = 0;
+    // pass 1 (branch-free): the two smallest approximate scores of this thread's strided share of the groups; the 8th
+    // smallest of a warp's 64 values bounds the 8th smallest over ALL candidates from above (8 distinct candidates lie
+    // below it), and so does the smallest of the warps' bounds -- all that step 1 needs.
     float m1 = INF, m2 = INF;
 #pragma unroll 4
-    for (int g = lane; g < ngroups; g += 32) {
+    for (int g = tid; g < ngroups; g += NT) {
         const float2 sc = __ldg(cs2 + g);
         const int2 id = __ldg(ci2 + g);
         const float a = id.x >= 0 ? sc.x : INF, bq = id.y >= 0 ? sc.y : INF;        // a <= bq (ascending per group)
@@ -121,40 +124,33 @@ __global__ void __launch_bounds__(32 * kRerankWarps) rerank_kernel(const float* 
         const unsigned who = __ballot_sync(0xffffffffu, h == mn);
         if (lane == __ffs(who) - 1) ++head;
     }
+    if (lane == 0) s_thr[wib] = thr;
+    __syncthreads();
+    thr = s_thr[0];
+#pragma unroll
+    for (int w = 1; w < kRerankWarps; ++w) thr = fminf(thr, s_thr[w]);
     const float xi = xx[i];
     const float eps = 0.015625f * sqrtf(xi) * sqrtf(yy[m]) * 1.01f;          // yy[m] = max_j |y_j|^2 (la_bank_prepare)
     const float cut = thr == INF ? INF : thr + 2.f * eps;
-    // pass 2, one trip per 32 groups: overflowed groups (the last kept score is still within the cut: the group may hide
-    // more) go to the rescan list, the candidates within the cut of the other groups are compacted into the survivor list
-    int novf = 0, cnt = 0;
-    bool scan_all = thr == INF;
+    // pass 2: overflowed groups (the last kept score is still within the cut: the group may hide more) go to the rescan
+    // list, the candidates within the cut of the other groups to the survivor list (order is irrelevant: the final
+    // selection orders by (distance, index))
 #pragma unroll 4
-    for (int g0 = 0; g0 < ngroups; g0 += 32) {
-        const int g = g0 + lane;
-        float2 sc = make_float2(INF, INF);
-        int2 id = make_int2(-1, -1);
-        if (g < ngroups) { sc = __ldg(cs2 + g); id = __ldg(ci2 + g); }
+    for (int g = tid; g < ngroups; g += NT) {
+        const float2 sc = __ldg(cs2 + g);
+        const int2 id = __ldg(ci2 + g);
         const bool ov = id.y >= 0 && sc.y <= cut;
         const bool k0 = !ov && id.x >= 0 && sc.x <= cut;           // (sc.y > cut here, so only the first entry can survive)
-        const unsigned bo = __ballot_sync(0xffffffffu, ov), bk = __ballot_sync(0xffffffffu, k0);
-        if (ov) {
-            const int slot = novf + __popc(bo & ((1u << lane) - 1));
-            if (slot < kMaxOvf) s_ovf[wib][slot] = g;
-        }
-        if (k0) {
-            const int slot = cnt + __popc(bk & ((1u << lane) - 1));
-            if (slot < kMaxList) s_list[wib][slot] = id.x;
-        }
-        novf += __popc(bo);
-        cnt += __popc(bk);
+        if (ov) { const int slot = atomicAdd(&s_cnt[1], 1); if (slot < kMaxOvf) s_ovf[slot] = g; }
+        if (k0) { const int slot = atomicAdd(&s_cnt[0], 1); if (slot < kMaxList) s_list[slot] = id.x; }
     }
-    if (novf > kMaxOvf || cnt > kMaxList) scan_all = true;
-    __syncwarp();
+    __syncthreads();
+    const int cnt = s_cnt[0], novf = s_cnt[1];
+    const bool scan_all = thr == INF || novf > kMaxOvf || cnt > kMaxList;
     float bd[8];
     int bi[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) { bd[t] = INF; bi[t] = 0x7fffffff; }
-    const float* x = X + static_cast<long long>(i) * K;
     auto insert = [&](float d, int id) {
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
@@ -164,60 +160,76 @@ __global__ void __launch_bounds__(32 * kRerankWarps) rerank_kernel(const float* 
             }
         }
     };
+    const float* x = X + static_cast<long long>(i) * K;
+    // work list of this warp: entry e of [survivors | codes of the overflowed groups] (or every code), e = wib mod warps
+    const int total = scan_all ? m : cnt + novf * kChunk;
+    auto code_of = [&](int e) {
+        if (scan_all) return e;
+        if (e < cnt) return s_list[e];
+        const int o = (e - cnt) / kChunk, j = s_ovf[o] * kChunk + (e - cnt) % kChunk;
+        return j < m ? j : -1;
+    };
     if ((K & 127) == 0 && K <= 1024) {
-        // query row in registers; a code row = K / 128 independent 16-byte loads per lane
-        float4 xr[8];
+        // query row in registers; a code row = K / 128 independent 16-byte loads per lane, the next row is requested
+        // before the current one is reduced
+        float4 xr[8], yr[8], yn[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q)
             if (q * 128 < K) xr[q] = __ldg(reinterpret_cast<const float4*>(x) + q * 32 + lane);
-        auto exact = [&](int j) {
-            const float4* y = reinterpret_cast<const float4*>(Y + static_cast<long long>(j) * K);
-            float4 yr[8];
+        auto load_row = [&](int j, float4 (&dst)[8]) {
+            const float4* y = reinterpret_cast<const float4*>(Y + static_cast<long long>(j < 0 ? 0 : j) * K);
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-                if (q * 128 < K) yr[q] = __ldg(y + q * 32 + lane);
-            double dot = 0.0;
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-                if (q * 128 < K) {
-                    dot += static_cast<double>(xr[q].x) * yr[q].x; dot += static_cast<double>(xr[q].y) * yr[q].y;
-                    dot += static_cast<double>(xr[q].z) * yr[q].z; dot += static_cast<double>(xr[q].w) * yr[q].w;
-                }
-            dot = warp_sum_d(dot);
-            insert((yy[j] + xi) - 2.f * static_cast<float>(dot), j);
+                if (q * 128 < K) dst[q] = __ldg(y + q * 32 + lane);
         };
-        if (scan_all) {
-            for (int j = 0; j < m; ++j) exact(j);
-        } else {
-            for (int c = 0; c < cnt; ++c) exact(s_list[wib][c]);
-            for (int o = 0; o < novf; ++o) {
-                const int j0 = s_ovf[wib][o] * kChunk;
-                for (int j = j0; j < j0 + kChunk && j < m; ++j) exact(j);
+        int e = wib;
+        int j = e < total ? code_of(e) : -1;
+        if (e < total) load_row(j, yr);
+        while (e < total) {
+            const int en = e + kRerankWarps;
+            const int jn = en < total ? code_of(en) : -1;
+            if (en < total) load_row(jn, yn);
+            if (j >= 0) {
+                double dot = 0.0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (q * 128 < K) {
+                        dot += static_cast<double>(xr[q].x) * yr[q].x; dot += static_cast<double>(xr[q].y) * yr[q].y;
+                        dot += static_cast<double>(xr[q].z) * yr[q].z; dot += static_cast<double>(xr[q].w) * yr[q].w;
+                    }
+                dot = warp_sum_d(dot);
+                insert((yy[j] + xi) - 2.f * static_cast<float>(dot), j);
             }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) yr[q] = yn[q];
+            e = en; j = jn;
         }
     } else {
-        auto exact = [&](int j) {
+        for (int e = wib; e < total; e += kRerankWarps) {
+            const int j = code_of(e);
+            if (j < 0) continue;
             const float* y = Y + static_cast<long long>(j) * K;
             double dot = 0.0;
             for (int kk = lane; kk < K; kk += 32) dot += static_cast<double>(x[kk]) * y[kk];
             dot = warp_sum_d(dot);
             insert((yy[j] + xi) - 2.f * static_cast<float>(dot), j);
-        };
-        if (scan_all) {
-            for (int j = 0; j < m; ++j) exact(j);
-        } else {
-            for (int c = 0; c < cnt; ++c) exact(s_list[wib][c]);
-            for (int o = 0; o < novf; ++o) {
-                const int j0 = s_ovf[wib][o] * kChunk;
-                for (int j = j0; j < j0 + kChunk && j < m; ++j) exact(j);
-            }
         }
     }
-    if (lane == 0)
-        for (int t = 0; t < k; ++t) {
-            out_dist[static_cast<long long>(i) * k + t] = bd[t];
-            out_idx[static_cast<long long>(i) * k + t] = bi[t] == 0x7fffffff ? -1 : bi[t] + index_offset;
-        }
+    // merge the warps' lists (every lane of a warp holds the same list)
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+        if (lane == t) { s_bd[wib][t] = bd[t]; s_bi[wib][t] = bi[t]; }
+    __syncthreads();
+    if (wib == 0) {
+        for (int w = 1; w < kRerankWarps; ++w)
+            for (int t = 0; t < 8; ++t)
+                if (s_bi[w][t] != 0x7fffffff) insert(s_bd[w][t], s_bi[w][t]);
+        if (lane == 0)
+            for (int t = 0; t < k; ++t) {
+                out_dist[static_cast<long long>(i) * k + t] = bd[t];
+                out_idx[static_cast<long long>(i) * k + t] = bi[t] == 0x7fffffff ? -1 : bi[t] + index_offset;
+            }
+    }
 }
 
 // max_j |y_j|^2 -> sqnorm[m]   (one block)
@@ -377,7 +389,7 @@ int la_nearest_codes(const float* d_X, int n, const float* d_Y, const void* d_ba
         int r = launch_tapgemm(P, sms, s);
         if (r) return la_fail_msg(r, "launch_tapgemm failed");
     }
-    rerank_kernel<<<(n + kRerankWarps - 1) / kRerankWarps, 32 * kRerankWarps, 0, s>>>(d_X, xx, d_Y, d_bank_sqnorm, n, m, K, cs, ci, L.ncand, k, index_offset, d_dist, d_idx);
+    rerank_kernel<<<n, 32 * kRerankWarps, 0, s>>>(d_X, xx, d_Y, d_bank_sqnorm, n, m, K, cs, ci, L.ncand, k, index_offset, d_dist, d_idx);
     DCU(cudaGetLastError());
     return 0;
 }

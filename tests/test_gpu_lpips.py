@@ -9,7 +9,7 @@ gradient is about sqrt(2 pdf(0) delta) -- 3e-3 for the 1.5e-5 forward error of s
 with cosine 0.99999; the loss itself agrees to 3e-6), 0.15-0.2 for bf16 operands (cosine 0.975-0.99).  The same holds
 for two fp32 runs of the reference on different devices, at their 1e-7 forward difference.  Hence: stand-alone gradient
 1e-2 + cosine 0.9999 (fp32_parity) / cosine 0.95 (bf16); loops that include the term with the author's weight of 10:
-relative L2 3e-3 (fp32_parity, measured 1.0-1.6e-3) / 1e-2 (bf16).
+relative L2 1e-3 (fp32_parity, measured 3-4e-4) / 1e-2 (bf16, measured 2.3e-3 / 4-7e-3).
 """
 import random
 
@@ -108,7 +108,7 @@ def test_augment_loop_with_all_four_terms(precision, script):
     l0 = losses[0].cpu()
     print(f'\n[4-term loop script={script} {precision}] rel_w={ew:.3e} rel_img={ei:.3e} loss0 ours: lat {l0[0]:.6f} pix {l0[1]:.6f} disc {l0[3]:.6f} '
           f'lpips {l0[4]:.6f} total {l0[2]:.6f} | oracle {orc.loss_log[0]}')
-    tol = 3e-3 if precision == 'fp32_parity' else 1e-2
+    tol = 1e-3 if precision == 'fp32_parity' else 1e-2
     assert abs(float(l0[4]) - orc.loss_log[0][4]) <= (1e-3 if precision == 'fp32_parity' else 3e-2) * abs(orc.loss_log[0][4])
     assert abs(float(l0[2]) - orc.loss_log[0][2]) <= (1e-3 if precision == 'fp32_parity' else 3e-2) * abs(orc.loss_log[0][2])
     assert ew < tol and ei < tol
