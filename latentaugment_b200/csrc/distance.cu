@@ -79,13 +79,15 @@ constexpr int kMaxOvf = 128, kMaxList = 512, kRerankWarps = 4;
 // One BLOCK of kRerankWarps warps per query (the kernel is a chain of memory latencies: with a warp per query only 7 warps
 // per SM were in flight at 1024 queries and it took 550 of the 770 us of a search): the warps split the groups of both
 // passes and the exact evaluations, and every loop keeps several independent loads in flight.
+template <int KQ>      // K / 128 (code rows as KQ independent 16-byte loads per lane), 0 = generic K
 __global__ void __launch_bounds__(32 * kRerankWarps) rerank_kernel(const float* __restrict__ X, const float* __restrict__ xx, const float* __restrict__ Y,
                                                      const float* __restrict__ yy, int n, int m, int K, const float* __restrict__ cand_score,
                                                      const int* __restrict__ cand_idx, int ncand, int k, long long index_offset,
                                                      float* out_dist, long long* out_idx) {
     __shared__ int s_list[kMaxList];
     __shared__ int s_ovf[kMaxOvf];
-    __shared__ float s_thr[kRerankWarps];
+    __shared__ float s_thr[kRerankWarps * 8];
+    static_assert(kRerankWarps * 8 <= 32, "one value per lane in the second level");
     __shared__ int s_cnt[2];                       // survivors, overflowed groups
     __shared__ float s_bd[kRerankWarps][8];
     __shared__ int s_bi[kRerankWarps][8];
@@ -98,9 +100,9 @@ __global__ void __launch_bounds__(32 * kRerankWarps) rerank_kernel(const float* 
     const int ngroups = ncand / kCand;
     constexpr int NT = 32 * kRerankWarps;
     if (tid < 2) s_cnt[tid] = 0;
-    // pass 1 (branch-free): the two smallest approximate scores of this thread's strided share of the groups; the 8th
-    // smallest of a warp's 64 values bounds the 8th smallest over ALL candidates from above (8 distinct candidates lie
-    // below it), and so does the smallest of the warps' bounds -- all that step 1 needs.
+    // pass 1 (branch-free): the two smallest approximate scores of this thread's strided share of the groups.  The 8th
+    // smallest of the threads' pairs bounds the 8th smallest over ALL candidates from above (8 distinct candidates lie at
+    // or below it), which is all that step 1 needs.
     float m1 = INF, m2 = INF;
 #pragma unroll 4
     for (int g = tid; g < ngroups; g += NT) {
@@ -112,25 +114,35 @@ __global__ void __launch_bounds__(32 * kRerankWarps) rerank_kernel(const float* 
         m1 = a1 ? a : m1;
         m2 = bq < m2 ? bq : m2;                                                     // bq >= a: it can only displace m2
     }
+    // the warp's 8 smallest values (pop the minimum of the lane heads 8 times) -> shared; the 8th smallest of the
+    // kRerankWarps * 8 values is the 8th smallest over all threads' pairs
     int head = 0;
-    float thr = INF;
     for (int r = 0; r < 8; ++r) {
         const float h = head == 0 ? m1 : (head == 1 ? m2 : INF);
         float mn = h;
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        thr = mn;
-        if (mn == INF) break;
-        const unsigned who = __ballot_sync(0xffffffffu, h == mn);
-        if (lane == __ffs(who) - 1) ++head;
+        if (lane == 0) s_thr[wib * 8 + r] = mn;
+        const unsigned who = __ballot_sync(0xffffffffu, h == mn && mn != INF);
+        if (who && lane == __ffs(who) - 1) ++head;
     }
-    if (lane == 0) s_thr[wib] = thr;
     __syncthreads();
-    thr = s_thr[0];
+    float thr = INF;
+    {
+        float v = lane < kRerankWarps * 8 ? s_thr[lane] : INF;
+        for (int r = 0; r < 8; ++r) {
+            float mn = v;
 #pragma unroll
-    for (int w = 1; w < kRerankWarps; ++w) thr = fminf(thr, s_thr[w]);
+            for (int o = 16; o >= 1; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            thr = mn;
+            if (mn == INF) break;
+            const unsigned who = __ballot_sync(0xffffffffu, v == mn);
+            if (lane == __ffs(who) - 1) v = INF;
+        }
+    }
     const float xi = xx[i];
-    const float eps = 0.015625f * sqrtf(xi) * sqrtf(yy[m]) * 1.01f;          // yy[m] = max_j |y_j|^2 (la_bank_prepare)
+    // |s^ - s| <= 2 |<x,y> - <bf16 x, bf16 y>| <= 2 (2 * 2^-9 + 2^-18) sum|x_k y_k| (+ K 2^-24 of fp32 accumulation) <= 2^-7 * 1.02 |x| |y|
+    const float eps = 0.0078125f * 1.02f * sqrtf(xi) * sqrtf(yy[m]);          // yy[m] = max_j |y_j|^2 (la_bank_prepare)
     const float cut = thr == INF ? INF : thr + 2.f * eps;
     // pass 2: overflowed groups (the last kept score is still within the cut: the group may hide more) go to the rescan
     // list, the candidates within the cut of the other groups to the survivor list (order is irrelevant: the final
@@ -169,40 +181,27 @@ __global__ void __launch_bounds__(32 * kRerankWarps) rerank_kernel(const float* 
         const int o = (e - cnt) / kChunk, j = s_ovf[o] * kChunk + (e - cnt) % kChunk;
         return j < m ? j : -1;
     };
-    if ((K & 127) == 0 && K <= 1024) {
-        // query row in registers; a code row = K / 128 independent 16-byte loads per lane, the next row is requested
-        // before the current one is reduced
-        float4 xr[8], yr[8], yn[8];
+    if constexpr (KQ > 0) {
+        // query row in registers; a code row = KQ independent 16-byte loads per lane (occupancy hides their latency:
+        // the first version also prefetched the next row and, at 196 registers, ran two blocks per SM)
+        float4 xr[KQ];
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-            if (q * 128 < K) xr[q] = __ldg(reinterpret_cast<const float4*>(x) + q * 32 + lane);
-        auto load_row = [&](int j, float4 (&dst)[8]) {
-            const float4* y = reinterpret_cast<const float4*>(Y + static_cast<long long>(j < 0 ? 0 : j) * K);
+        for (int q = 0; q < KQ; ++q) xr[q] = __ldg(reinterpret_cast<const float4*>(x) + q * 32 + lane);
+        for (int e = wib; e < total; e += kRerankWarps) {
+            const int j = code_of(e);
+            if (j < 0) continue;
+            const float4* y = reinterpret_cast<const float4*>(Y + static_cast<long long>(j) * K);
+            float4 yr[KQ];
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-                if (q * 128 < K) dst[q] = __ldg(y + q * 32 + lane);
-        };
-        int e = wib;
-        int j = e < total ? code_of(e) : -1;
-        if (e < total) load_row(j, yr);
-        while (e < total) {
-            const int en = e + kRerankWarps;
-            const int jn = en < total ? code_of(en) : -1;
-            if (en < total) load_row(jn, yn);
-            if (j >= 0) {
-                double dot = 0.0;
+            for (int q = 0; q < KQ; ++q) yr[q] = __ldg(y + q * 32 + lane);
+            double dot = 0.0;
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    if (q * 128 < K) {
-                        dot += static_cast<double>(xr[q].x) * yr[q].x; dot += static_cast<double>(xr[q].y) * yr[q].y;
-                        dot += static_cast<double>(xr[q].z) * yr[q].z; dot += static_cast<double>(xr[q].w) * yr[q].w;
-                    }
-                dot = warp_sum_d(dot);
-                insert((yy[j] + xi) - 2.f * static_cast<float>(dot), j);
+            for (int q = 0; q < KQ; ++q) {
+                dot += static_cast<double>(xr[q].x) * yr[q].x; dot += static_cast<double>(xr[q].y) * yr[q].y;
+                dot += static_cast<double>(xr[q].z) * yr[q].z; dot += static_cast<double>(xr[q].w) * yr[q].w;
             }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) yr[q] = yn[q];
-            e = en; j = jn;
+            dot = warp_sum_d(dot);
+            insert((yy[j] + xi) - 2.f * static_cast<float>(dot), j);
         }
     } else {
         for (int e = wib; e < total; e += kRerankWarps) {
@@ -389,7 +388,14 @@ int la_nearest_codes(const float* d_X, int n, const float* d_Y, const void* d_ba
         int r = launch_tapgemm(P, sms, s);
         if (r) return la_fail_msg(r, "launch_tapgemm failed");
     }
-    rerank_kernel<<<n, 32 * kRerankWarps, 0, s>>>(d_X, xx, d_Y, d_bank_sqnorm, n, m, K, cs, ci, L.ncand, k, index_offset, d_dist, d_idx);
+    const dim3 rb(32 * kRerankWarps);
+    switch (K) {
+        case 128: rerank_kernel<1><<<n, rb, 0, s>>>(d_X, xx, d_Y, d_bank_sqnorm, n, m, K, cs, ci, L.ncand, k, index_offset, d_dist, d_idx); break;
+        case 256: rerank_kernel<2><<<n, rb, 0, s>>>(d_X, xx, d_Y, d_bank_sqnorm, n, m, K, cs, ci, L.ncand, k, index_offset, d_dist, d_idx); break;
+        case 512: rerank_kernel<4><<<n, rb, 0, s>>>(d_X, xx, d_Y, d_bank_sqnorm, n, m, K, cs, ci, L.ncand, k, index_offset, d_dist, d_idx); break;
+        case 1024: rerank_kernel<8><<<n, rb, 0, s>>>(d_X, xx, d_Y, d_bank_sqnorm, n, m, K, cs, ci, L.ncand, k, index_offset, d_dist, d_idx); break;
+        default: rerank_kernel<0><<<n, rb, 0, s>>>(d_X, xx, d_Y, d_bank_sqnorm, n, m, K, cs, ci, L.ncand, k, index_offset, d_dist, d_idx); break;
+    }
     DCU(cudaGetLastError());
     return 0;
 }
