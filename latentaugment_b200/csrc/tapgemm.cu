@@ -1525,9 +1525,7 @@ int launch_bn_epi(const TapGemmParams& p, int num_sms, cudaStream_t stream) {
     static const int cost_env = getenv("LA_TILE_COST") ? atoi(getenv("LA_TILE_COST")) : 0;      // tuning switch
     if (p.cta2) {
         // CTA pairs: clusters of two CTAs (one TPC), each cluster walks a cost-balanced range of tile pairs
-        if constexpr (EPI == kEpiTopK) {
-            return static_cast<int>(cudaErrorInvalidValue);
-        } else {
+        {
             if (p.interleave) return static_cast<int>(cudaErrorInvalidValue);
             if (int r = set_smem_attr<BN, EPI, true>()) return r;
             const int clusters = (total + 1) / 2 < num_sms / 2 ? (total + 1) / 2 : num_sms / 2;
