@@ -310,7 +310,7 @@ def run_c5(args):
                 'warmup': max(args.warmup, 3), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong' if args.c5_total else 'weak',
                 'vs_baseline': None, 'dtype': 'bf16 candidates (tensor core), f32/f64 exact re-rank', 'data': 'synthetic',
                 'config': {'workload': f'c5: {codes} codes x {K} sharded over {world} GPU(s) ({per}/GPU), {nq} queries, k={k}, '
-                                       'fused GEMM + top-k + exact re-rank' + (' + NCCL all-gather + merge' if world > 1 else ''),
+                                       'GEMM with fused top-k + exact re-rank (one CUDA graph)' + (' + NCCL all-gather + merge' if world > 1 else ''),
                            'l2': f'bank shard {per * K * 2 / 2**20:.0f} MiB bf16 + {per * K * 4 / 2**20:.0f} MiB f32 per GPU vs 126 MB L2'},
                 'clocks': clk, 'indices_bit_exact_vs_pairwise': exact,
                 'e2e': {'value': nq / (e2e_ms * 1e-3), 'unit': 'queries/s', 'h2d_bytes_per_step': nq * K * 4, 'd2h_bytes_per_step': nq * k * 12},
@@ -321,7 +321,10 @@ def run_c5(args):
                              'hbm_floor_ms': per * K * 2 / (peak_bw * 1e9) * 1e3, 'whole_call_ms': ms},
                 'cpu_baseline': None}
         print(json.dumps(line), flush=True)
+    searcher.close()
+    torch.cuda.synchronize()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
