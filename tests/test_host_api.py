@@ -191,3 +191,18 @@ def test_lpips_flag_selects_taps_and_normaliser():
     import types
     crit = create_criteria(types.SimpleNamespace(w_latent=1.0, w_pix=0.0, w_lpips=1.0, w_disc=0.0))
     assert set(crit) == {'latent', 'lpips'} and isinstance(crit['lpips'], REGISTRY['lpips'])
+
+
+def test_lookahead_loop_passthrough_on_cpu():
+    """iterate() = the reference's caller loop with one batch of look-ahead; in the val phase (no augmentation, no GPU)
+    it must hand back every batch unchanged and in order, like set_input / forward / get_output."""
+    from latentaugment_b200.augments import create_augment
+    aug = create_augment(_opts(['--phase', 'val']))
+    batches = [{'A': torch.full((4, 1, 8, 8), float(i)), 'B': torch.full((4, 1, 8, 8), -float(i)), 'A_paths': [f'p{i}'] * 4, 'B_paths': [f'p{i}'] * 4}
+               for i in range(3)]
+    got = list(aug.iterate(iter(batches)))
+    assert len(got) == 3 and len(aug.stats_time) == 3
+    for (data, out), ref in zip(got, batches):
+        assert data is ref and out['A_paths'] == ref['A_paths']
+        assert torch.equal(out['A'], ref['A']) and torch.equal(out['B'], ref['B'])
+    assert list(aug.iterate(iter([]))) == []
