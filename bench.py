@@ -14,7 +14,12 @@ Workloads (BASELINE.json configs):
   c5: nearest-code sweep, 2^20 real codes sharded over the N ranks x 1024 queries, fused GEMM + top-k, exact
      re-rank, NCCL all-gather + merge inside the timed region (the one collective of the design).
   c1: SG2 128x128 1-ch, batch 4, 5 steps (the reference's CPU-runnable case; a parity-test case, not a bench line).
-One JSON line on stdout (rank 0).
+One JSON line on stdout (rank 0).  The default run (c2, bf16) also carries the other two GPU configurations as sub-objects,
+measured after the headline legs in the same launch at the same N: ``c5_sharded_search`` (2^17 codes per GPU -- at N = 8
+the 2^20-code sweep of BASELINE.json -- with the all-gather + merge in the timed region and the merged result checked against
+the gathered per-rank lists) and ``c3_strong_split`` (batch 128 split over the N ranks).  ``--no-extras`` skips them; a
+watchdog (``--extras-timeout``) prints the line without them if a leg wedges, and ``destroy_process_group`` runs under its
+own (tests/test_bench_flow.py exercises all of this on CPU with stand-ins for the CUDA-facing pieces).
 """
 import argparse
 import json
@@ -102,6 +107,152 @@ class ClockSampler:
         s = sorted(self.samples[start:]) or sorted(self.samples)
         med = s[len(s) // 2] if s else None
         return {'sm_mhz': med, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
+
+
+class LineEmitter:
+    """Rank 0 prints exactly ONE JSON line.  A watchdog may print it early -- with what is known by then -- and end the
+    process: a leg that hangs (a wedged collective, a teardown that never returns) must not lose the measured numbers."""
+
+    def __init__(self, rank, stream):
+        self.rank, self.stream, self.lock, self.done, self.line = rank, stream, threading.Lock(), False, None
+
+    def set(self, line):
+        with self.lock:
+            self.line = line
+
+    def update(self, extra):
+        with self.lock:
+            if self.line is not None and not self.done:
+                self.line.update(extra)
+
+    def emit(self):
+        with self.lock:
+            if self.done:
+                return
+            self.done = True
+            if self.rank == 0 and self.line is not None:
+                print(json.dumps(self.line), file=self.stream, flush=True)
+
+
+def start_watchdog(seconds, emitter, what):
+    """After ``seconds``: print the line as it stands (plus a note) and leave with exit code 0."""
+    def fire():
+        emitter.update({'watchdog': f'{what} did not finish within {seconds:.0f} s; the line was printed without it and the process ended'})
+        emitter.emit()
+        sys.stderr.write(f'bench.py: watchdog: {what} exceeded {seconds:.0f} s\n')
+        sys.stderr.flush()
+        os._exit(0)
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+    return t
+
+
+def cuda_device(index):
+    import torch
+    return torch.device(f'cuda:{index}')
+
+
+def teardown_group(world, limit=30.0):
+    """destroy_process_group under a watchdog (one 8-GPU run of this round hung right here)."""
+    if world <= 1:
+        return
+    import torch.distributed as dist
+    t = threading.Timer(limit, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
+    try:
+        dist.destroy_process_group()
+    finally:
+        t.cancel()
+
+
+def make_plugin(c, B, local_rank, precision, weights, micro_batches=1):
+    """The reference-facing plugin in synthetic mode (random-init generator, synthetic banks)."""
+    from latentaugment_b200.augments import create_augment
+    from latentaugment_b200.options.aug_options import AugOptions
+    w_lat, w_pix, w_lpips, w_disc = weights
+    argv = ['--aug', 'latent', '--synthetic', '--batch_size', str(B), '--gpu_ids', str(local_rank), '--gpu_ids_aug', str(local_rank),
+            '--img_resolution', str(c['img_resolution']), '--synthetic_channels', str(c['img_channels']), '--synthetic_bank', str(c['bank']),
+            '--synthetic_img_bank', str(c['img_bank']), '--synthetic_codes', str(max(4 * B, 256)), '--precision', precision,
+            '--opt_num_epochs', str(c['steps']), '--no_log',
+            '--synthetic_channel_base', str(c['channel_base']), '--synthetic_channel_max', str(c['channel_max']),
+            '--micro_batches', str(micro_batches)]
+    opt = AugOptions().parse(args={'p_thres': 0.0, 'w_lpips': w_lpips, 'w_disc': w_disc, 'w_pix': w_pix, 'w_latent': w_lat,
+                                   'init_w': 'inv', 'n_imgs': 0}, argv=argv)
+    return create_augment(opt)
+
+
+class PluginTimer:
+    """The two timed legs of a plugin workload: device-resident (``core.forward`` on codes already in HBM, CUDA events,
+    max over ranks) and end to end (``set_input / forward / get_output`` with host dicts, wall clock around a final
+    synchronize, max over ranks)."""
+
+    def __init__(self, aug, B, res, rank, world, dev):
+        self.aug, self.B, self.res, self.rank, self.world, self.dev = aug, B, res, rank, world, dev
+        self.core = aug.latent_aug.module
+        self.names = list(aug.stats_dataset_w.index.keys())
+
+    def batch_data(self, i):
+        import torch
+        B, res, names = self.B, self.res, self.names
+        fn = [names[((self.rank * 131 + i) * B + j) % len(names)] for j in range(B)]
+        img = torch.zeros([B, 1, res, res])
+        return {'A': img, 'B': img, 'A_paths': fn, 'B_paths': fn}
+
+    def barrier(self):
+        import torch
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        import torch
+        if self.world == 1:
+            return x
+        import torch.distributed as dist
+        t = torch.tensor([x], device=self.dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def resident(self, warmup, steps, clocks=None):
+        """-> (ms per step as the max over ranks, launches of this rank, the device-resident code batches); ``self.mark`` =
+        the clock sampler's position when the timed region starts"""
+        import torch
+        aug, core = self.aug, self.core
+        w_dev = [aug.sample_from_inversion(self.batch_data(i)['A_paths']).to(self.dev) for i in range(warmup + steps)]
+        for i in range(warmup):
+            core.forward(w_dev[i])
+        self.barrier()
+        self.mark = clocks.mark() if clocks is not None else 0
+        l0 = sum(e.launch_count for e in core.engines)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(steps):
+            core.forward(w_dev[warmup + i])
+        ev1.record()
+        self.barrier()
+        launches = sum(e.launch_count for e in core.engines) - l0
+        ms = self.max_over_ranks(ev0.elapsed_time(ev1)) / steps
+        return ms, launches, w_dev
+
+    def end_to_end(self, steps):
+        """-> (seconds per step as the max over ranks, the last output dict)"""
+        import torch
+        aug = self.aug
+        for i in range(3):
+            aug.set_input(self.batch_data(i)); aug.forward(); aug.get_output()
+        self.barrier()
+        t0 = time.perf_counter()
+        out = None
+        for i in range(steps):
+            aug.set_input(self.batch_data(i))
+            aug.forward()
+            out = aug.get_output()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        return self.max_over_ranks(t1 - t0) / steps, out
 
 
 def _full_cfg(cfg_name):
@@ -238,94 +389,159 @@ def gpu_reference(cfg_name, core, w0, dev, ours, reps=2):
     return out
 
 
-def run_c5(args):
-    """Config C5: queries x a row-sharded real-code bank; GEMM + fused top-k + exact re-rank + all-gather + merge."""
+def c5_leg(rank, world, dev, per, warmup, reps, scaling):
+    """Config C5 on an initialised process group (or a single process): queries x a row-sharded real-code bank; the local
+    search (query split -> GEMM + fused top-k -> exact re-rank) replayed as one CUDA graph, then -- with more than one
+    rank -- ONE NCCL all-gather of the per-rank (dist, idx) record + the merge kernel, all inside the timed region.
+    Returns the JSON object of the leg (the same on every rank)."""
     import torch
     import torch.distributed as dist
 
     from latentaugment_b200 import parallel
     from latentaugment_b200.engine import LatentBank, pairwise_sqdist
-    rank, world, lr = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
-    torch.cuda.set_device(lr)
-    dev = torch.device(f'cuda:{lr}')
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
-    per = C5['codes'] // max(world, 1) if args.c5_total else C5['codes'] // 8
     K, nq, k = C5['dim'], C5['queries'], C5['k']
     shard = torch.randn([per, K], generator=torch.Generator().manual_seed(1 + rank)).to(dev)
     X = torch.randn([nq, K], generator=torch.Generator().manual_seed(7)).to(dev)
     bank = LatentBank(shard, index_offset=rank * per)
-    searcher = parallel.ShardedNearest(bank, nq, k)          # search (+ all-gather + merge) captured once, replayed per call
+    searcher = parallel.ShardedNearest(bank, nq, k)          # local search captured once; exchange + merge follow it per call
+    try:
+        for _ in range(warmup):
+            d, i = searcher(X)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        clocks = ClockSampler(dev.index)
+        mark = clocks.mark()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            d, i = searcher(X)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1) / reps
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        clk = clocks.stop(mark)
+        # exact check of this rank's shard on 64 queries against the pairwise kernel (reference association order)
+        ds, is_ = bank.nearest(X[:64], k)
+        D = pairwise_sqdist(X[:64], shard)
+        ref_d, ref_i = torch.topk(D.t(), k, dim=1, largest=False, sorted=True)
+        exact = bool((ref_i + rank * per == is_).all()) or bool((ref_d == ds).all())
+        merged_ok = None
+        if world > 1:
+            # ... and of the merged result: every rank's local lists gathered the plain way and merged by a stable sort
+            # (rank order = index order, so ties go to the lowest index like the merge kernel's)
+            d_loc, i_loc = bank.nearest(X, k)
+            dl = [torch.empty_like(d_loc) for _ in range(world)]
+            il = [torch.empty_like(i_loc) for _ in range(world)]
+            dist.all_gather(dl, d_loc.contiguous())
+            dist.all_gather(il, i_loc.contiguous())
+            dc, ic = torch.cat(dl, dim=1), torch.cat(il, dim=1)
+            order = torch.sort(dc, dim=1, stable=True).indices[:, :k]
+            d, i = searcher(X)
+            ok = torch.tensor([int(bool((torch.gather(ic, 1, order) == i).all()) and bool((torch.gather(dc, 1, order) == d).all())), int(exact)],
+                              device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            merged_ok, exact = bool(ok[0].item()), bool(ok[1].item())
+        # host-buffer leg: queries from pinned host memory, (dist, idx) back to the host
+        Xh = X.cpu().pin_memory()
+        t0 = time.perf_counter()
+        for _ in range(20):
+            Xd = Xh.to(dev, non_blocking=True)
+            dd, ii = searcher(Xd)
+            dd.cpu(), ii.cpu()
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) / 20 * 1e3
+        if world > 1:
+            t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        graph = searcher.graph is not None
+    finally:
+        searcher.close()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except OSError:
+        pass
+    codes = world * per
+    flops = 2.0 * nq * codes * K
+    peak_tf = peaks.get('bf16_tflops', 1590.0)
+    peak_bw = peaks.get('hbm_gbs', 6650.0)
+    ach = flops / world / (ms * 1e-3) / 1e12
+    return {'metric': 'nearest-code queries/sec', 'value': nq / (ms * 1e-3), 'unit': 'queries/s', 'n_gpus': world, 'steps': reps,
+            'warmup': warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': scaling,
+            'vs_baseline': None, 'dtype': 'bf16 candidates (tensor core), f32/f64 exact re-rank', 'data': 'synthetic',
+            'config': {'workload': f'c5: {codes} codes x {K} sharded over {world} GPU(s) ({per}/GPU), {nq} queries, k={k}, '
+                                   'GEMM with fused top-k + exact re-rank (one CUDA graph)' + (' + NCCL all-gather + merge' if world > 1 else ''),
+                       'l2': f'bank shard {per * K * 2 / 2**20:.0f} MiB bf16 + {per * K * 4 / 2**20:.0f} MiB f32 per GPU vs 126 MB L2'},
+            'clocks': clk, 'indices_bit_exact_vs_pairwise': exact, 'merged_equals_gathered_lists': merged_ok,
+            'e2e': {'value': nq / (e2e_ms * 1e-3), 'unit': 'queries/s', 'h2d_bytes_per_step': nq * K * 4, 'd2h_bytes_per_step': nq * k * 12},
+            'gpu_launches': int(reps * (4 if world > 1 else 3)), 'graph_captured': graph,
+            'roofline': {'bound': 'tensor', 'kernel': 'tapgemm_kernel<EPI=TopK> (query x bank GEMM + fused per-chunk top-2)',
+                         'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'traffic': None,
+                         'peak_source': 'MEASURED_PEAKS.json bf16_tflops (burst)' if peaks else 'fallback 1.59 PFLOP/s',
+                         'note': 'achieved = 2 * queries * codes * K per GPU / the WHOLE search time (GEMM + re-rank + exchange), so it '
+                                 'understates the GEMM kernel alone',
+                         'hbm_floor_ms': (per * K * 2) / (peak_bw * 1e9) * 1e3},
+            'cpu_baseline': None}
 
-    def search():
-        return searcher(X)
-    for _ in range(max(args.warmup, 3)):
-        d, i = search()
-    torch.cuda.synchronize()
+
+def run_c5(args):
+    """``--config c5``: the nearest-code sweep as its own bench line."""
+    import torch
+    import torch.distributed as dist
+    rank, world, lr = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(lr)
+    dev = cuda_device(lr)
+    sys.stdout.flush()
+    json_fd = os.dup(1)               # the NCCL banner goes to fd 1: keep stdout for the one JSON line
+    os.dup2(2, 1)
+    emitter = LineEmitter(rank, os.fdopen(json_fd, 'w'))
     if world > 1:
-        dist.barrier()
-    clocks = ClockSampler(lr)
-    mark = clocks.mark()
-    reps = max(args.steps, 1) * 20
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        d, i = search()
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = e0.elapsed_time(e1) / reps
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    clk = clocks.stop(mark)
-    # exact check of this rank's shard on 64 queries against the pairwise kernel (reference association order)
-    ds, is_ = bank.nearest(X[:64], k)
-    D = pairwise_sqdist(X[:64], shard)
-    ref_d, ref_i = torch.topk(D.t(), k, dim=1, largest=False, sorted=True)
-    exact = bool((ref_i + rank * per == is_).all()) or bool((ref_d == ds).all())
-    # host-buffer leg: queries from pinned host memory, (dist, idx) back to the host
-    Xh = X.cpu().pin_memory()
-    t0 = time.perf_counter()
-    for _ in range(20):
-        Xd = Xh.to(dev, non_blocking=True)
-        dd, ii = searcher(Xd)
-        dd.cpu(), ii.cpu()
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) / 20 * 1e3
-    if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-        except OSError:
-            pass
-        codes = world * per
-        flops = 2.0 * nq * codes * K
-        peak_tf = peaks.get('bf16_tflops', 1590.0)
-        peak_bw = peaks.get('hbm_gbs', 6650.0)
-        ach = flops / world / (ms * 1e-3) / 1e12
-        line = {'metric': 'nearest-code queries/sec', 'value': nq / (ms * 1e-3), 'unit': 'queries/s', 'n_gpus': world, 'steps': reps,
-                'warmup': max(args.warmup, 3), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong' if args.c5_total else 'weak',
-                'vs_baseline': None, 'dtype': 'bf16 candidates (tensor core), f32/f64 exact re-rank', 'data': 'synthetic',
-                'config': {'workload': f'c5: {codes} codes x {K} sharded over {world} GPU(s) ({per}/GPU), {nq} queries, k={k}, '
-                                       'GEMM with fused top-k + exact re-rank (one CUDA graph)' + (' + NCCL all-gather + merge' if world > 1 else ''),
-                           'l2': f'bank shard {per * K * 2 / 2**20:.0f} MiB bf16 + {per * K * 4 / 2**20:.0f} MiB f32 per GPU vs 126 MB L2'},
-                'clocks': clk, 'indices_bit_exact_vs_pairwise': exact,
-                'e2e': {'value': nq / (e2e_ms * 1e-3), 'unit': 'queries/s', 'h2d_bytes_per_step': nq * K * 4, 'd2h_bytes_per_step': nq * k * 12},
-                'gpu_launches': int(reps * (5 if world > 1 else 4)), 'graph_captured': searcher.graph is not None,
-                'roofline': {'bound': 'tensor', 'kernel': 'tapgemm_kernel<EPI=TopK> (query x bank GEMM + fused per-tile top-k)',
-                             'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'traffic': None,
-                             'peak_source': 'MEASURED_PEAKS.json bf16_tflops (burst)' if peaks else 'fallback 1.59 PFLOP/s',
-                             'hbm_floor_ms': per * K * 2 / (peak_bw * 1e9) * 1e3, 'whole_call_ms': ms},
-                'cpu_baseline': None}
-        print(json.dumps(line), flush=True)
-    searcher.close()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        dist.init_process_group('nccl', device_id=dev)
+    per = C5['codes'] // max(world, 1) if args.c5_total else C5['codes'] // 8
+    wd = start_watchdog(300.0, emitter, 'the c5 sweep')
+    line = c5_leg(rank, world, dev, per, max(args.warmup, 3), max(args.steps, 1) * 20, 'strong' if args.c5_total else 'weak')
+    wd.cancel()
+    emitter.set(line)
+    emitter.emit()
+    teardown_group(world, args.teardown_timeout)
+
+
+def c3_leg(args, rank, local_rank, world, dev):
+    """Config C3 on an initialised process group: SG2 512x512, batch 128 SPLIT over the ranks (strong scaling), through the
+    plugin like the headline workload: device-resident and end-to-end numbers."""
+    import torch
+    c = _full_cfg('c3')
+    B = c['batch'] // world
+    res, C, steps = c['img_resolution'], c['img_channels'], c['steps']
+    aug = make_plugin(c, B, local_rank, 'bf16', (1.0, 1.0, 0.0, 0.0))
+    pt = PluginTimer(aug, B, res, rank, world, dev)
+    clocks = ClockSampler(local_rank)
+    ms, launches, _ = pt.resident(3, 3, clocks)
+    e2e_s, out = pt.end_to_end(3)
+    clk = clocks.stop(pt.mark)
+    ok = out['A'].shape == (B, 1, res, res) and bool(torch.isfinite(out['A']).all())
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except OSError:
+        pass
+    peak_sust = peaks.get('bf16_tflops_sustained', 1400.0)
+    fsyn = f_syn(res, C, channel_base=c['channel_base'], channel_max=c['channel_max'])
+    value = world * B / (ms * 1e-3)
+    del pt, aug
+    torch.cuda.empty_cache()
+    return {'metric': 'augmented images/sec', 'value': value, 'unit': 'img/s', 'n_gpus': world, 'steps': 3, 'warmup': 3, 'ms_per_step': ms,
+            'scaling': 'strong', 'config': {'workload': workload_name('c3', c, B), 'parallelism': f'batch {c["batch"]} split over {world} rank(s), no data-path collective'},
+            'e2e': {'value': world * B / e2e_s, 'unit': 'img/s', 'h2d_bytes_per_step': B * 512 * 4, 'd2h_bytes_per_step': B * C * res * res * 4},
+            'gpu_launches': int(launches), 'clocks': clk, 'output_finite': ok,
+            'whole_path_frac': (value / world) * (2 * steps + 1) * fsyn / (peak_sust * 1e12)}
 
 
 def main():
@@ -346,6 +562,9 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-gpu-reference', action='store_true')
     ap.add_argument('--no-fp32-parity', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='default c2 run only: skip the C5 (sharded search) and C3 (512x512 split) legs')
+    ap.add_argument('--extras-timeout', type=float, default=240.0, help='watchdog of those legs, seconds')
+    ap.add_argument('--teardown-timeout', type=float, default=30.0, help='watchdog of destroy_process_group, seconds')
     ap.add_argument('--profile', action='store_true', help='short run for ncu: skips the e2e leg, the baselines and the per-GEMM timing')
     ap.add_argument('--layers-out', default='', help='write the per-layer tap-GEMM timing table (JSON) here')
     args = ap.parse_args()
@@ -357,16 +576,21 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from latentaugment_b200.augments import create_augment
-    from latentaugment_b200.options.aug_options import AugOptions
-
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if args.warmup < 3:
         args.warmup = 3
     torch.cuda.set_device(local_rank)
-    dev = torch.device(f'cuda:{local_rank}')
+    dev = cuda_device(local_rank)
+    # stdout carries exactly ONE JSON line: everything else (plugin banners, the NCCL version line that
+    # the C library writes to fd 1) goes to stderr -- at the file-descriptor level.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = os.fdopen(json_fd, 'w')
+    sys.stdout = sys.stderr
+    emitter = LineEmitter(rank, real_stdout)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     c = _full_cfg(args.config)
@@ -378,84 +602,28 @@ def main():
         w_lpips, w_pix, w_lat, w_disc = 10.0, 0.1, 0.001, 0.01
 
     # ---- the reference-facing plugin, synthetic mode (random-init generator, synthetic banks)
-    argv = ['--aug', 'latent', '--synthetic', '--batch_size', str(B), '--gpu_ids', str(local_rank), '--gpu_ids_aug', str(local_rank),
-            '--img_resolution', str(res), '--synthetic_channels', str(C), '--synthetic_bank', str(c['bank']),
-            '--synthetic_img_bank', str(c['img_bank']), '--synthetic_codes', str(max(4 * B, 256)), '--precision', args.precision,
-            '--opt_num_epochs', str(steps), '--no_log',
-            '--synthetic_channel_base', str(c['channel_base']), '--synthetic_channel_max', str(c['channel_max']),
-            '--micro_batches', str(args.micro_batches)]
-    # stdout carries exactly ONE JSON line: everything else (plugin banners, the NCCL version line that
-    # the C library writes to fd 1) goes to stderr -- at the file-descriptor level.
-    sys.stdout.flush()
-    json_fd = os.dup(1)
-    os.dup2(2, 1)
-    real_stdout = os.fdopen(json_fd, 'w')
-    sys.stdout = sys.stderr
-    opt = AugOptions().parse(args={'p_thres': 0.0, 'w_lpips': w_lpips, 'w_disc': w_disc, 'w_pix': w_pix, 'w_latent': w_lat,
-                                   'init_w': 'inv', 'n_imgs': 0}, argv=argv)
-    aug = create_augment(opt)
+    aug = make_plugin(c, B, local_rank, args.precision, (w_lat, w_pix, w_lpips, w_disc), args.micro_batches)
     core = aug.latent_aug.module
     eng = core.engines[0]
-    names = list(aug.stats_dataset_w.index.keys())
-
-    def batch_data(i):
-        fn = [names[((rank * 131 + i) * B + j) % len(names)] for j in range(B)]
-        img = torch.zeros([B, 1, res, res])
-        return {'A': img, 'B': img, 'A_paths': fn, 'B_paths': fn}
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    pt = PluginTimer(aug, B, res, rank, world, dev)
 
     # ---- kernel-resident metric: inputs already in HBM, no host copies in the timed region
-    w_dev = [aug.sample_from_inversion(batch_data(i)['A_paths']).to(dev) for i in range(args.warmup + args.steps)]
-    for i in range(args.warmup):
-        core.forward(w_dev[i])
     clocks = ClockSampler(local_rank)
-    barrier()
-    mark = clocks.mark()
-    l0 = sum(e.launch_count for e in core.engines)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for i in range(args.steps):
-        core.forward(w_dev[args.warmup + i])
-    ev1.record()
-    barrier()
-    launches = sum(e.launch_count for e in core.engines) - l0
-    ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    ms, launches, w_dev = pt.resident(args.warmup, args.steps, clocks)
+    mark = pt.mark
     value = world * B / (ms * 1e-3)
 
     if args.profile:
         clocks.stop(mark)
-        if rank == 0:
-            print(json.dumps({'metric': 'augmented images/sec', 'value': value, 'unit': 'img/s', 'ms_per_step': ms,
-                              'gpu_launches': int(launches), 'note': 'profile mode (no e2e / roofline / baseline legs)'}),
-                  file=real_stdout, flush=True)
+        emitter.set({'metric': 'augmented images/sec', 'value': value, 'unit': 'img/s', 'ms_per_step': ms,
+                     'gpu_launches': int(launches), 'note': 'profile mode (no e2e / roofline / baseline legs)'})
+        emitter.emit()
         return
 
     # ---- end to end through the plugin API: host dict in, host dict out (the output of batch t is fetched while
     # batch t+1 runs: double-buffered pinned outputs, latent_aug.py get_output)
     time.sleep(3.0)      # both legs start from a comparable power / thermal state (the kernels are power-capped)
-    for i in range(3):
-        aug.set_input(batch_data(i)); aug.forward(); aug.get_output()
-    barrier()
-    t0 = time.perf_counter()
-    out = None
-    for i in range(args.steps):
-        aug.set_input(batch_data(i))
-        aug.forward()
-        out = aug.get_output()
-    torch.cuda.synchronize()
-    t1 = time.perf_counter()
-    e2e_s = max_over_ranks(t1 - t0) / args.steps
+    e2e_s, out = pt.end_to_end(args.steps)
     clk = clocks.stop(mark)
     e2e = {'value': world * B / e2e_s, 'unit': 'img/s', 'h2d_bytes_per_step': B * eng.w_dim * 4,
            'd2h_bytes_per_step': B * C * res * res * 4}
@@ -546,10 +714,26 @@ def main():
                            + ', no data-path collective' + (f'; {args.micro_batches} concurrent micro-batches per GPU' if args.micro_batches > 1 else '')},
                 'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cb}
         line.update(extra)
-    if rank == 0:
-        print(json.dumps(line), file=real_stdout, flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    emitter.set(line)
+    # ---- the other two GPU configurations of BASELINE.json in the same (driver-launched) run: C5 = the sharded nearest-code
+    # sweep with the design's ONE collective, C3 = 512x512 with batch 128 split over the ranks.  All collectives of the
+    # headline measurement are complete by now; a watchdog prints the line without these legs if one of them wedges.
+    headline = (args.config == 'c2' and args.precision == 'bf16' and w_lpips == 0 and w_disc == 0 and not args.author_weights
+                and not args.batch and args.micro_batches == 1)
+    if headline and not args.no_extras:
+        wd = start_watchdog(args.extras_timeout, emitter, 'the C5 / C3 legs')
+        extras = {}
+        for key, leg in (('c5_sharded_search', lambda: c5_leg(rank, world, dev, C5['codes'] // 8, 3, 40, 'weak')),
+                         ('c3_strong_split', lambda: c3_leg(args, rank, local_rank, world, dev))):
+            try:
+                extras[key] = leg()
+            except Exception as exc:      # noqa: BLE001 -- a failing extra leg must not lose the headline line
+                extras[key] = {'error': f'{type(exc).__name__}: {str(exc)[:300]}'}
+                break                     # the ranks may be out of step now: no further collective
+        wd.cancel()
+        emitter.update(extras)
+    emitter.emit()
+    teardown_group(world, args.teardown_timeout)
 
 
 if __name__ == '__main__':
