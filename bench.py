@@ -732,6 +732,12 @@ def main():
                 break                     # the ranks may be out of step now: no further collective
         wd.cancel()
         emitter.update(extras)
+        if any('error' in v for v in extras.values()):
+            emitter.emit()                # the ranks may be out of step (or the context poisoned): no graceful teardown
+            sys.stderr.write(f'bench.py: extra leg failed: {extras}\n')
+            sys.stderr.flush()
+            real_stdout.flush()
+            os._exit(0)
     emitter.emit()
     teardown_group(world, args.teardown_timeout)
 
