@@ -17,7 +17,8 @@ Workloads (BASELINE.json configs):
 One JSON line on stdout (rank 0).  The default run (c2, bf16) also carries the other two GPU configurations as sub-objects,
 measured after the headline legs in the same launch at the same N: ``c5_sharded_search`` (2^17 codes per GPU -- at N = 8
 the 2^20-code sweep of BASELINE.json -- with the all-gather + merge in the timed region and the merged result checked against
-the gathered per-rank lists) and ``c3_strong_split`` (batch 128 split over the N ranks).  ``--no-extras`` skips them; a
+the gathered per-rank lists), ``c3_strong_split`` (batch 128 split over the N ranks) and, at N = 1, ``four_terms_author_weights``
+(all four criteria at the author's weights).  ``--no-extras`` skips them; a
 watchdog (``--extras-timeout``) prints the line without them if a leg wedges, and ``destroy_process_group`` runs under its
 own (tests/test_bench_flow.py exercises all of this on CPU with stand-ins for the CUDA-facing pieces).
 """
@@ -513,6 +514,26 @@ def run_c5(args):
     teardown_group(world, args.teardown_timeout)
 
 
+def four_term_leg(rank, local_rank, world, dev):
+    """The headline workload with ALL FOUR criteria at the author's weights (backbone_latentaug.py:46-56: w_lpips 10, w_pix 0.1,
+    w_latent 0.001, w_disc 0.01): the discriminator and VGG16 forward / backward run inside every Adam step."""
+    import torch
+    c = _full_cfg('c2')
+    B, res, C, steps = c['batch'], c['img_resolution'], c['img_channels'], c['steps']
+    aug = make_plugin(c, B, local_rank, 'bf16', (0.001, 0.1, 10.0, 0.01))
+    pt = PluginTimer(aug, B, res, rank, world, dev)
+    ms, launches, _ = pt.resident(3, 3)
+    e2e_s, out = pt.end_to_end(3)
+    ok = out['A'].shape == (B, 1, res, res) and bool(torch.isfinite(out['A']).all())
+    del pt, aug
+    torch.cuda.empty_cache()
+    return {'metric': 'augmented images/sec', 'value': world * B / (ms * 1e-3), 'unit': 'img/s', 'n_gpus': world, 'steps': 3, 'warmup': 3,
+            'ms_per_step': ms, 'config': {'workload': workload_name('c2', c, B).replace(
+                'w_latent=w_pix=1', 'w_lpips=10 (VGG16 perceptual term), w_pix=0.1, w_latent=0.001, w_disc=0.01 (StyleGAN2 discriminator term)')},
+            'e2e': {'value': world * B / e2e_s, 'unit': 'img/s', 'h2d_bytes_per_step': B * 512 * 4, 'd2h_bytes_per_step': B * C * res * res * 4},
+            'gpu_launches': int(launches), 'output_finite': ok}
+
+
 def c3_leg(args, rank, local_rank, world, dev):
     """Config C3 on an initialised process group: SG2 512x512, batch 128 SPLIT over the ranks (strong scaling), through the
     plugin like the headline workload: device-resident and end-to-end numbers."""
@@ -723,8 +744,11 @@ def main():
     if headline and not args.no_extras:
         wd = start_watchdog(args.extras_timeout, emitter, 'the C5 / C3 legs')
         extras = {}
-        for key, leg in (('c5_sharded_search', lambda: c5_leg(rank, world, dev, C5['codes'] // 8, 3, 40, 'weak')),
-                         ('c3_strong_split', lambda: c3_leg(args, rank, local_rank, world, dev))):
+        legs = [('c5_sharded_search', lambda: c5_leg(rank, world, dev, C5['codes'] // 8, 3, 40, 'weak')),
+                ('c3_strong_split', lambda: c3_leg(args, rank, local_rank, world, dev))]
+        if world == 1:
+            legs.append(('four_terms_author_weights', lambda: four_term_leg(rank, local_rank, world, dev)))
+        for key, leg in legs:
             try:
                 extras[key] = leg()
             except Exception as exc:      # noqa: BLE001 -- a failing extra leg must not lose the headline line

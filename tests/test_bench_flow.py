@@ -44,6 +44,7 @@ def test_one_line_with_both_extra_legs_single_process():
     assert 'error' not in c5 and 'error' not in c3, (c5, c3)
     assert c5['indices_bit_exact_vs_pairwise'] is True and c5['merged_equals_gathered_lists'] is None and c5['gpu_launches'] == 3 * c5['steps']
     assert c3['scaling'] == 'strong' and c3['output_finite'] is True
+    assert line['four_terms_author_weights']['output_finite'] is True and 'w_lpips=10' in line['four_terms_author_weights']['config']['workload']
     rc, lines, _, err = _run(1, ['--no-extras'])
     assert rc == 0 and len(lines) == 1 and 'c5_sharded_search' not in json.loads(lines[0]), err[-2000:]
 
@@ -55,7 +56,7 @@ def test_two_ranks_gloo_merge_check_and_teardown():
     c5, c3 = line['c5_sharded_search'], line['c3_strong_split']
     assert line['n_gpus'] == 2 and c5['n_gpus'] == 2 and c5['merged_equals_gathered_lists'] is True and c5['indices_bit_exact_vs_pairwise'] is True
     assert c5['gpu_launches'] == 4 * c5['steps'] and 'NCCL all-gather' in c5['config']['workload']
-    assert c3['n_gpus'] == 2 and 'split over 2 rank(s)' in c3['config']['parallelism']
+    assert c3['n_gpus'] == 2 and 'split over 2 rank(s)' in c3['config']['parallelism'] and 'four_terms_author_weights' not in line
 
 
 def test_hung_extra_leg_keeps_the_headline_line():
