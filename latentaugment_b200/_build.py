@@ -110,7 +110,7 @@ def build(force=False, verbose=False):
         if os.path.exists(STAMP):
             os.remove(STAMP)
         raise RuntimeError('\n'.join(failed))
-    cmd = [_nvcc(), '-shared', '-o', LIB] + objs
+    cmd = [_nvcc(), '-shared'] + NVCC_FLAGS[:2] + ['-o', LIB] + objs      # (-gencode here too: no default-arch stub cubin in the library)
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f'link failed:\n{r.stdout}')
