@@ -63,8 +63,8 @@ __global__ void pairwise_kernel(const float* __restrict__ X, int n, const float*
     if (lane == 0) D[pair] = (static_cast<float>(yy) + static_cast<float>(xx)) - 2.f * static_cast<float>(yx);
 }
 
-// Exact re-rank, warp per query.  The tap-GEMM (ONE bf16 pass) left, per (query, 32-code chunk = "group"), the 2
-// smallest approximate scores s^ = |y|^2 - 2 <bf16(x), bf16(y)> in ascending order.  With eps = 2^-6 |x| max_j|y_j|
+// Exact re-rank, one block of kRerankWarps warps per query.  The tap-GEMM (ONE bf16 pass) left, per (query, 32-code chunk = "group"), the 2
+// smallest approximate scores s^ = |y|^2 - 2 <bf16(x), bf16(y)> in ascending order.  With eps ~ 2^-7 * 1.02 |x| max_j|y_j|
 // (>= the error of s^: two bf16 roundings of relative size 2^-9 each on every product, doubled by the factor -2, plus
 // the fp32 accumulation error, Cauchy-Schwarz on sum |x_k y_k|) the exact k best are found as follows:
 //   1. thr = the 8th smallest of the lanes' two best s^ (8 distinct candidates have s^ <= thr, so the k-th smallest EXACT
@@ -142,8 +142,11 @@ __global__ void __launch_bounds__(32 * kRerankWarps) rerank_kernel(const float* 
         }
     }
     const float xi = xx[i];
-    // |s^ - s| <= 2 |<x,y> - <bf16 x, bf16 y>| <= 2 (2 * 2^-9 + 2^-18) sum|x_k y_k| (+ K 2^-24 of fp32 accumulation) <= 2^-7 * 1.02 |x| |y|
-    const float eps = 0.0078125f * 1.02f * sqrtf(xi) * sqrtf(yy[m]);          // yy[m] = max_j |y_j|^2 (la_bank_prepare)
+    // |s^ - s| <= 2 |<x,y> - <bf16 x, bf16 y>| <= 2 (2 * 2^-9 + 2^-18) sum|x_k y_k| + 2 K 2^-24 sum|x_k y_k| (fp32 accumulation,
+    // worst case) <= 2^-7 (1.001 + K 2^-16) |x| |y| -- 1.02 covers K <= 1024, the K term takes over beyond; the last term
+    // covers the roundings of the fp32 distance the final order is defined on (|y|^2, |x|^2, their sum, the result: 4 ulps)
+    const float slack = fmaxf(1.02f, 1.004f + static_cast<float>(K) * 1.5259e-5f);
+    const float eps = 0.0078125f * slack * sqrtf(xi) * sqrtf(yy[m]) + 4.8e-7f * (xi + yy[m]);   // yy[m] = max_j |y_j|^2 (la_bank_prepare)
     const float cut = thr == INF ? INF : thr + 2.f * eps;
     // pass 2: overflowed groups (the last kept score is still within the cut: the group may hide more) go to the rescan
     // list, the candidates within the cut of the other groups to the survivor list (order is irrelevant: the final
