@@ -1,10 +1,10 @@
-"""``AugOptions`` (reference ``options/aug_options.py:4-17``)."""
+"""``AugOptions`` (reference ``options/aug_options.py:4-17``): the shared flags of ``BaseOptions`` plus ``--phase``."""
 from .base_options import BaseOptions
 
 
 class AugOptions(BaseOptions):
     def initialize(self, parser):
-        parser = BaseOptions.initialize(self, parser)
-        parser.add_argument('--phase', type=str, default='train', help='train, val, test, etc')
+        parser = super().initialize(parser)
+        parser.add_argument('--phase', default='train', type=str, help="'train', 'val' or 'test': which split of the inverted codes is read")
         self.isTrain = True
         return parser
