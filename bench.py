@@ -315,7 +315,9 @@ def run_reference(args):
     if rank != 0:
         return
     name = args.config if args.config in CONFIGS else 'c2'
-    c = CONFIGS[name]
+    c = _full_cfg(name)
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    per_gpu = args.batch or (c['batch'] // world if c.get('strong') else c['batch'])
     vals = []
     for _ in range(max(args.warmup - 2, 0)):      # each call already does its own untimed warm-up pass
         cpu_baseline(name)
@@ -330,9 +332,23 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': 'augmented images/sec', 'value': v, 'unit': 'img/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * wall / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': workload_name(name, c, c['batch'])}, 'cpu_baseline': cb,
+            'config': config_object(name, c, per_gpu, world, args.precision), 'cpu_baseline': cb,
             'e2e': {'value': v, 'unit': 'img/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
     print(json.dumps(line))
+
+
+def config_object(name, c, per_gpu, world, precision, weights=(1.0, 1.0, 0.0, 0.0), micro_batches=1):
+    """The ``config`` object of the line: the same for the product arm and for ``--impl reference`` given the same flags
+    (the reference arm runs "on your arm's config")."""
+    w_lat, w_pix, w_lpips, w_disc = weights
+    terms = f'w_latent={w_lat:g}, w_pix={w_pix:g}' + (f', w_lpips={w_lpips:g} (VGG16 perceptual term)' if w_lpips > 0 else '') + \
+        (f', w_disc={w_disc:g} (StyleGAN2 discriminator term)' if w_disc > 0 else '')
+    strong = bool(c.get('strong'))
+    return {'workload': workload_name(name, c, per_gpu).replace('w_latent=w_pix=1', terms),
+            'precision': precision,
+            'l2': 'working set >> L2: ~2 GB of activations written and re-read per Adam step',
+            'parallelism': (f'batch {c["batch"]} split over {world} rank(s)' if strong else f'batch-sharded x{world}')
+            + ', no data-path collective' + (f'; {micro_batches} concurrent micro-batches per GPU' if micro_batches > 1 else '')}
 
 
 def workload_name(name, c, per_gpu):
@@ -721,18 +737,12 @@ def main():
         cb = None
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_baseline(args.config)
-        terms = f'w_latent={w_lat:g}, w_pix={w_pix:g}' + (f', w_lpips={w_lpips:g} (VGG16 perceptual term)' if w_lpips > 0 else '') + \
-            (f', w_disc={w_disc:g} (StyleGAN2 discriminator term)' if w_disc > 0 else '')
         line = {'metric': 'augmented images/sec', 'value': value, 'unit': 'img/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong' if strong else 'weak',
                 'vs_baseline': None,
                 'dtype': 'bf16 operands, f32 accumulate' if args.precision == 'bf16' else 'split-bf16 (hi+lo) operands, f32 accumulate',
                 'data': 'synthetic',
-                'config': {'workload': workload_name(args.config, c, B).replace('w_latent=w_pix=1', terms),
-                           'precision': args.precision,
-                           'l2': 'working set >> L2: ~2 GB of activations written and re-read per Adam step',
-                           'parallelism': (f'batch {c["batch"]} split over {world} rank(s)' if strong else f'batch-sharded x{world}')
-                           + ', no data-path collective' + (f'; {args.micro_batches} concurrent micro-batches per GPU' if args.micro_batches > 1 else '')},
+                'config': config_object(args.config, c, B, world, args.precision, (w_lat, w_pix, w_lpips, w_disc), args.micro_batches),
                 'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cb}
         line.update(extra)
     emitter.set(line)
