@@ -144,3 +144,33 @@ def test_lpips_oracle_matches_reference_golden(golden):
             for k, t in enumerate(f):
                 s, a = g['feat_sums'][c][k]
                 assert abs(float(t.sum()) - s) < 1e-3 * a and abs(float(t.abs().sum()) - a) < 1e-4 * a
+
+
+def test_four_term_loop_matches_reference_golden(golden):
+    """The oracle loop with all four criteria against tests/golden/loop_four_terms.pt = the REFERENCE's own
+    ``LatentAug.forward`` (crop draws, ``calc_loss_lpips_torchscript`` on LPIPS feature vectors, ``calc_loss_disc``, the sign
+    combination, Adam) run by oracle/make_golden_four_terms.py; also pins the product's host-side bank-crop order."""
+    from latentaugment_b200.augments.utils.util_latent_aug import feature_bank_crops
+    from oracle import lpips as olp
+    from oracle import sg2_disc
+    g = golden('loop_four_terms.pt')
+    cfg, wts = g['cfg'], g['weights']
+    wl = synthetic.make_workload(dict(cfg), noise_strength=0.1)
+    D = sg2_disc.make_discriminator(img_resolution=cfg['img_resolution'], img_channels=cfg['img_channels'],
+                                    channel_base=cfg['channel_base'], channel_max=cfg['channel_max'])
+    taps = tuple(g['taps'])
+    st = olp.random_vgg_state(g['vgg_seed'], taps)
+    random.seed(g['crop_seed'])
+    crops = feature_bank_crops(wl['X'], cfg['img_resolution'], 64)
+    assert torch.equal(crops, g['bank_crops']), 'bank windows are drawn in another order than the reference draws them'
+    lp = dict(state=st, taps=taps, script=True, bank_feats=olp.bank_features(st, crops, taps))
+    orc = ola.LatentAugOracle(wl['G'], wl['W'], wl['X'], num_epochs=cfg['steps'], D=D, lpips=lp, fused=True, **wts)
+    random.seed(g['loop_seed'])
+    torch.manual_seed(1234)
+    img, w_aug = orc.forward(wl['w0'].clone())
+    ref = g['losses']
+    for t, (l_lat, l_pix, _, l_disc, l_lpips) in enumerate(orc.loss_log):
+        for ours, theirs, tol in ((l_lat, ref[t, 0], 1e-5), (l_pix, ref[t, 1], 1e-4), (l_disc, ref[t, 2], 1e-4), (l_lpips, ref[t, 3], 1e-5)):
+            assert abs(ours - float(theirs)) <= tol * abs(float(theirs)), (t, ours, float(theirs))
+    assert rel_l2(w_aug[:, 0], g['w_aug']) < 1e-5, rel_l2(w_aug[:, 0], g['w_aug'])
+    assert rel_l2(img, g['img']) < 2e-4, rel_l2(img, g['img'])
