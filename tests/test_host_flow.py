@@ -1,0 +1,151 @@
+"""CPU tests of the plugin's HOST logic above the engine (``LatentAug`` / ``LatentAugment``): construction in synthetic
+mode with all four criteria attached, sharding of a batch over ``--gpu_ids_aug 0,1`` x ``--micro_batches`` and the order the
+parts come back in, the term-weight rescaling of micro-batches, the ``rand_aug`` path, the first-call loss log, the
+look-ahead loop.  The CUDA engine is replaced by a recording stand-in (the engine itself is what the ``-m gpu`` tests
+check); nothing here computes on a GPU."""
+import json
+import os
+
+import pytest
+import torch
+
+
+class RecordingEngine:
+    """Stands in for ``engine.SynthesisEngine``: same constructor and method signatures, arithmetic that makes the
+    sample order visible (image i is filled with ``w0[i, 0, 0]``, ``w_aug = w0 + 1``)."""
+    instances = []
+
+    def __init__(self, state, *, img_resolution, img_channels, w_dim=512, z_dim=512, conv_clamp=256.0, batch, precision='fp32_parity',
+                 device=None, mapping_lr_multiplier=0.01):
+        self.res, self.C, self.w_dim, self.z_dim, self.batch, self.precision = img_resolution, img_channels, w_dim, z_dim, batch, precision
+        self.requested_device = device
+        self.device = torch.device('cpu')
+        self.num_ws = 2 * (img_resolution.bit_length() - 1) - 2
+        self.calls, self.launch_count = [], 0
+        RecordingEngine.instances.append(self)
+
+    def set_latent_bank(self, W):
+        self.calls.append(('latent_bank', tuple(W.shape)))
+
+    def set_image_bank(self, X):
+        self.calls.append(('image_bank', tuple(X.shape)))
+
+    def set_discriminator(self, state, channels=None, conv_clamp=256.0, mbstd_group_size=4):
+        self.calls.append(('disc', len(state)))
+
+    def set_lpips(self, state, taps=(16, 23, 30), crop_size=64, **kw):
+        self.calls.append(('lpips', tuple(taps), crop_size))
+
+    def set_feature_bank(self, crops):
+        self.calls.append(('feature_bank', tuple(crops.shape)))
+
+    def mapping(self, z, truncation_psi=1.0):
+        return (z[:, :1, None] * truncation_psi).expand(z.shape[0], self.num_ws, self.w_dim).contiguous()
+
+    def synthesis(self, ws, noise_mode='random', noise=None):
+        self.calls.append(('synthesis', noise_mode, ws.shape[0]))
+        return ws[:, 0, 0].reshape(-1, 1, 1, 1).expand(ws.shape[0], self.C, self.res, self.res).contiguous()
+
+    def augment(self, w0, *, num_steps=10, lr=0.01, return_losses=False, **kw):
+        assert w0.shape == (self.batch, 1, self.w_dim)
+        self.calls.append(('augment', dict(kw, num_steps=num_steps, lr=lr)))
+        img = w0[:, 0, 0].reshape(-1, 1, 1, 1).expand(self.batch, self.C, self.res, self.res).contiguous()
+        out = (img, w0[:, 0] + 1.0)
+        if return_losses:
+            out += (torch.arange(num_steps * 5, dtype=torch.float32).reshape(num_steps, 5),)
+        return out
+
+
+@pytest.fixture
+def fake_engine(monkeypatch):
+    from latentaugment_b200 import engine
+    RecordingEngine.instances = []
+    monkeypatch.setattr(engine, 'SynthesisEngine', RecordingEngine)
+    return RecordingEngine
+
+
+def _make(argv, args, tmp_path=None):
+    from latentaugment_b200.augments import create_augment
+    from latentaugment_b200.options.aug_options import AugOptions
+    base = ['--aug', 'latent', '--synthetic', '--img_resolution', '128', '--synthetic_channels', '2', '--synthetic_channel_base', '8192',
+            '--synthetic_channel_max', '64', '--synthetic_bank', '16', '--synthetic_img_bank', '5', '--synthetic_codes', '32']
+    if tmp_path is not None:
+        base += ['--checkpoints_dir', str(tmp_path)]
+    opt = AugOptions().parse(args=dict({'p_thres': 0.0, 'init_w': 'inv'}, **args), argv=base + argv)
+    aug = create_augment(opt)
+    aug.device = torch.device('cpu')          # the caller-side device of the stand-in run
+    aug._sync_forward = False
+    return aug, opt
+
+
+def _batch(aug, n, start=0):
+    names = list(aug.stats_dataset_w.index)[start:start + n]
+    return {'A': torch.zeros(n, 1, 128, 128), 'B': torch.zeros(n, 1, 128, 128), 'A_paths': names, 'B_paths': names}
+
+
+def test_all_four_criteria_attach_and_batch_order_over_two_gpus_and_micro_batches(fake_engine):
+    aug, opt = _make(['--batch_size', '8', '--gpu_ids_aug', '0,1', '--micro_batches', '2', '--opt_num_epochs', '3', '--no_log'],
+                     {'w_disc': 0.0, 'w_lpips': 2.0, 'w_pix': 0.5, 'w_latent': 0.25})
+    engs = fake_engine.instances
+    assert [e.requested_device for e in engs] == ['cuda:0', 'cuda:0', 'cuda:1', 'cuda:1'] and all(e.batch == 2 for e in engs)
+    for e in engs:
+        kinds = [c[0] for c in e.calls]
+        assert kinds[:2] == ['latent_bank', 'image_bank'] and 'lpips' in kinds and 'feature_bank' in kinds
+        assert ('lpips', (4, 9, 16, 23, 30), 64) in e.calls                      # --lpips_script default: the five-tap form
+        assert ('feature_bank', (5, 2, 64, 64)) in e.calls
+    data = _batch(aug, 8)
+    aug.set_input(data)
+    aug.forward()
+    out = aug.get_output()
+    core = aug.latent_aug.module
+    w_in = aug.w_AB                                                               # [8, 1, w_dim] as sampled from the table
+    assert torch.equal(w_in[:, 0], core.stats_dataset_w.codes[:8])
+    # part p of engine p comes back in position p: images carry w0[i, 0, 0]
+    assert torch.equal(out['A'][:, 0, 0, 0], w_in[:, 0, 0]) and torch.equal(out['B'][:, 0, 0, 0], w_in[:, 0, 0])
+    assert aug.w_AB_aug.shape == (8, core.num_ws, core.w_dim) and torch.equal(aug.w_AB_aug[:, 3], w_in[:, 0] + 1.0)
+    # micro-batches: a part's means run over batch / (world * micro) samples -> pair-MEAN terms get weight / micro
+    kw = [c[1] for c in engs[0].calls if c[0] == 'augment'][0]
+    assert kw['w_latent'] == pytest.approx(0.125) and kw['w_pix'] == pytest.approx(0.25) and kw['w_lpips'] == pytest.approx(1.0)
+    assert kw['num_steps'] == 3 and kw['lpips_norm_mode'] == 0 and kw['final_noise_mode'] == 'random' and kw['soft_aug'] is False
+    # every part got the SAME crop window (drawn once per forward call, util_latent_aug.py:216)
+    crops = {tuple(c[1]['lpips_crop']) for e in engs for c in e.calls if c[0] == 'augment'}
+    assert len(crops) == 1
+    assert aug.get_latent_output()['w'].shape == (8, core.w_dim) and aug.get_latent_input()['paths'] == data['A_paths']
+
+
+def test_discriminator_term_refuses_micro_batches(fake_engine):
+    with pytest.raises(ValueError):
+        _make(['--batch_size', '4', '--micro_batches', '2', '--no_log'], {'w_lpips': 0.0})        # w_disc stays at its default of 1
+
+
+def test_rand_aug_path(fake_engine):
+    aug, opt = _make(['--batch_size', '4', '--rand_aug', '--no_log'], {'truncation_psi': 0.5})
+    e = fake_engine.instances[0]
+    assert opt.w_pix == opt.w_lpips == opt.w_latent == opt.w_disc == 0.0 and opt.opt_num_epochs == 0
+    assert not any(c[0] in ('image_bank', 'lpips', 'disc') for c in e.calls)
+    torch.manual_seed(3)
+    z = torch.randn([4, aug.z_dim])
+    torch.manual_seed(3)
+    aug.set_input(_batch(aug, 4))
+    aug.forward()
+    out = aug.get_output()
+    assert ('synthesis', 'random', 4) in e.calls and not any(c[0] == 'augment' for c in e.calls)
+    assert torch.allclose(out['A'][:, 0, 0, 0], z[:, 0] * 0.5)                  # G.mapping(z, truncation_psi) -> G.synthesis, :202-205
+    assert aug.get_latent_output()['paths'] == ''
+
+
+def test_first_call_loss_log_and_lookahead_loop(fake_engine, tmp_path):
+    aug, opt = _make(['--batch_size', '4', '--opt_num_epochs', '2', '--verbose_log', 'true'], {'w_lpips': 0.0, 'w_disc': 0.0}, tmp_path)
+    core = aug.latent_aug.module
+    batches = [_batch(aug, 4, 4 * i) for i in range(3)]
+    got = list(aug.iterate(iter(batches)))
+    assert [d['A_paths'] for d, _ in got] == [b['A_paths'] for b in batches]
+    for (d, o), b in zip(got, batches):
+        idx = [core.stats_dataset_w.index[n] for n in b['A_paths']]
+        assert torch.equal(o['A'][:, 0, 0, 0], core.stats_dataset_w.codes[idx][:, 0])
+    # the per-epoch losses of the FIRST call only (reference :278-300), columns (latent, pix, total, disc, lpips)
+    assert sorted(core.stats_loss) == ['epoch_0', 'epoch_1'] and core.verbose_flag is False
+    assert core.stats_loss['epoch_1'] == {'loss_latent': 5.0, 'loss_pix': 6.0, 'loss_lpips': 9.0, 'loss_disc': 8.0, 'loss': 7.0}
+    log = os.path.join(core.save_dir, 'losses.jsonl')
+    assert json.load(open(log)) == core.stats_loss
+    assert len(aug.stats_time) == 3
