@@ -14,13 +14,14 @@ class RecordingEngine:
     """Stands in for ``engine.SynthesisEngine``: same constructor and method signatures, arithmetic that makes the
     sample order visible (image i is filled with ``w0[i, 0, 0]``, ``w_aug = w0 + 1``)."""
     instances = []
+    num_ws_of = staticmethod(lambda res: 2 * (res.bit_length() - 1) - 2)
 
     def __init__(self, state, *, img_resolution, img_channels, w_dim=512, z_dim=512, conv_clamp=256.0, batch, precision='fp32_parity',
                  device=None, mapping_lr_multiplier=0.01):
         self.res, self.C, self.w_dim, self.z_dim, self.batch, self.precision = img_resolution, img_channels, w_dim, z_dim, batch, precision
         self.requested_device = device
         self.device = torch.device('cpu')
-        self.num_ws = 2 * (img_resolution.bit_length() - 1) - 2
+        self.num_ws = type(self).num_ws_of(img_resolution)
         self.calls, self.launch_count = [], 0
         RecordingEngine.instances.append(self)
 
@@ -149,3 +150,38 @@ def test_first_call_loss_log_and_lookahead_loop(fake_engine, tmp_path):
     log = os.path.join(core.save_dir, 'losses.jsonl')
     assert json.load(open(log)) == core.stats_loss
     assert len(aug.stats_time) == 3
+
+
+def test_constructor_reads_the_reference_directory_layout(fake_engine, tmp_path, monkeypatch):
+    """``--interim_dir`` pointing at the reference's tree (util_latent_aug.py:133-181): the zips of tests/golden/formats go in as
+    they are -- banks by the slice schedule, inverted codes into the pinned table -- and what reaches the engine is what the
+    REFERENCE's own classes made of the same zips (expected.pt, oracle/make_golden_formats.py)."""
+    import shutil
+
+    from conftest import GOLDEN
+    from latentaugment_b200.augments import create_augment
+    from latentaugment_b200.options.aug_options import AugOptions
+    from latentaugment_b200.utils import synthetic
+    F = os.path.join(GOLDEN, 'formats')
+    expected = torch.load(os.path.join(F, 'expected.pt'), weights_only=True)
+    root = tmp_path / 'interim' / 'Pelvis'
+    os.makedirs(root)
+    shutil.copy(os.path.join(F, 'codes.zip'), root / 'codes-w.zip')
+    shutil.copy(os.path.join(F, 'images.zip'), root / 'imgs.zip')
+    state = synthetic.random_generator_state(img_resolution=8, img_channels=2, w_dim=16, z_dim=16, channel_base=256, channel_max=32)
+    torch.save(state, tmp_path / 'g.pt')
+    monkeypatch.setattr(fake_engine, 'num_ws_of', staticmethod(lambda res: 6))      # the fixture zips hold [6, 16] codes
+    seen = {}
+    monkeypatch.setattr(fake_engine, 'set_latent_bank', lambda self, W: seen.__setitem__('W', W.clone()))
+    monkeypatch.setattr(fake_engine, 'set_image_bank', lambda self, X: seen.__setitem__('X', X.clone()))
+    argv = ['--aug', 'latent', '--batch_size', '2', '--no_log', '--generator_state', str(tmp_path / 'g.pt'), '--img_resolution', '8',
+            '--interim_dir', str(tmp_path / 'interim'), '--dataset_aug', 'Pelvis', '--dataset_w_name', 'codes-w', '--dataset_name_aug', 'imgs',
+            '--step_w', '5', '--step_img', '10', '--checkpoints_dir', str(tmp_path)]
+    opt = AugOptions().parse(args={'p_thres': 0.0, 'init_w': 'inv', 'w_lpips': 0.0, 'w_disc': 0.0}, argv=argv)
+    aug = create_augment(opt)
+    assert torch.equal(seen['W'].cpu(), expected['latent_step5']) and torch.equal(seen['X'].cpu(), expected['img_step10'])
+    assert list(aug.stats_dataset_w.index) == expected['fnames']
+    names = [expected['fnames'][0], expected['fnames'][7]]
+    w = aug.sample_from_inversion(names)
+    assert w.shape == (2, 1, 16) and torch.equal(w[0, 0], expected['w0'][0])
+    assert os.path.isfile(root / 'cache_dir' / 'latent-step_5-maxitems_16.pkl')
