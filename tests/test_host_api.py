@@ -206,3 +206,86 @@ def test_lookahead_loop_passthrough_on_cpu():
         assert data is ref and out['A_paths'] == ref['A_paths']
         assert torch.equal(out['A'], ref['A']) and torch.equal(out['B'], ref['B'])
     assert list(aug.iterate(iter([]))) == []
+
+
+class _CpuBank:
+    """LatentBank stand-in on CPU: exact search of this rank's rows, GLOBAL indices, writes into ``out`` like the real one."""
+
+    def __init__(self, Y, index_offset=0):
+        self.Y, self.K, self.off = Y, Y.shape[1], index_offset
+
+    def nearest(self, X, k=1, out=None):
+        d, i = torch.sort(torch.cdist(X, self.Y).square(), dim=1, stable=True)
+        d, i = d[:, :k].contiguous(), (i[:, :k] + self.off).contiguous()
+        if out is not None:
+            out[0].copy_(d)
+            out[1].copy_(i)
+            return out
+        return d, i
+
+
+class _CpuLib:
+    """The one C-ABI call of ShardedNearest._exchange, executed on host memory: reads the gathered records through the raw
+    pointers / strides it is given (so the record layout and the pointer arithmetic of the caller are what is tested)."""
+
+    @staticmethod
+    def la_merge_topk_strided(d_dist, d_idx, shards, n, k, dist_stride, idx_stride, d_out_dist, d_out_idx, stream):
+        import numpy as np
+        f32 = ctypes.POINTER(ctypes.c_float)
+        i64 = ctypes.POINTER(ctypes.c_longlong)
+        dist = np.ctypeslib.as_array(ctypes.cast(d_dist, f32), shape=((shards - 1) * dist_stride + n * k,))
+        idx = np.ctypeslib.as_array(ctypes.cast(d_idx, i64), shape=((shards - 1) * idx_stride + n * k,))
+        od = np.ctypeslib.as_array(ctypes.cast(d_out_dist, f32), shape=(n * k,))
+        oi = np.ctypeslib.as_array(ctypes.cast(d_out_idx, i64), shape=(n * k,))
+        for q in range(n):
+            cand = sorted((float(dist[s * dist_stride + q * k + t]), int(idx[s * idx_stride + q * k + t])) for s in range(shards) for t in range(k))
+            for t in range(k):
+                od[q * k + t], oi[q * k + t] = cand[t]
+        return 0
+
+
+def _sharded_worker(rank, world, port, q):
+    import contextlib
+
+    import torch.distributed as dist
+
+    from latentaugment_b200 import _lib, engine, parallel
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    # CUDA-only pieces of the class, stubbed: the library call, stream / device plumbing (use_graph=False: no capture)
+    _lib.load = lambda: _CpuLib
+    _lib.check = lambda rc: None
+    engine._stream_ptr = lambda dev: None
+    engine._ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+    torch.cuda.synchronize = lambda *a: None
+    torch.cuda.device = lambda dev: contextlib.nullcontext()
+    gen = torch.Generator().manual_seed(0)
+    Y = torch.randn([96, 16], generator=gen)
+    X = torch.randn([7, 16], generator=gen)
+    b, e = parallel.shard_range(96, rank, world)
+    s = parallel.ShardedNearest(_CpuBank(Y[b:e], b), 7, 3, use_graph=False)
+    d, i = s(X)
+    d2, i2 = s(X.clone())                        # static buffers: a second call gives the same answer
+    dr, ir = torch.sort(torch.cdist(X, Y).square(), dim=1, stable=True)
+    ok = (s.world == world and s.rec_bytes == 7 * 3 * 16 and torch.equal(i, ir[:, :3]) and torch.allclose(d, dr[:, :3])
+          and torch.equal(i2, ir[:, :3]) and i.dtype == torch.int64 and d.dtype == torch.float32)
+    s.close()
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_nearest_class_gloo_world2():
+    """parallel.ShardedNearest under a 2-rank gloo group: local search into the packed (dist | pad | idx) record, ONE
+    all_gather_into_tensor of it, the merge call with the strides / offsets of that record."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
