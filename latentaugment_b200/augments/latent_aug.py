@@ -96,7 +96,7 @@ class LatentAugment(BaseAugment):
         self.verbose_log = opt.verbose_log
         self.stats_time = []
         self._host_out, self._pending, self._pending_src = {}, None, None
-        self._sync_forward = True
+        self._sync_forward, self._passthrough = True, False
         if self.phase == 'train':
             print('\nTrain phase.')
             if self.rand_aug:                                # :126-137
@@ -139,11 +139,14 @@ class LatentAugment(BaseAugment):
     # event only.  With the reference's call order (set_input, forward, get_output) the copy is already in flight
     # when get_output is called; with the look-ahead loop ``iterate()`` the copy of batch t runs while batch t+1
     # computes.  A returned dict stays valid until the next-but-one forward().
-    def _start_d2h(self, t):
+    def _start_d2h(self, t, tag='img'):
+        """-> (host tensor, event or None); ``tag`` separates the staging slots of tensors with equal shapes."""
         if not t.is_cuda:
-            self._pending = (t.detach(), None)
-            return
-        key = (tuple(t.shape), t.dtype, t.device)
+            pending = (t.detach(), None)
+            if tag == 'img':
+                self._pending = pending
+            return pending
+        key = (tag, tuple(t.shape), t.dtype, t.device)
         slot = self._host_out.get(key)
         if slot is None:
             slot = self._host_out[key] = {'buf': [torch.empty(t.shape, dtype=t.dtype).pin_memory() for _ in range(2)], 'i': 0,
@@ -156,7 +159,10 @@ class LatentAugment(BaseAugment):
             slot['buf'][i].copy_(t.detach(), non_blocking=True)
             slot['ev'][i].record(cs)
         t.record_stream(cs)
-        self._pending = (slot['buf'][i], slot['ev'][i])
+        pending = (slot['buf'][i], slot['ev'][i])
+        if tag == 'img':
+            self._pending = pending
+        return pending
 
     def _host_output(self):
         if self._pending is None or self._pending_src is not self.real_AB_aug:
@@ -187,6 +193,7 @@ class LatentAugment(BaseAugment):
     def forward(self):
         since = time.time()
         if random.random() > self.p_thres and self.phase == 'train':
+            self._passthrough = False
             if self.rand_aug:
                 w_AB = self.sample_from_randn().to(self.device)
                 self.real_AB_aug, self.w_AB_aug = self.latent_aug.module.forward_ganrand(w_AB)
@@ -208,6 +215,7 @@ class LatentAugment(BaseAugment):
             if self.verbose_log:
                 print('Augmentation completed in {:.0f}m {:.3f}s'.format(time_elapsed // 60, time_elapsed % 60))
         else:
+            self._passthrough = True
             self.real_AB_aug = torch.cat((self.real_A, self.real_B), dim=1)
             self._pending, self._pending_src = (self.real_AB_aug, None), self.real_AB_aug
             time_elapsed = time.time() - since
@@ -215,11 +223,14 @@ class LatentAugment(BaseAugment):
                 print('No augmentation, time {:.0f}m {:.3f}s'.format(time_elapsed // 60, time_elapsed % 60))
         self.stats_time.append(time_elapsed)
 
-    def iterate(self, loader):
+    def iterate(self, loader, with_latents=False):
         """Look-ahead form of the caller loop (reference backbone_latentaug.py:91-124: ``for data in dataset:
         set_input; forward; get_output; <write>``): yields ``(data, output_dict)`` per batch with the forward of batch
         t+1 ENQUEUED before the output of batch t is awaited, so the device->host copy and the caller's work on batch
-        t (pickling, disk writes) overlap the next batch's kernels.  Same values as the three-call sequence."""
+        t (pickling, disk writes) overlap the next batch's kernels.  Same values as the three-call sequence.
+        ``with_latents``: yields ``(data, output_dict, get_latent_input() dict, get_latent_output() dict)`` of that batch --
+        the two latent tensors travel on the copy stream too (calling ``get_latent_*`` inside the loop would read batch
+        t+1's codes and wait for its kernels)."""
         prev = None
         self._sync_forward = False
         try:
@@ -227,13 +238,37 @@ class LatentAugment(BaseAugment):
                 self.set_input(data)
                 self.forward()
                 cur = (data, self._pending, self.fname)
+                if with_latents:
+                    cur += (self._latents_d2h(),)
                 if prev is not None:
-                    yield prev[0], self._finish(prev)
+                    yield self._yield(prev, with_latents)
                 prev = cur
             if prev is not None:
-                yield prev[0], self._finish(prev)
+                yield self._yield(prev, with_latents)
         finally:
             self._sync_forward = True
+
+    def _latents_d2h(self):
+        """Async copies of this batch's input / augmented codes (``None`` on the pass-through branch, where the reference's
+        ``get_latent_*`` would read stale or missing attributes)."""
+        if self._passthrough:
+            return None
+        return (self._start_d2h(self.w_AB, 'w_in'), self._start_d2h(reverse_broadcasting(self.w_AB_aug).contiguous(), 'w_aug'))
+
+    def _yield(self, item, with_latents):
+        out = self._finish(item[:3])
+        if not with_latents:
+            return item[0], out
+        lat, fname = item[3], item[2]
+        if lat is None:
+            return item[0], out, None, None
+        host = []
+        for buf, ev in lat:
+            if ev is not None:
+                ev.synchronize()
+            host.append(buf.numpy().squeeze().copy())          # owned, like the reference's .cpu().numpy()
+        paths = fname if not self.rand_aug else ''
+        return item[0], out, {'w': host[0], 'paths': paths}, {'w': host[1], 'paths': paths}
 
     def _finish(self, item):
         _, (buf, ev), fname = item

@@ -185,3 +185,56 @@ def test_constructor_reads_the_reference_directory_layout(fake_engine, tmp_path,
     w = aug.sample_from_inversion(names)
     assert w.shape == (2, 1, 16) and torch.equal(w[0, 0], expected['w0'][0])
     assert os.path.isfile(root / 'cache_dir' / 'latent-step_5-maxitems_16.pkl')
+
+
+def test_caller_loop_with_async_writer_matches_the_sequential_calls(fake_engine, tmp_path):
+    """``util_io.augment_dataset`` (look-ahead loop + asynchronous pickle writer) leaves the files of the reference's inner
+    loop (backbone_latentaug.py:91-124): same names, same dict layouts, same values as set_input / forward / get_output /
+    get_latent_* called in sequence."""
+    import numpy as np
+
+    from latentaugment_b200.augments.utils import util_io
+    aug, opt = _make(['--batch_size', '4', '--opt_num_epochs', '2', '--no_log'], {'w_lpips': 0.0, 'w_disc': 0.0})
+    batches = [_batch(aug, 4, 4 * i) for i in range(5)]
+    seq = []
+    for b in batches[:3]:
+        aug.set_input(b)
+        aug.forward()
+        o = aug.get_output()
+        li, lo = aug.get_latent_input(), aug.get_latent_output()
+        # (copies: with the stand-in engine everything stays on the CPU, so these are views of the code table's two staging buffers)
+        seq.append(({k: (v.clone() if torch.is_tensor(v) else v) for k, v in o.items()}, dict(li, w=li['w'].copy()), dict(lo, w=lo['w'].copy())))
+    out = tmp_path / 'run'
+    for d in ('img', 'latent', 'img_aug'):                 # no latent_aug directory: that file is skipped, as in the reference
+        os.makedirs(out / d)
+    n = util_io.augment_dataset(aug, batches, str(out), n_iter=3, verbose=False)
+    assert n == 3
+    assert sorted(os.listdir(out / 'img')) == ['img_0', 'img_1', 'img_2'] and sorted(os.listdir(out / 'latent')) == ['w_0', 'w_1', 'w_2']
+    assert sorted(os.listdir(out / 'img_aug')) == ['img_aug_0', 'img_aug_1', 'img_aug_2'] and not os.path.exists(out / 'latent_aug')
+    for i in range(3):
+        data = util_io.read_pickle(out / 'img' / f'img_{i}')
+        assert data['A_paths'] == batches[i]['A_paths'] and torch.equal(data['A'], batches[i]['A'])
+        got = util_io.read_pickle(out / 'img_aug' / f'img_aug_{i}')
+        assert sorted(got) == ['A', 'A_paths', 'B', 'B_paths'] and got['A_paths'] == seq[i][0]['A_paths']
+        assert torch.equal(got['A'], seq[i][0]['A']) and torch.equal(got['B'], seq[i][0]['B']) and got['A'].shape == (4, 1, 128, 128)
+        w = util_io.read_pickle(out / 'latent' / f'w_{i}')
+        assert isinstance(w['w'], np.ndarray) and w['w'].shape == seq[i][1]['w'].shape and np.array_equal(w['w'], seq[i][1]['w'])
+        assert w['paths'] == seq[i][1]['paths']
+    # augmented codes through the loop == get_latent_output of the sequential calls
+    lat = [(wi, wo) for _, _, wi, wo in aug.iterate(iter(batches[:3]), with_latents=True)]
+    for i in range(3):
+        assert np.array_equal(lat[i][1]['w'], seq[i][2]['w']) and lat[i][1]['w'].shape == (4, aug.w_dim)
+
+
+def test_async_writer_reports_errors_and_bounds_its_queue(tmp_path):
+    from latentaugment_b200.augments.utils import util_io
+    w = util_io.AsyncPickleWriter(max_pending=2)
+    x = torch.arange(6.0)
+    w.submit({'x': x}, str(tmp_path / 'a'))
+    x += 1                                               # the writer owns a copy: later changes of the staging buffer do not leak
+    w.close()
+    assert torch.equal(util_io.read_pickle(tmp_path / 'a')['x'], torch.arange(6.0)) and w.written == 1
+    w = util_io.AsyncPickleWriter()
+    w.submit({'x': 1}, str(tmp_path / 'no_such_dir' / 'b'))
+    with pytest.raises(OSError):
+        w.close()
