@@ -59,6 +59,43 @@ def feature_bank_crops(X, res, crop_size, preprocess='center_random_crop'):
     return out
 
 
+def reference_network_pickle_path(opt):
+    """The reference's own location of the network pickle (``load_stylegan``, util_latent_aug.py:466-472):
+    ``{model_dir}/{dataset_aug}/training-runs/{dataset_name_aug}/{modalities_aug}/<the one run whose name contains
+    exp_stylegan>/{network_pkl_stylegan}``; ``None`` when ``--model_dir`` is unset or the tree does not exist."""
+    model_dir = getattr(opt, 'model_dir', '')
+    if not model_dir:
+        return None
+    dir_model = os.path.join(model_dir, opt.dataset_aug, 'training-runs', opt.dataset_name_aug, str(opt.modalities_aug))
+    if not os.path.isdir(dir_model):
+        return None
+    runs = [x for x in os.listdir(dir_model) if opt.exp_stylegan in x]
+    assert len(runs) == 1, f'{len(runs)} runs under {dir_model} match exp_stylegan={opt.exp_stylegan!r}: exactly one expected'
+    return os.path.join(dir_model, runs[0], opt.network_pkl_stylegan)
+
+
+def load_stylegan_states(path):
+    """``G_ema`` / ``D`` of a reference network pickle as plain ``state_dict``s (:473-484 keeps the modules; the engine reads
+    parameters only).  The pickles embed the source of their classes and need the reference's ``torch_utils`` / ``dnnlib``
+    importable (``torch_utils/persistence.py:118-227``) -- true inside the reference's code base, which is where this
+    plugin is dropped in; elsewhere convert once with ``tools/export_reference_pickle.py``.  Plain ``pickle.load`` as in the
+    reference: only open files you trust."""
+    import pickle
+    print(f'Loading stylegan from "{path}"...')
+    try:
+        with open(path, 'rb') as f:
+            nets = pickle.load(f)
+    except ModuleNotFoundError as exc:
+        raise ModuleNotFoundError(
+            f'{exc}: the network pickle needs the reference\'s models/stylegan3 (torch_utils, dnnlib) on sys.path; or convert it '
+            'once with tools/export_reference_pickle.py and pass --generator_state / --discriminator_state') from exc
+
+    def sd(net):
+        return {k: v.detach().cpu().float() for k, v in net.state_dict().items()}
+    print('Done.')
+    return sd(nets['G_ema']), (sd(nets['D']) if 'D' in nets else None)
+
+
 class InvertedCodeTable:
     """Preloaded table of inverted codes keyed by sample file name: replaces the reference's
     per-sample zip read + unpickle in ``sample_from_inversion`` (latent_aug.py:310-324;
@@ -121,17 +158,21 @@ class LatentAug:
         self.module = self
 
         # ---- generator (reference: load_stylegan, :466-484)
+        pickle_disc_state = None
         if generator_state is None:
+            pkl = None if getattr(opt, 'generator_state', '') else reference_network_pickle_path(opt)
             if getattr(opt, 'generator_state', ''):
                 generator_state = torch.load(opt.generator_state, map_location='cpu', weights_only=True)
+            elif pkl is not None:                                    # the reference's own --model_dir tree and pickle
+                generator_state, pickle_disc_state = load_stylegan_states(pkl)
             elif getattr(opt, 'synthetic', False):
                 generator_state = synthetic.random_generator_state(
                     img_resolution=opt.img_resolution, img_channels=opt.synthetic_channels,
                     channel_base=opt.synthetic_channel_base, channel_max=opt.synthetic_channel_max, seed=0)
             else:
                 raise FileNotFoundError(
-                    'no generator given: pass --generator_state <state_dict.pt> (reference names, legacy.py:171-203) '
-                    'or --synthetic; the reference\'s source-embedding pickles need its persistence module')
+                    'no generator given: pass --model_dir <the reference\'s tree holding its network pickle>, --generator_state '
+                    '<state_dict.pt> (reference names, legacy.py:171-203) or --synthetic')
         self.generator_state = generator_state
         kw = synthetic.infer_generator_kwargs(generator_state)
         self.res, self.img_channels = kw['img_resolution'], kw['img_channels']
@@ -192,6 +233,8 @@ class LatentAug:
             disc_state = None
             if getattr(opt, 'discriminator_state', ''):
                 disc_state = torch.load(opt.discriminator_state, map_location='cpu', weights_only=True)
+            elif pickle_disc_state is not None:                      # D of the same pickle, as the reference (:117)
+                disc_state = pickle_disc_state
             elif getattr(opt, 'synthetic', False):
                 disc_state = synthetic.random_discriminator_state(
                     img_resolution=self.res, img_channels=self.img_channels, channel_base=opt.synthetic_channel_base,

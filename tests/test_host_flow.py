@@ -238,3 +238,45 @@ def test_async_writer_reports_errors_and_bounds_its_queue(tmp_path):
     w.submit({'x': 1}, str(tmp_path / 'no_such_dir' / 'b'))
     with pytest.raises(OSError):
         w.close()
+
+
+def test_constructor_loads_the_reference_network_pickle_tree(fake_engine, tmp_path, monkeypatch):
+    """``--model_dir`` laid out as the reference expects (``load_stylegan``, util_latent_aug.py:466-484): the one run directory
+    matching ``--exp_stylegan`` holds a pickle of ``{'G_ema': module, 'D': module}``; G's parameters reach the engine, D's the
+    realism term -- no separate state files."""
+    import pickle
+
+    from latentaugment_b200.augments import create_augment
+    from latentaugment_b200.options.aug_options import AugOptions
+    from oracle import sg2, sg2_disc
+    cfg = dict(img_resolution=16, img_channels=2, channel_base=512, channel_max=32)
+    G = sg2.Generator(**cfg).eval()
+    D = sg2_disc.make_discriminator(**cfg)
+    run = tmp_path / 'models' / 'DS' / 'training-runs' / 'DSname' / 'm0,m1' / '00003-stylegan2-DS-gpus2'
+    os.makedirs(run)
+    os.makedirs(run.parent / '00004-other-run')
+    with open(run / 'network-snapshot-005320.pkl', 'wb') as f:
+        pickle.dump({'G_ema': G, 'D': D, 'G': G}, f)
+    seen = {}
+    monkeypatch.setattr(fake_engine, 'set_discriminator', lambda self, state, **kw: seen.__setitem__('D', state))
+    real_init = fake_engine.__init__
+
+    def init(self, state, **kw):
+        seen['G'] = state
+        real_init(self, state, **kw)
+    monkeypatch.setattr(fake_engine, '__init__', init)
+    argv = ['--aug', 'latent', '--batch_size', '2', '--no_log', '--model_dir', str(tmp_path / 'models'), '--dataset_aug', 'DS',
+            '--dataset_name_aug', 'DSname', '--modalities_aug', 'm0,m1', '--img_resolution', '16', '--checkpoints_dir', str(tmp_path),
+            '--synthetic', '--synthetic_bank', '8', '--synthetic_img_bank', '3', '--synthetic_codes', '8',
+            '--synthetic_channel_base', '512', '--synthetic_channel_max', '32']       # (--synthetic only supplies the banks here)
+    opt = AugOptions().parse(args={'p_thres': 0.0, 'init_w': 'inv', 'w_lpips': 0.0, 'w_disc': 1.0}, argv=argv)
+    aug = create_augment(opt)
+    gs = G.state_dict()
+    assert seen['G'].keys() == gs.keys() and all(torch.equal(seen['G'][k], gs[k].float()) for k in gs)
+    ds = D.state_dict()
+    assert seen['D'].keys() == ds.keys() and all(torch.equal(seen['D'][k], ds[k].float()) for k in ds)
+    assert aug.latent_aug.module.res == 16 and aug.latent_aug.module.img_channels == 2
+    # two runs matching the experiment id: refuse, as the reference's assert does
+    os.makedirs(run.parent / '00003-duplicate')
+    with pytest.raises(AssertionError):
+        create_augment(opt)
