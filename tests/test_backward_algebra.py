@@ -275,3 +275,67 @@ def test_manual_backward_to_w_equals_autograd():
     assert abs(l_lat - float(ll)) < 1e-9 * abs(float(ll)) and abs(l_pix - float(lp)) < 1e-6 * abs(float(lp))
     rel = float((g_w - g_ref).norm() / g_ref.norm())
     assert rel < 1e-5, rel
+
+
+def test_bank_moment_forms_equal_the_pairwise_losses():
+    """DESIGN.md §3.3 / SURVEY.md App. B: the loop keeps only the banks' first and second moments.  Values and gradients of
+    the latent, pixel and perceptual criteria computed from moments (the formulas the kernels implement, in fp64) against
+    autograd through the oracle's pairwise forms."""
+    from oracle import latent_aug as ola
+    from oracle import lpips as olp
+    g = torch.Generator().manual_seed(3)
+    # ---- latent: w_latent * mean_ij |x_i - y_j|^2 / K
+    n, m, nw, K = 5, 37, 6, 16
+    x = torch.randn([n, nw, K], generator=g, dtype=torch.float64, requires_grad=True)
+    Y = torch.randn([m, nw, K], generator=g, dtype=torch.float64)
+    loss = ola.calc_loss_latent(x, Y, 0.7)
+    loss.backward()
+    xf, Yf = x.detach().reshape(n, -1), Y.reshape(m, -1)
+    ybar, y2 = Yf.mean(0), (Yf * Yf).sum(1).mean()
+    val = 0.7 * ((xf * xf).sum(1).mean() - 2.0 * (xf.mean(0) * ybar).sum() + y2) / (nw * K)
+    grad = 0.7 * 2.0 / (n * nw * K) * (xf - ybar)
+    assert abs(float(val - loss.detach())) < 1e-12 * abs(float(loss.detach()))
+    assert torch.allclose(grad.reshape(n, nw, K), x.grad, rtol=1e-12, atol=1e-15)
+    # ---- pixel: per modality over the centre crop, averaged over modalities
+    C, res = 2, 32
+    img = torch.randn([n, C, res, res], generator=g, dtype=torch.float64, requires_grad=True)
+    X = torch.randn([m, C, res, res], generator=g, dtype=torch.float64)
+    loss = ola.calc_loss_pix(ola.center_crop(img, res), ola.center_crop(X, res), 0.3, C)
+    loss.backward()
+    off, size = ola.center_crop_bounds(res)
+    val, grad = 0.0, torch.zeros_like(img)
+    for c in range(C):
+        xc = img.detach()[:, c, off:off + size, off:off + size].reshape(n, -1)
+        bc = X[:, c, off:off + size, off:off + size].reshape(m, -1)
+        val = val + 0.3 * ((xc * xc).sum(1).mean() - 2.0 * (xc.mean(0) * bc.mean(0)).sum() + (bc * bc).sum(1).mean()) / (size * size) / C
+        grad[:, c, off:off + size, off:off + size] = (0.3 * 2.0 / (n * size * size * C) * (xc - bc.mean(0))).reshape(n, size, size)
+    assert abs(float(val - loss.detach())) < 1e-12 * abs(float(loss.detach()))
+    assert torch.allclose(grad, img.grad, rtol=1e-12, atol=1e-15)
+    # ---- perceptual: pair distance sum_taps mean_hw sum_c w_c (n^_x - n^_y)^2 through the bank moments b = mean_j n^_j and
+    # M2 = mean_j sum_c w_c n^_j^2 / hw; gradient w.r.t. the UN-normalised activation through the normalisation pull-back
+    taps = olp.TAPS_INTREE
+    st = {k: v.double() for k, v in olp.random_vgg_state(7, taps).items()}
+    lw = olp.lin_weights(st, taps)
+    acts = [torch.rand([n, c, s, s], generator=g, dtype=torch.float64, requires_grad=True) for c, s in ((256, 4), (512, 2), (512, 1))]
+    bank = [olp.normalize_activation(torch.rand([m, a.shape[1], a.shape[2], a.shape[3]], generator=g, dtype=torch.float64)) for a in acts]
+    for script in (True, False):
+        for a in acts:
+            a.grad = None
+        D = olp.pair_distance([olp.normalize_activation(a) for a in acts], bank, lw)          # [m, n]
+        loss = 2.5 * (D.sum() / (n * m) if script else D.sum() / m)
+        loss.backward()
+        norm = 1.0 / n if script else 1.0                                # per-pair weight after the bank mean: 1/(n m) or 1/m
+        val = 0.0
+        for a, b, w in zip(acts, bank, lw):
+            x = a.detach()
+            hw = x.shape[2] * x.shape[3]
+            wv = w.reshape(1, -1, 1, 1)
+            r = torch.sqrt((x * x).sum(1, keepdim=True))
+            nh = x / (r + 1e-10)
+            bbar = b.mean(0, keepdim=True)
+            m2 = (wv * b * b).sum((1, 2, 3)).mean() / hw
+            val = val + 2.5 * norm * ((wv * (nh * nh - 2.0 * nh * bbar)).sum() / hw + n * m2)
+            seed = 2.5 * norm * (2.0 / hw) * wv * (nh - bbar)                                  # d loss / d n^
+            gx = seed / (r + 1e-10) - x * (seed * x).sum(1, keepdim=True) / (r * (r + 1e-10) ** 2)
+            assert torch.allclose(gx, a.grad, rtol=1e-9, atol=1e-14), script
+        assert abs(float(val - loss.detach())) < 1e-11 * abs(float(loss.detach())), script
