@@ -289,3 +289,66 @@ def test_sharded_nearest_class_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def _generator_desc(res, img_c, cb=32768, cm=512):
+    import math
+
+    from latentaugment_b200 import _lib
+    from latentaugment_b200.utils.synthetic import channels_for
+    d = _lib.GeneratorDesc()
+    d.img_resolution, d.img_channels, d.w_dim, d.z_dim = res, img_c, 512, 512
+    d.num_blocks = int(math.log2(res)) - 1
+    d.conv_clamp = 256.0
+    ch = channels_for(res, cb, cm)
+    for b in range(d.num_blocks):
+        d.channels[b] = ch[4 << b]
+    d.mapping_layers, d.mapping_lr_multiplier = 8, 0.01
+    return d
+
+
+def test_workspace_planners_run_on_the_host_for_the_benchmark_shapes():
+    """The ``*_workspace_bytes`` entry points are pure host planning (no device needed): they accept the shapes of
+    BASELINE.json's configs, scale with the batch, and reject shapes the kernels do not cover."""
+    from latentaugment_b200 import _lib
+    lib = _lib.load()
+    GiB = 2.0 ** 30
+
+    def engine_bytes(d, batch, precision):
+        n = ctypes.c_size_t(0)
+        rc = lib.la_engine_workspace_bytes(ctypes.byref(d), batch, _lib.PRECISION[precision], ctypes.byref(n))
+        return rc, n.value
+    c2 = _generator_desc(256, 3)
+    rc, b32 = engine_bytes(c2, 32, 'bf16')
+    assert rc == 0 and 3.5 * GiB < b32 < 6 * GiB                       # DESIGN.md §2: 4.7 GiB
+    rc, p32 = engine_bytes(c2, 32, 'fp32_parity')
+    assert rc == 0 and 1.7 * b32 < p32 < 2.2 * b32                     # hi + lo planes of every activation-like tensor
+    rc, b16 = engine_bytes(c2, 16, 'bf16')
+    assert rc == 0 and 0.45 * b32 < b16 < 0.6 * b32
+    c3 = _generator_desc(512, 3)
+    rc, big = engine_bytes(c3, 128, 'bf16')
+    assert rc == 0 and 30 * GiB < big < 45 * GiB                       # fits one B200 (180 GB) with room for D and VGG
+    rc, _ = engine_bytes(_generator_desc(128, 1), 4, 'fp32_parity')
+    assert rc == 0
+    bad = _generator_desc(256, 3)
+    bad.channels[3] = 48                                               # channel counts must be multiples of 64
+    assert engine_bytes(bad, 32, 'bf16')[0] != 0 and lib.la_last_error()
+    assert engine_bytes(c2, 0, 'bf16')[0] != 0
+    # nearest-code search: candidate lists (2 per 32 codes per padded query) dominate
+    n = ctypes.c_size_t(0)
+    assert lib.la_nearest_codes_workspace_bytes(1024, 131072, 512, 4, ctypes.byref(n)) == 0
+    cand = 1024 * (131072 // 32) * 2 * 8
+    assert cand <= n.value < cand + 8 * 2 ** 20
+    assert lib.la_nearest_codes_workspace_bytes(1024, 131072, 512, 9, ctypes.byref(n)) != 0        # k <= 8
+    # perceptual term: workspace grows with batch x modalities
+    v = _lib.VggDesc()
+    v.crop_size = 64
+    dummy = ctypes.create_string_buffer(64)                            # planning reads which pointers are set, never what they point to
+    for i in range(_lib.LA_VGG_CONVS):
+        v.d_conv_weight[i] = v.d_conv_bias[i] = ctypes.addressof(dummy)
+    for k in (2, 3, 4):                                                # the in-tree taps relu3_3, relu4_3, relu5_3
+        v.d_lin_weight[k] = ctypes.addressof(dummy)
+    a, b = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    assert lib.la_lpips_workspace_bytes(ctypes.byref(v), 32, 3, _lib.PRECISION['bf16'], ctypes.byref(a)) == 0
+    assert lib.la_lpips_workspace_bytes(ctypes.byref(v), 32, 1, _lib.PRECISION['bf16'], ctypes.byref(b)) == 0
+    assert a.value > b.value > 0
